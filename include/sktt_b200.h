@@ -1,0 +1,250 @@
+/*
+ * sktt_b200.h -- C-ABI of the B200-native ALS/MALS sweep hot path of scikit_tt.
+ *
+ * The reference (PGelss/scikit_tt) is pure Python and has no FFI layer of its own; the boundary
+ * it offers is the Python call surface (sle.als/mals, evp.als, ode.implicit_euler, TT.ortho_*).
+ * Each entry point below therefore cites the reference *Python function* (file:line under
+ * /root/reference) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stubs a
+ * maintainer would add to those functions.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless the name
+ *     ends in _host; tensors are dense, C-contiguous (last index fastest), exactly the layout of
+ *     the reference's numpy cores.
+ *   - dtype: SKTT_F64 (double) or SKTT_C128 (interleaved re,im doubles == numpy complex128).
+ *   - every call is asynchronous on the context's stream unless it returns a value through a
+ *     *_host pointer, in which case it synchronises that stream before returning.
+ *   - return value: 0 ok; <0 argument/usage error; >0 numerical failure (singular pivot, no
+ *     convergence) or CUDA runtime error.  Nothing throws across the ABI; sktt_last_error()
+ *     returns a human-readable message for the last non-zero status of the context.
+ *   - a context is bound to one device and one stream and is used by one host thread at a time.
+ */
+#ifndef SKTT_B200_H
+#define SKTT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sktt_ctx sktt_ctx;
+
+enum { SKTT_F64 = 0, SKTT_C128 = 1 };
+
+/* conjugation mode of the op-stack updates (which copy of the solution core is conjugated) */
+enum {
+    SKTT_CONJ_ROW = 0, /* sle.py:217-219 / :274-276 and evp.py:323-325: conj on the row-side (m) core   */
+    SKTT_CONJ_COL = 1  /* evp.py:281-283 (left stacks of evp.als): conj on the column-side (n) core     */
+};
+
+/* status codes */
+enum {
+    SKTT_OK = 0,
+    SKTT_ERR_ARG = -1,
+    SKTT_ERR_DTYPE = -2,
+    SKTT_ERR_WORKSPACE = -3,
+    SKTT_ERR_SINGULAR = 1,
+    SKTT_ERR_NOCONV = 2,
+    SKTT_ERR_CUDA = 3
+};
+
+/* ------------------------------------------------------------------ context ------------------ */
+int sktt_version(void);
+int sktt_ctx_create(int device, void* cuda_stream, sktt_ctx** out);
+int sktt_ctx_destroy(sktt_ctx* ctx);
+int sktt_ctx_set_stream(sktt_ctx* ctx, void* cuda_stream);
+const char* sktt_last_error(sktt_ctx* ctx);
+/* number of kernel launches issued through this context since creation (bench.py: gpu_launches) */
+int64_t sktt_launch_count(sktt_ctx* ctx);
+/* force a kernel family: 0 auto, 1 SIMT DFMA tiles only, 2 DMMA tensor tiles where legal */
+int sktt_ctx_set_gemm_mode(sktt_ctx* ctx, int mode);
+
+/* ------------------------------------------------------------------ generic contraction ------
+ * C[cm(i) + cn(j)] = alpha * sum_k opA(A[am(i) + ak(k)]) * opB(B[bk(k) + bn(j)]) + beta * C[..]
+ * with two-level index maps off(i) = (i / d) * s_hi + (i % d) * s_lo (element units).  Every
+ * tensordot of the reference (np.tensordot call sites listed in SURVEY.md 8c) is one such call,
+ * executed without the transpose copies numpy makes.                                            */
+typedef struct {
+    int64_t d;
+    int64_t s_hi;
+    int64_t s_lo;
+} sktt_idx2;
+
+int sktt_gemm2(sktt_ctx* ctx, int dtype, int64_t M, int64_t N, int64_t K,
+               const double* alpha, /* 2 doubles (re, im); host */
+               const void* A, sktt_idx2 am, sktt_idx2 ak, int conjA,
+               const void* B, sktt_idx2 bk, sktt_idx2 bn, int conjB,
+               const double* beta, /* 2 doubles; host */
+               void* C, sktt_idx2 cm, sktt_idx2 cn);
+
+/* ------------------------------------------------------------------ interface stacks ---------
+ * Shapes: Lst [r, R, r]; x [r, n, r2] (solution core, col_dims==1 squeezed); A [R, m, n, R2];
+ *         out [r2, R2, r2].  m == n is required by the reference's use of one solution core on
+ *         both sides.  work: device scratch of sktt_stack_op_work(...) elements of dtype.       */
+int64_t sktt_stack_op_work(int64_t r, int64_t R, int64_t m, int64_t n, int64_t r2, int64_t R2);
+
+/* sle.__construct_stack_left_op  (scikit_tt/solvers/sle.py:194-219), conj_mode SKTT_CONJ_ROW
+ * evp.__construct_left_stacks    (scikit_tt/solvers/evp.py:253-288), conj_mode SKTT_CONJ_COL   */
+int sktt_stack_left_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n,
+                       int64_t r2, int64_t R2, const void* Lst, const void* x, const void* A,
+                       void* out, void* work, int conj_mode);
+
+/* sle.__construct_stack_right_op (scikit_tt/solvers/sle.py:250-276)
+ * evp.__construct_right_stacks   (scikit_tt/solvers/evp.py:295-330)
+ * Shapes: Rst [r2, R2, r2]; out [r, R, r].                                                      */
+int sktt_stack_right_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n,
+                        int64_t r2, int64_t R2, const void* Rst, const void* x, const void* A,
+                        void* out, void* work);
+
+/* sle.__construct_stack_left_rhs / _right_rhs (scikit_tt/solvers/sle.py:222-247, :279-305) and
+ * the deflation stacks of evp (scikit_tt/solvers/evp.py:290-292, :332-334).
+ * Shapes: bL [p, r]; b [p, m, p2] (rhs core); x [r, m, r2]; out_left [p2, r2];
+ *         bR [p2, r2]; out_right [p, r].  work: p*m*r2 (left) / p2*m*r (right) elements.         */
+int sktt_stack_left_rhs(sktt_ctx* ctx, int dtype, int64_t p, int64_t r, int64_t m, int64_t p2,
+                        int64_t r2, const void* bL, const void* b, const void* x, void* out,
+                        void* work);
+int sktt_stack_right_rhs(sktt_ctx* ctx, int dtype, int64_t p, int64_t r, int64_t m, int64_t p2,
+                         int64_t r2, const void* bR, const void* b, const void* x, void* out,
+                         void* work);
+
+/* ------------------------------------------------------------------ micro systems ------------
+ * sle.__construct_micro_matrix_als (scikit_tt/solvers/sle.py:308-347), evp.py:359-365:
+ *   Mout[(c,m,c2),(a,n,a2)] = sum_{b,b2} Lst[a,b,c] A[b,m,n,b2] Rst[a2,b2,c2]   (row-major N x N)
+ *   work: r*r*m*n*R2 elements.                                                                  */
+int sktt_micro_matrix_als(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n,
+                          int64_t r2, int64_t R2, const void* Lst, const void* A, const void* Rst,
+                          void* Mout, void* work);
+
+/* matrix-free product with the same micro matrix (SURVEY.md row a4'):
+ *   y[c,m,c2] = sum Lst[a,b,c] v[a,n,a2] A[b,m,n,b2] Rst[a2,b2,c2];  work: sktt_stack_op_work   */
+int sktt_micro_matvec_als(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n,
+                          int64_t r2, int64_t R2, const void* Lst, const void* A, const void* Rst,
+                          const void* v, void* y, void* work);
+
+/* sle.__construct_micro_matrix_mals (scikit_tt/solvers/sle.py:350-390): two-site micro matrix
+ *   Mout[(c,m,m2,c3),(a,n,n2,a3)] = sum Lst[a,b,c] A1[b,m,n,b2] A2[b2,m2,n2,b3] Rst[a3,b3,c3]
+ *   work: sktt_micro_matrix_mals_work elements.                                                 */
+int64_t sktt_micro_matrix_mals_work(int64_t r, int64_t R, int64_t m, int64_t n, int64_t R2,
+                                    int64_t m2, int64_t n2, int64_t R3, int64_t r3);
+int sktt_micro_matrix_mals(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n,
+                           int64_t R2, int64_t m2, int64_t n2, int64_t R3, int64_t r3,
+                           const void* Lst, const void* A1, const void* A2, const void* Rst,
+                           void* Mout, void* work);
+
+/* two-site matrix-free product (matrix-free form); v, y: [r, n, n2, r3]       */
+int64_t sktt_micro_matvec_mals_work(int64_t r, int64_t R, int64_t m, int64_t n, int64_t R2,
+                                    int64_t m2, int64_t n2, int64_t R3, int64_t r3);
+int sktt_micro_matvec_mals(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n,
+                           int64_t R2, int64_t m2, int64_t n2, int64_t R3, int64_t r3,
+                           const void* Lst, const void* A1, const void* A2, const void* Rst,
+                           const void* v, void* y, void* work);
+
+/* sle.__construct_micro_rhs_als (scikit_tt/solvers/sle.py:393-430), evp.py:377-379:
+ *   f[c,m,c2] = sum bL[p,c] b[p,m,p2] bR[p2,c2];  work: r*m*p2 elements                          */
+int sktt_micro_rhs_als(sktt_ctx* ctx, int dtype, int64_t p, int64_t r, int64_t m, int64_t p2,
+                       int64_t r2, const void* bL, const void* b, const void* bR, void* f,
+                       void* work);
+/* sle.__construct_micro_rhs_mals (scikit_tt/solvers/sle.py:433-472):
+ *   f[c,m,m2,c3] = sum bL[p,c] b1[p,m,p2] b2[p2,m2,p3] bR[p3,c3]; work: r*m*p2 + r*m*m2*p3       */
+int sktt_micro_rhs_mals(sktt_ctx* ctx, int dtype, int64_t p, int64_t r, int64_t m, int64_t p2,
+                        int64_t m2, int64_t p3, int64_t r3, const void* bL, const void* b1,
+                        const void* b2, const void* bR, void* f, void* work);
+
+/* evp.__construct_micro_matrices deflation term (scikit_tt/solvers/evp.py:376-381):
+ *   M += shift * t t^H   (t: N vector)                                                          */
+int sktt_rank1_update(sktt_ctx* ctx, int dtype, int64_t N, double shift, const void* t, void* M);
+
+/* ------------------------------------------------------------------ local linear solves ------
+ * np.linalg.solve / scipy.linalg.lu_factor+lu_solve in sle.__update_core_als/_mals
+ * (scikit_tt/solvers/sle.py:505-509, :588-594): blocked right-looking LU with partial (row)
+ * pivoting, row-major N x N matrix overwritten by L\U, pivots in ipiv (device int32[N]);
+ * info_host receives 0 or the 1-based index of an exactly-zero pivot.                           */
+int sktt_lu_factor(sktt_ctx* ctx, int dtype, int64_t N, void* Mat, int32_t* ipiv, int* info_host);
+int sktt_lu_solve(sktt_ctx* ctx, int dtype, int64_t N, int64_t nrhs, const void* LU,
+                  const int32_t* ipiv, void* B /* [N, nrhs] row-major, overwritten */);
+
+/* SPD fast path: lower Cholesky, row-major; info_host = 0 or index of first non-positive pivot  */
+int sktt_chol_factor(sktt_ctx* ctx, int dtype, int64_t N, void* Mat, int* info_host);
+int sktt_chol_solve(sktt_ctx* ctx, int dtype, int64_t N, int64_t nrhs, const void* Lfac, void* B);
+
+/* matrix-free Krylov solves of the ALS micro system M u = f (M as in sktt_micro_matvec_als), used
+ * where the dense N x N micro matrix of sle.py:343-345 cannot exist (C3/C4).
+ * u holds the initial guess on entry.  tol is relative to ||f||_2.  iters_host/relres_host are
+ * written on return.  sites == 1: A2 NULL (one-site); sites == 2: two-site (MALS) operator.
+ * work: sktt_krylov_work(...) elements of dtype.                                                 */
+typedef struct {
+    int sites;              /* 1 (ALS) or 2 (MALS) */
+    int64_t r, R, m, n, R2; /* left rank, operator ranks, mode sizes of site 1                   */
+    int64_t m2, n2, R3;     /* site 2 (ignored for sites == 1; then r3 is the right rank r2)      */
+    int64_t r3;
+    const void* Lst;
+    const void* A1;
+    const void* A2;
+    const void* Rst;
+} sktt_local_op;
+
+int64_t sktt_krylov_work(const sktt_local_op* op, int method, int restart);
+/* method 0: CG (Hermitian positive definite), 1: restarted GMRES(restart)                       */
+int sktt_krylov_solve(sktt_ctx* ctx, int dtype, const sktt_local_op* op, int method, int restart,
+                      const void* f, void* u, double tol, int max_iters, void* work,
+                      int* iters_host, double* relres_host);
+
+/* ------------------------------------------------------------------ orthonormalisation -------
+ * scipy.linalg.qr(mode='economic') in sle.__update_core_als (scikit_tt/solvers/sle.py:517-525):
+ * Householder QR of the row-major m x n matrix A; Q (m x min(m,n), row-major) overwrites the
+ * leading part of Q_out; R (min(m,n) x n) goes to R_out if non-NULL.
+ * work: sktt_qr_work(m, n) elements.                                                            */
+int64_t sktt_qr_work(int64_t m, int64_t n);
+int sktt_qr_left(sktt_ctx* ctx, int dtype, int64_t m, int64_t n, const void* A, void* Q_out,
+                 void* R_out, void* work);
+/* scipy.linalg.rq(mode='economic') in sle.__update_core_als (scikit_tt/solvers/sle.py:533-541):
+ * A (m x n) = R Q with Q (min(m,n) x n) having orthonormal rows.                                 */
+int sktt_rq_right(sktt_ctx* ctx, int dtype, int64_t m, int64_t n, const void* A, void* Q_out,
+                  void* R_out, void* work);
+
+/* scipy.linalg.svd + the truncation rule of sle.__update_core_mals (scikit_tt/solvers/sle.py:
+ * 603-614, :626-639), TT.ortho_left/ortho_right (scikit_tt/tensor_train.py:1162-1182, :1268-1288)
+ * and utils.truncated_svd (scikit_tt/utils.py:111-158): one-sided Jacobi SVD of the row-major
+ * m x n matrix A; U (m x k), S (k doubles), Vh (k x n), k = min(m,n), all row-major.
+ * Rank rule: keep s_i / s_0 > threshold (strict; skipped when threshold == 0), then at most
+ * max_rank (<= 0 means unbounded).  new_rank_host receives the kept rank.
+ * work: sktt_svd_work(m, n) elements.                                                           */
+int64_t sktt_svd_work(int64_t m, int64_t n);
+int sktt_svd_truncate(sktt_ctx* ctx, int dtype, int64_t m, int64_t n, const void* A, void* U,
+                      double* S, void* Vh, double threshold, int64_t max_rank, void* work,
+                      int* new_rank_host, int* sweeps_host);
+
+/* ------------------------------------------------------------------ local eigen solves -------
+ * scipy.linalg.eigh(subset_by_index=largest k) in evp.__update_core (scikit_tt/solvers/evp.py:
+ * 434-439): cyclic Jacobi on the dense Hermitian N x N micro matrix; eigenvalues ascending in
+ * W (N doubles), eigenvectors in the columns of V (row-major N x N).  Mat is destroyed.          */
+int sktt_eigh_jacobi(sktt_ctx* ctx, int dtype, int64_t N, void* Mat, double* W, void* V,
+                     int* sweeps_host);
+
+/* scipy.linalg.eig / scipy.sparse.linalg.eigs(sigma=...) in evp.__update_core (scikit_tt/solvers/
+ * evp.py:417-432): k eigenpairs closest to sigma of the general N x N matrix Mat (optionally of
+ * the pencil (Mat, Bmat)) by shift-invert Arnoldi on the LU factors of (Mat - sigma Bmat).
+ * dtype is the storage type of Mat; results are always complex128: lam (k complex), vecs
+ * (row-major N x k complex).  v0 == NULL starts from ones (as evp.py:418).
+ * work: sktt_eig_si_work(N, k, ncv) complex128 elements.                                        */
+int64_t sktt_eig_si_work(int64_t N, int64_t k, int64_t ncv);
+int sktt_eig_shift_invert(sktt_ctx* ctx, int dtype, int64_t N, void* Mat, const void* Bmat,
+                          double sigma, int64_t k, int64_t ncv, double tol, int max_restarts,
+                          void* lam, void* vecs, void* work, int* nconv_host);
+
+/* ------------------------------------------------------------------ small helpers ------------ */
+/* out[i] = alpha * x[i] (+ y[i] if y != NULL), n elements */
+int sktt_axpby(sktt_ctx* ctx, int dtype, int64_t n, const double* alpha, const void* x,
+               const double* beta, const void* y, void* out);
+/* ||x||_2 and <x,y> (conjugating x), synchronising */
+int sktt_nrm2(sktt_ctx* ctx, int dtype, int64_t n, const void* x, double* out_host);
+int sktt_dotc(sktt_ctx* ctx, int dtype, int64_t n, const void* x, const void* y,
+              double* out_host /* 2 doubles */);
+/* f64 -> c128 widening and back (real part) */
+int sktt_widen(sktt_ctx* ctx, int64_t n, const double* x, void* out_c128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKTT_B200_H */
