@@ -1,0 +1,338 @@
+"""Device context: one sktt_ctx per (process, CUDA device), torch tensors as the memory owner.
+
+PyTorch is plumbing here (device memory, streams, host<->device copies); every arithmetic step of
+the ALS/MALS path goes through the C-ABI of libsktt_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F64, C128, CONJ_ROW, CONJ_COL, Idx2, LocalOp, SkttError
+
+_contexts = {}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def dtype_code(t):
+    if t.dtype == torch.float64:
+        return F64
+    if t.dtype == torch.complex128:
+        return C128
+    raise TypeError(f"scikit_tt_b200 supports float64 and complex128 only, got {t.dtype}")
+
+
+class Device:
+    """Thin object wrapper over the C-ABI; methods mirror include/sktt_b200.h one to one."""
+
+    def __init__(self, index=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("scikit_tt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.index = torch.cuda.current_device() if index is None else int(index)
+        self.device = torch.device("cuda", self.index)
+        with torch.cuda.device(self.index):
+            self.stream = torch.cuda.current_stream()
+        h = C.c_void_p()
+        st = self.lib.sktt_ctx_create(self.index, C.c_void_p(self.stream.cuda_stream), C.byref(h))
+        if st != 0:
+            raise SkttError(st, "sktt_ctx_create failed (is this an sm_100 device?)")
+        self.h = h
+        self._work = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sktt_ctx_destroy(self.h)
+            self.h = None
+
+    def _check(self, st):
+        if st != 0:
+            msg = self.lib.sktt_last_error(self.h)
+            raise SkttError(st, msg.decode() if msg else "")
+
+    def launches(self):
+        return int(self.lib.sktt_launch_count(self.h))
+
+    def set_gemm_mode(self, mode):
+        self._check(self.lib.sktt_ctx_set_gemm_mode(self.h, int(mode)))
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)
+
+    def work(self, n, dtype, tag="w"):
+        """Reusable scratch tensor of at least n elements."""
+        key = (tag, dtype)
+        t = self._work.get(key)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(int(n), 1024), dtype=dtype, device=self.device)
+            self._work[key] = t
+        return t
+
+    def to_device(self, a, dtype=None):
+        """numpy array -> contiguous device tensor (float64 / complex128)."""
+        a = np.ascontiguousarray(a)
+        if dtype is None:
+            dtype = torch.complex128 if np.iscomplexobj(a) else torch.float64
+        npdt = np.complex128 if dtype == torch.complex128 else np.float64
+        return torch.from_numpy(a.astype(npdt, copy=False)).to(self.device)
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------ stacks
+    def stack_left_op(self, Lst, x, A, conj_mode=CONJ_ROW):
+        r, n, r2 = x.shape
+        R, m, n_, R2 = A.shape
+        out = self.empty((r2, R2, r2), x.dtype)
+        w = self.work(self.lib.sktt_stack_op_work(r, R, m, n, r2, R2), x.dtype)
+        self._check(self.lib.sktt_stack_left_op(self.h, dtype_code(x), r, R, m, n_, r2, R2, _ptr(Lst), _ptr(x), _ptr(A),
+                                                _ptr(out), _ptr(w), conj_mode))
+        return out
+
+    def stack_right_op(self, Rst, x, A):
+        r, n, r2 = x.shape
+        R, m, n_, R2 = A.shape
+        out = self.empty((r, R, r), x.dtype)
+        w = self.work(self.lib.sktt_stack_op_work(r, R, m, n, r2, R2), x.dtype)
+        self._check(self.lib.sktt_stack_right_op(self.h, dtype_code(x), r, R, m, n_, r2, R2, _ptr(Rst), _ptr(x), _ptr(A),
+                                                 _ptr(out), _ptr(w)))
+        return out
+
+    def stack_left_rhs(self, bL, b, x):
+        p, m, p2 = b.shape
+        r, _, r2 = x.shape
+        out = self.empty((p2, r2), x.dtype)
+        w = self.work(r * m * p2, x.dtype)
+        self._check(self.lib.sktt_stack_left_rhs(self.h, dtype_code(x), p, r, m, p2, r2, _ptr(bL), _ptr(b), _ptr(x),
+                                                 _ptr(out), _ptr(w)))
+        return out
+
+    def stack_right_rhs(self, bR, b, x):
+        p, m, p2 = b.shape
+        r, _, r2 = x.shape
+        out = self.empty((p, r), x.dtype)
+        w = self.work(r * m * p2, x.dtype)
+        self._check(self.lib.sktt_stack_right_rhs(self.h, dtype_code(x), p, r, m, p2, r2, _ptr(bR), _ptr(b), _ptr(x),
+                                                  _ptr(out), _ptr(w)))
+        return out
+
+    # ------------------------------------------------------------------ micro systems
+    def micro_matrix_als(self, Lst, A, Rst):
+        r = Lst.shape[0]
+        r2 = Rst.shape[0]
+        R, m, n, R2 = A.shape
+        out = self.empty((r * m * r2, r * n * r2), A.dtype)
+        w = self.work(R * m * n * r2 * r2, A.dtype)
+        self._check(self.lib.sktt_micro_matrix_als(self.h, dtype_code(A), r, R, m, n, r2, R2, _ptr(Lst), _ptr(A),
+                                                   _ptr(Rst), _ptr(out), _ptr(w)))
+        return out
+
+    def micro_matvec_als(self, Lst, A, Rst, v):
+        r = Lst.shape[0]
+        r2 = Rst.shape[0]
+        R, m, n, R2 = A.shape
+        y = self.empty((r, m, r2), v.dtype)
+        w = self.work(self.lib.sktt_stack_op_work(r, R, m, n, r2, R2), v.dtype)
+        self._check(self.lib.sktt_micro_matvec_als(self.h, dtype_code(v), r, R, m, n, r2, R2, _ptr(Lst), _ptr(A),
+                                                   _ptr(Rst), _ptr(v), _ptr(y), _ptr(w)))
+        return y
+
+    def micro_matrix_mals(self, Lst, A1, A2, Rst):
+        r = Lst.shape[0]
+        r3 = Rst.shape[0]
+        R, m, n, R2 = A1.shape
+        _, m2, n2, R3 = A2.shape
+        out = self.empty((r * m * m2 * r3, r * n * n2 * r3), A1.dtype)
+        w = self.work(self.lib.sktt_micro_matrix_mals_work(r, R, m, n, R2, m2, n2, R3, r3), A1.dtype)
+        self._check(self.lib.sktt_micro_matrix_mals(self.h, dtype_code(A1), r, R, m, n, R2, m2, n2, R3, r3, _ptr(Lst),
+                                                    _ptr(A1), _ptr(A2), _ptr(Rst), _ptr(out), _ptr(w)))
+        return out
+
+    def micro_matvec_mals(self, Lst, A1, A2, Rst, v):
+        r = Lst.shape[0]
+        r3 = Rst.shape[0]
+        R, m, n, R2 = A1.shape
+        _, m2, n2, R3 = A2.shape
+        y = self.empty((r, m, m2, r3), v.dtype)
+        w = self.work(self.lib.sktt_micro_matvec_mals_work(r, R, m, n, R2, m2, n2, R3, r3), v.dtype)
+        self._check(self.lib.sktt_micro_matvec_mals(self.h, dtype_code(v), r, R, m, n, R2, m2, n2, R3, r3, _ptr(Lst),
+                                                    _ptr(A1), _ptr(A2), _ptr(Rst), _ptr(v), _ptr(y), _ptr(w)))
+        return y
+
+    def micro_rhs_als(self, bL, b, bR):
+        p, m, p2 = b.shape
+        r, r2 = bL.shape[1], bR.shape[1]
+        f = self.empty((r, m, r2), b.dtype)
+        w = self.work(r * m * p2, b.dtype)
+        self._check(self.lib.sktt_micro_rhs_als(self.h, dtype_code(b), p, r, m, p2, r2, _ptr(bL), _ptr(b), _ptr(bR),
+                                                _ptr(f), _ptr(w)))
+        return f
+
+    def micro_rhs_mals(self, bL, b1, b2, bR):
+        p, m, p2 = b1.shape
+        _, m2, p3 = b2.shape
+        r, r3 = bL.shape[1], bR.shape[1]
+        f = self.empty((r, m, m2, r3), b1.dtype)
+        w = self.work(r * m * p2 + r * m * m2 * p3, b1.dtype)
+        self._check(self.lib.sktt_micro_rhs_mals(self.h, dtype_code(b1), p, r, m, p2, m2, p3, r3, _ptr(bL), _ptr(b1),
+                                                 _ptr(b2), _ptr(bR), _ptr(f), _ptr(w)))
+        return f
+
+    def rank1_update(self, M, t, shift):
+        self._check(self.lib.sktt_rank1_update(self.h, dtype_code(M), M.shape[0], float(shift), _ptr(t), _ptr(M)))
+
+    # ------------------------------------------------------------------ dense solves
+    def lu_factor(self, M):
+        """In-place LU of the square row-major matrix M; returns (ipiv tensor, info)."""
+        N = M.shape[0]
+        ipiv = torch.empty(2 * N, dtype=torch.int32, device=self.device)
+        info = C.c_int(0)
+        self._check(self.lib.sktt_lu_factor(self.h, dtype_code(M), N, _ptr(M), _ptr(ipiv), C.byref(info)))
+        return ipiv, info.value
+
+    def lu_solve(self, LU, ipiv, B):
+        """Overwrites B ([N] or [N, nrhs]) with the solution."""
+        N = LU.shape[0]
+        nrhs = 1 if B.dim() == 1 else B.shape[1]
+        self._check(self.lib.sktt_lu_solve(self.h, dtype_code(LU), N, nrhs, _ptr(LU), _ptr(ipiv), _ptr(B)))
+        return B
+
+    def solve(self, M, f):
+        """np.linalg.solve semantics (M destroyed): raises numpy.linalg.LinAlgError when singular."""
+        ipiv, info = self.lu_factor(M)
+        if info != 0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        x = f.reshape(-1).clone()
+        return self.lu_solve(M, ipiv, x)
+
+    def chol_factor(self, M):
+        info = C.c_int(0)
+        self._check(self.lib.sktt_chol_factor(self.h, dtype_code(M), M.shape[0], _ptr(M), C.byref(info)))
+        return info.value
+
+    def chol_solve(self, Lfac, B):
+        N = Lfac.shape[0]
+        nrhs = 1 if B.dim() == 1 else B.shape[1]
+        self._check(self.lib.sktt_chol_solve(self.h, dtype_code(Lfac), N, nrhs, _ptr(Lfac), _ptr(B)))
+        return B
+
+    # ------------------------------------------------------------------ Krylov
+    def local_op(self, Lst, A1, Rst, A2=None):
+        op = LocalOp()
+        op.sites = 1 if A2 is None else 2
+        op.r = Lst.shape[0]
+        op.R, op.m, op.n, op.R2 = A1.shape
+        if A2 is None:
+            op.m2 = op.n2 = 1
+            op.R3 = op.R2
+        else:
+            _, op.m2, op.n2, op.R3 = A2.shape
+        op.r3 = Rst.shape[0]
+        op.Lst, op.A1, op.Rst = Lst.data_ptr(), A1.data_ptr(), Rst.data_ptr()
+        op.A2 = A2.data_ptr() if A2 is not None else None
+        op._keep = (Lst, A1, A2, Rst)
+        return op
+
+    def krylov_solve(self, op, f, u, method="cg", tol=1e-13, max_iters=5000, restart=40):
+        """Solves the micro system matrix-free; u (initial guess) is overwritten. Returns (iters, relres)."""
+        meth = {"cg": 0, "gmres": 1}[method]
+        nwork = self.lib.sktt_krylov_work(C.byref(op), meth, restart)
+        w = self.work(nwork, f.dtype, tag="krylov")
+        iters, relres = C.c_int(0), C.c_double(0.0)
+        st = self.lib.sktt_krylov_solve(self.h, dtype_code(f), C.byref(op), meth, restart, _ptr(f), _ptr(u), float(tol),
+                                        int(max_iters), _ptr(w), C.byref(iters), C.byref(relres))
+        return st, iters.value, relres.value
+
+    # ------------------------------------------------------------------ orthonormalisation
+    def qr(self, A, want_r=False):
+        m, n = A.shape
+        k = min(m, n)
+        Q = self.empty((m, k), A.dtype)
+        R = self.empty((k, n), A.dtype) if want_r else None
+        self._check(self.lib.sktt_qr_left(self.h, dtype_code(A), m, n, _ptr(A), _ptr(Q), _ptr(R), C.c_void_p(0)))
+        return (Q, R) if want_r else Q
+
+    def rq(self, A, want_r=False):
+        m, n = A.shape
+        k = min(m, n)
+        Q = self.empty((k, n), A.dtype)
+        R = self.empty((m, k), A.dtype) if want_r else None
+        self._check(self.lib.sktt_rq_right(self.h, dtype_code(A), m, n, _ptr(A), _ptr(Q), _ptr(R), C.c_void_p(0)))
+        return (R, Q) if want_r else Q
+
+    def svd(self, A, threshold=0.0, max_rank=0):
+        """Economic SVD + the reference's rank rule.  Returns (U, S, Vh, rank) untruncated + kept rank."""
+        m, n = A.shape
+        k = min(m, n)
+        U = self.empty((m, k), A.dtype)
+        S = self.empty((k,), torch.float64)
+        Vh = self.empty((k, n), A.dtype)
+        w = self.work(self.lib.sktt_svd_work(m, n), A.dtype, tag="svd")
+        rank, sweeps = C.c_int(0), C.c_int(0)
+        mr = 0 if (max_rank is None or max_rank == np.inf or max_rank <= 0) else int(max_rank)
+        self._check(self.lib.sktt_svd_truncate(self.h, dtype_code(A), m, n, _ptr(A), _ptr(U), _ptr(S), _ptr(Vh),
+                                               float(threshold), mr, _ptr(w), C.byref(rank), C.byref(sweeps)))
+        self.last_svd_sweeps = sweeps.value
+        return U, S, Vh, rank.value
+
+    # ------------------------------------------------------------------ eigen
+    def eigh(self, M):
+        N = M.shape[0]
+        W = self.empty((N,), torch.float64)
+        V = self.empty((N, N), M.dtype)
+        sweeps = C.c_int(0)
+        self._check(self.lib.sktt_eigh_jacobi(self.h, dtype_code(M), N, _ptr(M), _ptr(W), _ptr(V), C.byref(sweeps)))
+        return W, V
+
+    def eig_shift_invert(self, M, sigma, k, B=None, ncv=None, tol=1e-13, max_restarts=20):
+        """k eigenpairs of (M, B) closest to sigma; M is destroyed. Returns (lam[k], vecs[N,k]) complex128."""
+        N = M.shape[0]
+        if ncv is None:
+            ncv = min(N, max(2 * k + 1, 20))
+        ncv = min(int(ncv), 64, N)
+        lam = self.empty((k,), torch.complex128)
+        vecs = self.empty((N, k), torch.complex128)
+        w = self.work(self.lib.sktt_eig_si_work(N, k, ncv), torch.complex128, tag="eig")
+        nconv = C.c_int(0)
+        self._check(self.lib.sktt_eig_shift_invert(self.h, dtype_code(M), N, _ptr(M), _ptr(B), float(sigma), k, ncv,
+                                                   float(tol), int(max_restarts), _ptr(lam), _ptr(vecs), _ptr(w),
+                                                   C.byref(nconv)))
+        self.last_eig_nconv = nconv.value
+        return lam, vecs
+
+    # ------------------------------------------------------------------ misc
+    def gemm2(self, M, N, K, A, am, ak, B, bk, bn, Cmat, cm, cn, conjA=0, conjB=0, alpha=(1.0, 0.0), beta=(0.0, 0.0)):
+        al = (C.c_double * 2)(*alpha)
+        be = (C.c_double * 2)(*beta)
+        mk = lambda t: Idx2(*t)
+        self._check(self.lib.sktt_gemm2(self.h, dtype_code(A), M, N, K, al, _ptr(A), mk(am), mk(ak), conjA, _ptr(B),
+                                        mk(bk), mk(bn), conjB, be, _ptr(Cmat), mk(cm), mk(cn)))
+
+    def nrm2(self, x):
+        out = C.c_double(0.0)
+        self._check(self.lib.sktt_nrm2(self.h, dtype_code(x), x.numel(), _ptr(x), C.byref(out)))
+        return out.value
+
+
+def get_device(index=None):
+    """Per-process cache of Device objects keyed by CUDA device index."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("scikit_tt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    idx = torch.cuda.current_device() if index is None else int(index)
+    dev = _contexts.get(idx)
+    if dev is None:
+        dev = Device(idx)
+        _contexts[idx] = dev
+    else:
+        # follow torch's current stream
+        with torch.cuda.device(idx):
+            s = torch.cuda.current_stream()
+        if s.cuda_stream != dev.stream.cuda_stream:
+            dev.stream = s
+            dev.lib.sktt_ctx_set_stream(dev.h, C.c_void_p(s.cuda_stream))
+    return dev

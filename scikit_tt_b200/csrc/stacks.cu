@@ -1,0 +1,306 @@
+// stacks.cu -- interface stacks, micro matrices, matrix-free micro-matvecs and micro right-hand
+// sides of the ALS/MALS sweeps, expressed as chains of two-level strided contractions (gemm.cu)
+// whose intermediates stay in L2.  Index names follow SURVEY.md section 3:
+//   a, c : left solution rank (column side / row side)      a2, c2 : right solution rank
+//   b, b2: operator ranks                                    n, m   : column / row mode index
+#include "common.cuh"
+
+static inline Idx2 two(long long d, long long s_hi, long long s_lo) { return mk_idx(d, s_hi, s_lo); }
+
+extern "C" int64_t sktt_stack_op_work(int64_t r, int64_t R, int64_t m, int64_t n, int64_t r2, int64_t R2) {
+    int64_t t1 = R * r * n * r2, t2 = r * m * r2 * R2;
+    return t1 + t2;
+}
+
+// T1[(b,c),(n,a2)] = sum_a L[a,(b,c)] X[a,(n,a2)]            (first tensordot of sle.py:217)
+static int left_step1(sktt_ctx* ctx, int dtype, long long r, long long R, long long ncols, const void* Lst,
+                      const void* X, int conjX, void* T1) {
+    GemmDesc g = gemm_desc(R * r, ncols, r, Lst, lin_idx(1), lin_idx(R * r), X, lin_idx(ncols), lin_idx(1), T1,
+                           lin_idx(ncols), lin_idx(1));
+    g.conjB = conjX;
+    return sktt_gemm_run(ctx, dtype, g);
+}
+
+// T2[c,m,a2,b2] = sum_{b,n} T1[b,c,n,a2] A[b,m,n,b2]           (second tensordot of sle.py:218)
+static int left_step2(sktt_ctx* ctx, int dtype, long long r, long long R, long long m, long long n, long long r2,
+                      long long R2, const void* T1, const void* A, void* T2) {
+    GemmDesc g = gemm_desc(r * r2, m * R2, R * n, T1, two(r2, n * r2, 1), two(n, r * n * r2, r2), A,
+                           two(n, m * n * R2, R2), two(R2, n * R2, 1), T2, two(r2, m * r2 * R2, R2),
+                           two(R2, r2 * R2, 1));
+    return sktt_gemm_run(ctx, dtype, g);
+}
+
+extern "C" int sktt_stack_left_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n, int64_t r2,
+                                  int64_t R2, const void* Lst, const void* x, const void* A, void* out, void* work,
+                                  int conj_mode) {
+    if (!ctx) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    if (m != n) return sktt_fail(ctx, SKTT_ERR_ARG, "stack_left_op: row and column mode sizes must agree");
+    size_t es = dtype_size(dtype);
+    char* T1 = (char*)work;
+    char* T2 = T1 + (size_t)(R * r * n * r2) * es;
+    const int conj_col = (conj_mode == SKTT_CONJ_COL), conj_row = !conj_col;
+    SKTT_TRY(left_step1(ctx, dtype, r, R, n * r2, Lst, x, conj_col, T1));
+    SKTT_TRY(left_step2(ctx, dtype, r, R, m, n, r2, R2, T1, A, T2));
+    // out[(a2,b2),c2] = sum_{(c,m)} T2[(c,m),(a2,b2)] X2[(c,m),c2]     (third tensordot, sle.py:219)
+    GemmDesc g = gemm_desc(r2 * R2, r2, r * m, T2, lin_idx(1), lin_idx(r2 * R2), x, lin_idx(r2), lin_idx(1), out,
+                           lin_idx(r2), lin_idx(1));
+    g.conjB = conj_row;
+    return sktt_gemm_run(ctx, dtype, g);
+}
+
+extern "C" int sktt_stack_right_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n, int64_t r2,
+                                   int64_t R2, const void* Rst, const void* x, const void* A, void* out, void* work) {
+    if (!ctx) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    if (m != n) return sktt_fail(ctx, SKTT_ERR_ARG, "stack_right_op: row and column mode sizes must agree");
+    size_t es = dtype_size(dtype);
+    char* U1 = (char*)work;                                  // [c, m, a2, b2]
+    char* U2 = U1 + (size_t)(r * m * r2 * R2) * es;          // [n, a2, b, c]
+    // U1[(c,m),(a2,b2)] = sum_c2 conj(x)[(c,m),c2] Rst[(a2,b2),c2]          (sle.py:274)
+    GemmDesc g1 = gemm_desc(r * m, r2 * R2, r2, x, lin_idx(r2), lin_idx(1), Rst, lin_idx(1), lin_idx(r2), U1,
+                            lin_idx(r2 * R2), lin_idx(1));
+    g1.conjA = 1;
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g1));
+    // U2[n,a2,b,c] = sum_{m,b2} A[b,m,n,b2] U1[c,m,a2,b2]                   (sle.py:275)
+    GemmDesc g2 = gemm_desc(R * n, r * r2, m * R2, A, two(n, m * n * R2, R2), two(R2, n * R2, 1), U1,
+                            two(R2, r2 * R2, 1), two(r2, m * r2 * R2, R2), U2, two(n, r, r2 * R * r),
+                            two(r2, 1, R * r));
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g2));
+    // out[a,(b,c)] = sum_{(n,a2)} x[a,(n,a2)] U2[(n,a2),(b,c)]              (sle.py:276)
+    GemmDesc g3 = gemm_desc(r, R * r, n * r2, x, lin_idx(n * r2), lin_idx(1), U2, lin_idx(R * r), lin_idx(1), out,
+                            lin_idx(R * r), lin_idx(1));
+    return sktt_gemm_run(ctx, dtype, g3);
+}
+
+// ---------------------------------------------------------------------------------- rhs stacks --
+extern "C" int sktt_stack_left_rhs(sktt_ctx* ctx, int dtype, int64_t p, int64_t r, int64_t m, int64_t p2, int64_t r2,
+                                   const void* bL, const void* b, const void* x, void* out, void* work) {
+    if (!ctx) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    // Tb[c,(m,p2)] = sum_p bL[p,c] b[p,(m,p2)]                              (sle.py:246)
+    GemmDesc g1 = gemm_desc(r, m * p2, p, bL, lin_idx(1), lin_idx(r), b, lin_idx(m * p2), lin_idx(1), work,
+                            lin_idx(m * p2), lin_idx(1));
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g1));
+    // out[p2,c2] = sum_{(c,m)} Tb[(c,m),p2] conj(x)[(c,m),c2]               (sle.py:247)
+    GemmDesc g2 = gemm_desc(p2, r2, r * m, work, lin_idx(1), lin_idx(p2), x, lin_idx(r2), lin_idx(1), out,
+                            lin_idx(r2), lin_idx(1));
+    g2.conjB = 1;
+    return sktt_gemm_run(ctx, dtype, g2);
+}
+
+extern "C" int sktt_stack_right_rhs(sktt_ctx* ctx, int dtype, int64_t p, int64_t r, int64_t m, int64_t p2,
+                                    int64_t r2, const void* bR, const void* b, const void* x, void* out, void* work) {
+    if (!ctx) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    // Tb[(c,m),p2] = sum_c2 conj(x)[(c,m),c2] bR[p2,c2]                     (sle.py:303)
+    GemmDesc g1 = gemm_desc(r * m, p2, r2, x, lin_idx(r2), lin_idx(1), bR, lin_idx(1), lin_idx(r2), work,
+                            lin_idx(p2), lin_idx(1));
+    g1.conjA = 1;
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g1));
+    // out[p,c] = sum_{(m,p2)} b[p,(m,p2)] Tb[c,(m,p2)]                      (sle.py:304-305)
+    GemmDesc g2 = gemm_desc(p, r, m * p2, b, lin_idx(m * p2), lin_idx(1), work, lin_idx(1), lin_idx(m * p2), out,
+                            lin_idx(r), lin_idx(1));
+    return sktt_gemm_run(ctx, dtype, g2);
+}
+
+// ---------------------------------------------------------------------------------- micro rhs ---
+extern "C" int sktt_micro_rhs_als(sktt_ctx* ctx, int dtype, int64_t p, int64_t r, int64_t m, int64_t p2, int64_t r2,
+                                  const void* bL, const void* b, const void* bR, void* f, void* work) {
+    if (!ctx) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    // Tb[c,(m,p2)] = sum_p bL[p,c] b[p,(m,p2)]                              (sle.py:424)
+    GemmDesc g1 = gemm_desc(r, m * p2, p, bL, lin_idx(1), lin_idx(r), b, lin_idx(m * p2), lin_idx(1), work,
+                            lin_idx(m * p2), lin_idx(1));
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g1));
+    // f[(c,m),c2] = sum_p2 Tb[(c,m),p2] bR[p2,c2]                           (sle.py:425)
+    GemmDesc g2 = gemm_desc(r * m, r2, p2, work, lin_idx(p2), lin_idx(1), bR, lin_idx(r2), lin_idx(1), f,
+                            lin_idx(r2), lin_idx(1));
+    return sktt_gemm_run(ctx, dtype, g2);
+}
+
+extern "C" int sktt_micro_rhs_mals(sktt_ctx* ctx, int dtype, int64_t p, int64_t r, int64_t m, int64_t p2, int64_t m2,
+                                   int64_t p3, int64_t r3, const void* bL, const void* b1, const void* b2,
+                                   const void* bR, void* f, void* work) {
+    if (!ctx) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    size_t es = dtype_size(dtype);
+    char* Tb1 = (char*)work;                       // [c, m, p2]
+    char* Tb2 = Tb1 + (size_t)(r * m * p2) * es;   // [c, m, m2, p3]
+    GemmDesc g1 = gemm_desc(r, m * p2, p, bL, lin_idx(1), lin_idx(r), b1, lin_idx(m * p2), lin_idx(1), Tb1,
+                            lin_idx(m * p2), lin_idx(1));                       // sle.py:464
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g1));
+    GemmDesc g2 = gemm_desc(r * m, m2 * p3, p2, Tb1, lin_idx(p2), lin_idx(1), b2, lin_idx(m2 * p3), lin_idx(1), Tb2,
+                            lin_idx(m2 * p3), lin_idx(1));                      // sle.py:465
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g2));
+    GemmDesc g3 = gemm_desc(r * m * m2, r3, p3, Tb2, lin_idx(p3), lin_idx(1), bR, lin_idx(r3), lin_idx(1), f,
+                            lin_idx(r3), lin_idx(1));                           // sle.py:466
+    return sktt_gemm_run(ctx, dtype, g3);
+}
+
+// ---------------------------------------------------------------------------------- matvecs -----
+extern "C" int sktt_micro_matvec_als(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n, int64_t r2,
+                                     int64_t R2, const void* Lst, const void* A, const void* Rst, const void* v,
+                                     void* y, void* work) {
+    if (!ctx) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    size_t es = dtype_size(dtype);
+    char* T1 = (char*)work;
+    char* T2 = T1 + (size_t)(R * r * n * r2) * es;
+    SKTT_TRY(left_step1(ctx, dtype, r, R, n * r2, Lst, v, 0, T1));
+    SKTT_TRY(left_step2(ctx, dtype, r, R, m, n, r2, R2, T1, A, T2));
+    // y[(c,m),c2] = sum_{(a2,b2)} T2[(c,m),(a2,b2)] Rst[(a2,b2),c2]
+    GemmDesc g = gemm_desc(r * m, r2, r2 * R2, T2, lin_idx(r2 * R2), lin_idx(1), Rst, lin_idx(r2), lin_idx(1), y,
+                           lin_idx(r2), lin_idx(1));
+    return sktt_gemm_run(ctx, dtype, g);
+}
+
+extern "C" int64_t sktt_micro_matvec_mals_work(int64_t r, int64_t R, int64_t m, int64_t n, int64_t R2, int64_t m2,
+                                               int64_t n2, int64_t R3, int64_t r3) {
+    return R * r * n * n2 * r3 + r * m * R2 * n2 * r3 + r * m * m2 * r3 * R3;
+}
+
+extern "C" int sktt_micro_matvec_mals(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n,
+                                      int64_t R2, int64_t m2, int64_t n2, int64_t R3, int64_t r3, const void* Lst,
+                                      const void* A1, const void* A2, const void* Rst, const void* v, void* y,
+                                      void* work) {
+    if (!ctx) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    size_t es = dtype_size(dtype);
+    char* T1 = (char*)work;                                        // [b, c, n, n2, a3]
+    char* T2 = T1 + (size_t)(R * r * n * n2 * r3) * es;            // [c, m, b2, n2, a3]
+    char* T3 = T2 + (size_t)(r * m * R2 * n2 * r3) * es;           // [c, m, m2, a3, b3]
+    SKTT_TRY(left_step1(ctx, dtype, r, R, n * n2 * r3, Lst, v, 0, T1));
+    const long long q = n2 * r3;
+    GemmDesc g2 = gemm_desc(r * q, m * R2, R * n, T1, two(q, n * q, 1), two(n, r * n * q, q), A1,
+                            two(n, m * n * R2, R2), two(R2, n * R2, 1), T2, two(q, m * R2 * q, 1), two(R2, R2 * q, q));
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g2));
+    GemmDesc g3 = gemm_desc(r * m * r3, m2 * R3, R2 * n2, T2, two(r3, R2 * n2 * r3, 1), lin_idx(r3), A2,
+                            two(n2, m2 * n2 * R3, R3), two(R3, n2 * R3, 1), T3, two(r3, m2 * r3 * R3, R3),
+                            two(R3, r3 * R3, 1));
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g3));
+    GemmDesc g4 = gemm_desc(r * m * m2, r3, r3 * R3, T3, lin_idx(r3 * R3), lin_idx(1), Rst, lin_idx(r3), lin_idx(1), y,
+                            lin_idx(r3), lin_idx(1));
+    return sktt_gemm_run(ctx, dtype, g4);
+}
+
+// ---------------------------------------------------------------------------------- micro matrices
+// Mout[(c,mu,c3),(a,nu,a3)] = sum_b L[a,b,c] W[b,mu,nu,a3,c3]; mu = (m,m2), nu = (n,n2) composite mode
+// indices; W is addressed as W[b, m, n, m2, n2, a3, c3] (m2 = n2 = 1 for ALS).
+template <typename T>
+__global__ void micro_expand_kernel(int r, int R, int m, int n, int m2, int n2, int r3, const T* __restrict__ Lst,
+                                    const T* __restrict__ W, T* __restrict__ Mout) {
+    // one CTA per (mu, nu); threads sweep (c, c3, a, a3) with a3 fastest (contiguous in Mout)
+    const int mu = blockIdx.y, nu = blockIdx.x;
+    const int mi = mu / m2, m2i = mu % m2, ni = nu / n2, n2i = nu % n2;
+    const long long ncolmode = (long long)n * n2, nrowmode = (long long)m * m2;
+    const long long Ncol = (long long)r * ncolmode * r3;
+    const long long wstride_b = (long long)m * n * m2 * n2 * r3 * r3;
+    const long long wbase = ((((long long)mi * n + ni) * m2 + m2i) * n2 + n2i) * r3 * r3;
+    extern __shared__ unsigned char smem_raw[];
+    T* Ws = (T*)smem_raw;  // [R][r3*r3] (a3, c3)
+    const int rr3 = r3 * r3;
+    for (int e = threadIdx.x; e < R * rr3; e += blockDim.x) Ws[e] = W[wbase + (long long)(e / rr3) * wstride_b + e % rr3];
+    __syncthreads();
+    const long long total = (long long)r * r * rr3;
+    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+        int a3 = (int)(e % r3);
+        long long t = e / r3;
+        int a = (int)(t % r);
+        t /= r;
+        int c3 = (int)(t % r3);
+        int c = (int)(t / r3);
+        T s = Num<T>::zero();
+        for (int b = 0; b < R; ++b) Num<T>::fma(s, Lst[((long long)a * R + b) * r + c], Ws[b * rr3 + a3 * r3 + c3]);
+        long long row = ((long long)c * nrowmode + mu) * r3 + c3;
+        long long col = ((long long)a * ncolmode + nu) * r3 + a3;
+        Mout[row * Ncol + col] = s;
+    }
+}
+
+template <typename T>
+static int launch_expand(sktt_ctx* ctx, int r, int R, int m, int n, int m2, int n2, int r3, const void* Lst,
+                         const void* W, void* Mout) {
+    size_t smem = (size_t)R * r3 * r3 * sizeof(T);
+    if (smem > 200 * 1024) return sktt_fail(ctx, SKTT_ERR_ARG, "micro_matrix: R*r2^2 tile exceeds shared memory");
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(micro_expand_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(200 * 1024)));
+        configured = 200 * 1024;
+    }
+    dim3 grid(n * n2, m * m2);
+    long long per = (long long)r * r * r3 * r3;
+    int threads = per >= 1024 ? 1024 : (per >= 256 ? 256 : 64);
+    micro_expand_kernel<T><<<grid, threads, smem, ctx->stream>>>(r, R, m, n, m2, n2, r3, (const T*)Lst, (const T*)W,
+                                                                  (T*)Mout);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// W[b,m,n,a2,c2] = sum_b2 A[(b,m,n),b2] Rst[a2,b2,c2]
+static int right_fold(sktt_ctx* ctx, int dtype, long long rows, long long R2, long long r2, const void* A,
+                      const void* Rst, void* W) {
+    GemmDesc g = gemm_desc(rows, r2 * r2, R2, A, lin_idx(R2), lin_idx(1), Rst, lin_idx(r2), two(r2, R2 * r2, 1), W,
+                           lin_idx(r2 * r2), lin_idx(1));
+    return sktt_gemm_run(ctx, dtype, g);
+}
+
+extern "C" int sktt_micro_matrix_als(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n, int64_t r2,
+                                     int64_t R2, const void* Lst, const void* A, const void* Rst, void* Mout,
+                                     void* work) {
+    if (!ctx) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    SKTT_TRY(right_fold(ctx, dtype, R * m * n, R2, r2, A, Rst, work));   // second tensordot of sle.py:340
+    if (dtype == SKTT_F64)                                               // first tensordot + transpose, sle.py:339-345
+        return launch_expand<double>(ctx, (int)r, (int)R, (int)m, (int)n, 1, 1, (int)r2, Lst, work, Mout);
+    return launch_expand<cplx>(ctx, (int)r, (int)R, (int)m, (int)n, 1, 1, (int)r2, Lst, work, Mout);
+}
+
+extern "C" int64_t sktt_micro_matrix_mals_work(int64_t r, int64_t R, int64_t m, int64_t n, int64_t R2, int64_t m2,
+                                               int64_t n2, int64_t R3, int64_t r3) {
+    (void)r;
+    return R2 * m2 * n2 * r3 * r3 + R * m * n * m2 * n2 * r3 * r3;
+}
+
+extern "C" int sktt_micro_matrix_mals(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n,
+                                      int64_t R2, int64_t m2, int64_t n2, int64_t R3, int64_t r3, const void* Lst,
+                                      const void* A1, const void* A2, const void* Rst, void* Mout, void* work) {
+    if (!ctx) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    size_t es = dtype_size(dtype);
+    char* W2 = (char*)work;                                          // [b2, m2, n2, a3, c3]
+    char* V = W2 + (size_t)(R2 * m2 * n2 * r3 * r3) * es;            // [b, m, n, m2, n2, a3, c3]
+    SKTT_TRY(right_fold(ctx, dtype, R2 * m2 * n2, R3, r3, A2, Rst, W2));          // sle.py:383
+    long long ncol = m2 * n2 * r3 * r3;
+    GemmDesc g = gemm_desc(R * m * n, ncol, R2, A1, lin_idx(R2), lin_idx(1), W2, lin_idx(ncol), lin_idx(1), V,
+                           lin_idx(ncol), lin_idx(1));                            // sle.py:382
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g));
+    if (dtype == SKTT_F64)                                                        // sle.py:381, :386-388
+        return launch_expand<double>(ctx, (int)r, (int)R, (int)m, (int)n, (int)m2, (int)n2, (int)r3, Lst, V, Mout);
+    return launch_expand<cplx>(ctx, (int)r, (int)R, (int)m, (int)n, (int)m2, (int)n2, (int)r3, Lst, V, Mout);
+}
+
+// M += shift * t t^H  (evp.py:381)
+template <typename T>
+__global__ void rank1_kernel(long long N, double shift, const T* __restrict__ t, T* __restrict__ M) {
+    long long total = N * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        long long i = e / N, j = e % N;
+        T v = Num<T>::scale(Num<T>::mul(t[i], Num<T>::conj(t[j])), shift);
+        M[e] = Num<T>::add(M[e], v);
+    }
+}
+
+extern "C" int sktt_rank1_update(sktt_ctx* ctx, int dtype, int64_t N, double shift, const void* t, void* M) {
+    if (!ctx) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    long long total = N * N;
+    int blocks = (int)((total + 255) / 256 < 4LL * ctx->sm_count ? (total + 255) / 256 : 4LL * ctx->sm_count);
+    if (blocks < 1) return 0;
+    if (dtype == SKTT_F64) rank1_kernel<double><<<blocks, 256, 0, ctx->stream>>>(N, shift, (const double*)t, (double*)M);
+    else rank1_kernel<cplx><<<blocks, 256, 0, ctx->stream>>>(N, shift, (const cplx*)t, (cplx*)M);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}
