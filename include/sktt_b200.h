@@ -158,7 +158,8 @@ int sktt_rank1_update(sktt_ctx* ctx, int dtype, int64_t N, double shift, const v
 /* ------------------------------------------------------------------ local linear solves ------
  * np.linalg.solve / scipy.linalg.lu_factor+lu_solve in sle.__update_core_als/_mals
  * (scikit_tt/solvers/sle.py:505-509, :588-594): blocked right-looking LU with partial (row)
- * pivoting, row-major N x N matrix overwritten by L\U, pivots in ipiv (device int32[N]);
+ * pivoting, row-major N x N matrix overwritten by L\U; ipiv is device int32[2 N]: the LAPACK-style
+ * pivot rows (0-based) in [0, N), the accumulated row permutation in [N, 2 N);
  * info_host receives 0 or the 1-based index of an exactly-zero pivot.                           */
 int sktt_lu_factor(sktt_ctx* ctx, int dtype, int64_t N, void* Mat, int32_t* ipiv, int* info_host);
 int sktt_lu_solve(sktt_ctx* ctx, int dtype, int64_t N, int64_t nrhs, const void* LU,
@@ -167,6 +168,12 @@ int sktt_lu_solve(sktt_ctx* ctx, int dtype, int64_t N, int64_t nrhs, const void*
 /* SPD fast path: lower Cholesky, row-major; info_host = 0 or index of first non-positive pivot  */
 int sktt_chol_factor(sktt_ctx* ctx, int dtype, int64_t N, void* Mat, int* info_host);
 int sktt_chol_solve(sktt_ctx* ctx, int dtype, int64_t N, int64_t nrhs, const void* Lfac, void* B);
+/* one triangular half of the above: backward == 0 solves L Y = B, backward != 0 solves L^H X = B
+ * (in place, B [N, nrhs] row-major).  Used to reduce the Hermitian-definite pencil of
+ * scipy.linalg.eigh(M, b=B) in evp.__update_core (scikit_tt/solvers/evp.py:434-437) to standard form:
+ * C = L^-1 M L^-H, v = L^-H y.                                                                   */
+int sktt_chol_trsm(sktt_ctx* ctx, int dtype, int64_t N, int64_t nrhs, const void* Lfac, void* B,
+                   int backward);
 
 /* matrix-free Krylov solves of the ALS micro system M u = f (M as in sktt_micro_matvec_als), used
  * where the dense N x N micro matrix of sle.py:343-345 cannot exist (C3/C4).

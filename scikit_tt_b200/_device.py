@@ -221,6 +221,14 @@ class Device:
         self._check(self.lib.sktt_chol_solve(self.h, dtype_code(Lfac), N, nrhs, _ptr(Lfac), _ptr(B)))
         return B
 
+    def chol_trsm(self, Lfac, B, backward=False):
+        """L^-1 B (backward=False) or L^-H B (backward=True); returns a new tensor."""
+        N = Lfac.shape[0]
+        X = B.contiguous().clone()
+        nrhs = 1 if X.dim() == 1 else X.shape[1]
+        self._check(self.lib.sktt_chol_trsm(self.h, dtype_code(Lfac), N, nrhs, _ptr(Lfac), _ptr(X), int(bool(backward))))
+        return X
+
     # ------------------------------------------------------------------ Krylov
     def local_op(self, Lst, A1, Rst, A2=None):
         op = LocalOp()
@@ -237,6 +245,12 @@ class Device:
         op.A2 = A2.data_ptr() if A2 is not None else None
         op._keep = (Lst, A1, A2, Rst)
         return op
+
+    def local_matvec(self, op, v):
+        Lst, A1, A2, Rst = op._keep
+        if A2 is None:
+            return self.micro_matvec_als(Lst, A1, Rst, v)
+        return self.micro_matvec_mals(Lst, A1, A2, Rst, v)
 
     def krylov_solve(self, op, f, u, method="cg", tol=1e-13, max_iters=5000, restart=40):
         """Solves the micro system matrix-free; u (initial guess) is overwritten. Returns (iters, relres)."""
@@ -313,10 +327,46 @@ class Device:
         self._check(self.lib.sktt_gemm2(self.h, dtype_code(A), M, N, K, al, _ptr(A), mk(am), mk(ak), conjA, _ptr(B),
                                         mk(bk), mk(bn), conjB, be, _ptr(Cmat), mk(cm), mk(cn)))
 
+    def matmul(self, A, B, opa='N', opb='N', out=None):
+        """op(A) @ op(B) for 2-D row-major device tensors; op in {'N', 'T', 'C'} resolved in the tile loaders."""
+        big = 1 << 40
+        am, ak = ((big, 0, A.shape[1]), (big, 0, 1)) if opa == 'N' else ((big, 0, 1), (big, 0, A.shape[1]))
+        bk, bn = ((big, 0, B.shape[1]), (big, 0, 1)) if opb == 'N' else ((big, 0, 1), (big, 0, B.shape[1]))
+        M, K = (A.shape[0], A.shape[1]) if opa == 'N' else (A.shape[1], A.shape[0])
+        K2, N = (B.shape[0], B.shape[1]) if opb == 'N' else (B.shape[1], B.shape[0])
+        if K != K2:
+            raise ValueError(f"matmul: inner extents differ ({K} vs {K2})")
+        if out is None:
+            out = self.empty((M, N), A.dtype)
+        self.gemm2(M, N, K, A, am, ak, B, bk, bn, out, (big, 0, N), (big, 0, 1), conjA=int(opa == 'C'), conjB=int(opb == 'C'))
+        return out
+
+    def widen(self, x):
+        """float64 -> complex128 copy on the device."""
+        if x.dtype == torch.complex128:
+            return x
+        out = self.empty(x.shape, torch.complex128)
+        self._check(self.lib.sktt_widen(self.h, x.numel(), _ptr(x.contiguous()), _ptr(out)))
+        return out
+
+    def dotc(self, x, y):
+        """sum conj(x) * y (host scalar)."""
+        out = (C.c_double * 2)(0.0, 0.0)
+        self._check(self.lib.sktt_dotc(self.h, dtype_code(x), x.numel(), _ptr(x), _ptr(y), out))
+        return complex(out[0], out[1]) if x.dtype == torch.complex128 else out[0]
+
     def nrm2(self, x):
         out = C.c_double(0.0)
         self._check(self.lib.sktt_nrm2(self.h, dtype_code(x), x.numel(), _ptr(x), C.byref(out)))
         return out.value
+
+
+def common_dtype(*tensors):
+    """Promote a group of device tensors to complex128 if any of them is complex."""
+    if any(t.dtype == torch.complex128 for t in tensors):
+        dev = get_device()
+        return tuple(dev.widen(t) for t in tensors)
+    return tensors
 
 
 def get_device(index=None):

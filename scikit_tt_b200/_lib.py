@@ -54,6 +54,7 @@ SIGNATURES = {
     "sktt_lu_solve": (i32, [vp, i32, i64, i64, vp, vp, vp]),
     "sktt_chol_factor": (i32, [vp, i32, i64, vp, pint]),
     "sktt_chol_solve": (i32, [vp, i32, i64, i64, vp, vp]),
+    "sktt_chol_trsm": (i32, [vp, i32, i64, i64, vp, vp, i32]),
     "sktt_krylov_work": (i64, [C.POINTER(LocalOp), i32, i32]),
     "sktt_krylov_solve": (i32, [vp, i32, C.POINTER(LocalOp), i32, i32, vp, vp, dbl, i32, vp, pint, pdbl]),
     "sktt_qr_work": (i64, [i64, i64]),

@@ -521,10 +521,11 @@ __global__ void chol_subst_diag_kernel(const T* __restrict__ L, int N, int j0, i
     }
 }
 
+// which: 1 forward half (L y = b), 2 backward half (L^H x = y), 3 both
 template <typename T>
-static int chol_solve_impl(sktt_ctx* ctx, int dtype, int N, int nrhs, const T* L, T* B) {
+static int chol_solve_impl(sktt_ctx* ctx, int dtype, int N, int nrhs, const T* L, T* B, int which = 3) {
     // forward: for each block, solve diagonal then B[j1:,:] -= L[j1:, j0:j1] x_blk
-    for (int j0 = 0; j0 < N; j0 += LU_NB) {
+    for (int j0 = 0; (which & 1) && j0 < N; j0 += LU_NB) {
         int nb = N - j0 < LU_NB ? N - j0 : LU_NB;
         chol_subst_diag_kernel<T, false><<<1, 128, 0, ctx->stream>>>(L, N, j0, nb, B, nrhs);
         SKTT_LAUNCH_CHECK(ctx);
@@ -540,7 +541,7 @@ static int chol_solve_impl(sktt_ctx* ctx, int dtype, int N, int nrhs, const T* L
     }
     // backward with L^H: for blocks from the end, solve diagonal then B[:j0,:] -= L[j0:j1, :j0]^H x_blk
     int last = ((N - 1) / LU_NB) * LU_NB;
-    for (int j0 = last; j0 >= 0; j0 -= LU_NB) {
+    for (int j0 = last; (which & 2) && j0 >= 0; j0 -= LU_NB) {
         int nb = N - j0 < LU_NB ? N - j0 : LU_NB;
         chol_subst_diag_kernel<T, true><<<1, 128, 0, ctx->stream>>>(L, N, j0, nb, B, nrhs);
         SKTT_LAUNCH_CHECK(ctx);
@@ -562,4 +563,15 @@ extern "C" int sktt_chol_solve(sktt_ctx* ctx, int dtype, int64_t N, int64_t nrhs
     if (N <= 0 || nrhs <= 0) return sktt_fail(ctx, SKTT_ERR_ARG, "chol_solve: bad extents");
     if (dtype == SKTT_F64) return chol_solve_impl<double>(ctx, dtype, (int)N, (int)nrhs, (const double*)Lfac, (double*)B);
     return chol_solve_impl<cplx>(ctx, dtype, (int)N, (int)nrhs, (const cplx*)Lfac, (cplx*)B);
+}
+
+extern "C" int sktt_chol_trsm(sktt_ctx* ctx, int dtype, int64_t N, int64_t nrhs, const void* Lfac, void* B,
+                              int backward) {
+    if (!ctx || !Lfac || !B) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    if (N <= 0 || nrhs <= 0) return sktt_fail(ctx, SKTT_ERR_ARG, "chol_trsm: bad extents");
+    const int which = backward ? 2 : 1;
+    if (dtype == SKTT_F64)
+        return chol_solve_impl<double>(ctx, dtype, (int)N, (int)nrhs, (const double*)Lfac, (double*)B, which);
+    return chol_solve_impl<cplx>(ctx, dtype, (int)N, (int)nrhs, (const cplx*)Lfac, (cplx*)B, which);
 }

@@ -1,0 +1,133 @@
+"""Alternating linear schemes for A x = b in TT format -- same call surface as
+scikit_tt/solvers/sle.py of PGelss/scikit_tt (`als` :10, `mals` :98), executed on the GPU.
+
+Per micro-step (reference lines in brackets): interface-stack updates [sle.py:194-305] ->
+micro right-hand side [:393-472] -> micro system, either assembled densely and LU-factorised
+exactly as the reference does [:308-390, :505-509, :588-594] or, where that matrix cannot exist,
+applied matrix-free inside CG / GMRES -> Householder QR / RQ of the solved core [:517-541] (ALS) or
+truncated SVD split of the solved super-core [:603-650] (MALS).  All of it runs through the C-ABI of
+libsktt_b200.so; cores and stacks stay in HBM between micro-steps.
+"""
+import numpy as np
+import torch
+
+from .. import _device
+from ..tensor_train import TT
+from . import _local
+
+
+class _State:
+    def __init__(self, operator, initial_guess, right_hand_side):
+        self.dev = dev = _device.get_device()
+        cplx = _local.any_complex(operator, initial_guess, right_hand_side)
+        self.dtype = torch.complex128 if cplx else torch.float64
+        self.d = operator.order
+        self.A = _local.Uploaded(dev, operator, self.dtype, vector=False)
+        self.b = _local.Uploaded(dev, right_hand_side, self.dtype, vector=True)
+        self.x = list(_local.Uploaded(dev, initial_guess, self.dtype, vector=True).cores)   # sle.py:45 (copy)
+        d = self.d
+        self.Lop, self.Rop = [None] * d, [None] * d
+        self.Lrhs, self.Rrhs = [None] * d, [None] * d
+        self.one3 = _local.ones(dev, (1, 1, 1), self.dtype)
+        self.one2 = _local.ones(dev, (1, 1), self.dtype)
+
+    # sle.py:194-247
+    def left(self, i):
+        dev = self.dev
+        if i == 0:
+            self.Lop[i], self.Lrhs[i] = self.one3, self.one2
+        else:
+            self.Lop[i] = dev.stack_left_op(self.Lop[i - 1], self.x[i - 1], self.A[i - 1])
+            self.Lrhs[i] = dev.stack_left_rhs(self.Lrhs[i - 1], self.b[i - 1], self.x[i - 1])
+
+    # sle.py:250-305
+    def right(self, i):
+        dev = self.dev
+        if i == self.d - 1:
+            self.Rop[i], self.Rrhs[i] = self.one3, self.one2
+        else:
+            self.Rop[i] = dev.stack_right_op(self.Rop[i + 1], self.x[i + 1], self.A[i + 1])
+            self.Rrhs[i] = dev.stack_right_rhs(self.Rrhs[i + 1], self.b[i + 1], self.x[i + 1])
+
+    def result(self):
+        return TT(_local.download_vector_cores(self.x))
+
+
+def als(operator, initial_guess, right_hand_side, repeats=1, solver='solve'):
+    """ALS sweeps for operator @ x = right_hand_side (sle.py:10-95).
+
+    solver: 'solve' / 'lu' (reference values; both an LU with partial pivoting here as there) pick the
+    dense path while r*n*r' <= _local.DENSE_LIMIT and the matrix-free path above it; 'dense', 'cg',
+    'gmres' force one.  Returns a new TT; inputs are not modified.
+    """
+    st = _State(operator, initial_guess, right_hand_side)
+    dev, d, x = st.dev, st.d, st.x
+    for i in range(d - 1, -1, -1):                                        # sle.py:54-56
+        st.right(i)
+    for _ in range(repeats):                                              # sle.py:62
+        for i in range(d):                                                # first half sweep, sle.py:65-77
+            st.left(i)
+            if i < d - 1:
+                u, (r, n, r2) = _micro_als(st, i, solver)
+                q = dev.qr(u.reshape(r * n, r2))                          # sle.py:517-525
+                x[i] = q.reshape(r, n, q.shape[1])
+        for i in range(d - 1, -1, -1):                                    # second half sweep, sle.py:80-90
+            st.right(i)
+            u, (r, n, r2) = _micro_als(st, i, solver)
+            if i > 0:
+                q = dev.rq(u.reshape(r, n * r2))                          # sle.py:533-541
+                x[i] = q.reshape(q.shape[0], n, r2)
+            else:
+                x[i] = u.reshape(r, n, r2)                                # sle.py:546
+    return st.result()
+
+
+def _micro_als(st, i, solver):
+    dev = st.dev
+    L, R, A = st.Lop[i], st.Rop[i], st.A[i]
+    f = dev.micro_rhs_als(st.Lrhs[i], st.b[i], st.Rrhs[i])                # sle.py:424-428
+    r, n, r2 = L.shape[0], A.shape[2], R.shape[0]
+    op = dev.local_op(L, A, R)
+    guess = st.x[i] if tuple(st.x[i].shape) == (r, n, r2) else None
+    u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_als(L, A, R), op, f, guess)
+    return u, (r, n, r2)
+
+
+def mals(operator, initial_guess, right_hand_side, repeats=1, solver='solve', threshold=1e-12, max_rank=np.inf):
+    """MALS sweeps (two-site micro systems, truncated-SVD core splitting; sle.py:98-191)."""
+    st = _State(operator, initial_guess, right_hand_side)
+    dev, d, x = st.dev, st.d, st.x
+    for i in range(d - 1, 0, -1):                                         # sle.py:148-151
+        st.right(i)
+    for _ in range(repeats):
+        for i in range(d - 1):                                            # sle.py:160-172
+            st.left(i)
+            if i < d - 2:
+                u, (r, n, n2, r3) = _micro_mals(st, i, solver)
+                U, S, Vh, k = dev.svd(u.reshape(r * n, n2 * r3), threshold=threshold, max_rank=max_rank)   # sle.py:603-614
+                x[i] = U[:, :k].contiguous().reshape(r, n, k)             # sle.py:616-620
+        for i in range(d - 2, -1, -1):                                    # sle.py:175-186
+            st.right(i + 1)
+            u, (r, n, n2, r3) = _micro_mals(st, i, solver)
+            mat = u.reshape(r * n, n2 * r3)
+            U, S, Vh, k = dev.svd(mat, threshold=threshold, max_rank=max_rank)                             # sle.py:626-639
+            vh = Vh[:k, :].contiguous()
+            x[i + 1] = vh.reshape(k, n2, r3)                              # sle.py:645
+            if i == 0:
+                x[i] = dev.matmul(mat, vh, opb='C').reshape(r, n, k)      # U diag(s), sle.py:647-650
+    return st.result()
+
+
+def _micro_mals(st, i, solver):
+    dev = st.dev
+    L, R, A1, A2 = st.Lop[i], st.Rop[i + 1], st.A[i], st.A[i + 1]
+    f = dev.micro_rhs_mals(st.Lrhs[i], st.b[i], st.b[i + 1], st.Rrhs[i + 1])   # sle.py:464-470
+    r, n, n2, r3 = L.shape[0], A1.shape[2], A2.shape[2], R.shape[0]
+    op = dev.local_op(L, A1, R, A2=A2)
+    guess = None
+    xi, xj = st.x[i], st.x[i + 1]
+    if xi.dim() == 3 and xj.dim() == 3 and xi.shape[0] == r and xj.shape[2] == r3 and xi.shape[2] == xj.shape[0] \
+            and r * n * n2 * r3 > _local.DENSE_LIMIT:
+        guess = dev.matmul(xi.reshape(r * n, xi.shape[2]), xj.reshape(xj.shape[0], n2 * r3))
+    u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_mals(L, A1, A2, R), op, f.reshape(r, n, n2, r3), guess)
+    return u, (r, n, n2, r3)

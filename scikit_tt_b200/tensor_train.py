@@ -1,0 +1,372 @@
+"""Tensor-train container with the reference's attribute surface (order / row_dims / col_dims /
+ranks / cores, cores being host numpy arrays of shape r_i x m_i x n_i x r_{i+1}) -- mirrors
+scikit_tt/tensor_train.py:10-267 of PGelss/scikit_tt.
+
+Scope: the orthonormalisation path -- TT.ortho_left / ortho_right / ortho and
+the 2-norm built on it (tensor_train.py:1092-1332, :1408-1427) -- runs on the GPU through the
+C-ABI (QR + one-sided Jacobi SVD with the reference's rank rule, one contraction to push the
+non-orthonormal factor into the neighbouring core).  Everything else in this file is the thin
+host-side algebra needed to *state* problems for the solvers (I - hA, A + B, alpha * A, eye, ones,
+...); that is input construction, not hot path, and stays plain numpy with the reference's
+semantics.
+"""
+import numpy as np
+
+from . import _device
+
+
+def _is_int(v):
+    return isinstance(v, (int, np.integer)) and not isinstance(v, bool)
+
+
+def _rank_list(order, ranks):
+    if isinstance(ranks, list):
+        return ranks
+    return [1] + [ranks] * (order - 1) + [1]
+
+
+class TT(object):
+    """Tensor train / TT operator.  TT(list_of_4d_cores) or TT(full_ndarray) as in the reference
+    (tensor_train.py:149-267); threshold / max_rank trigger an `ortho` pass on construction."""
+
+    def __init__(self, x, threshold=0, max_rank=np.inf, progress=False, string=None):
+        if isinstance(x, list):
+            if not all(isinstance(c, np.ndarray) and c.ndim == 4 for c in x):
+                raise ValueError('List elements must be 4-dimensional arrays.')
+            if not all(x[i].shape[3] == x[i + 1].shape[0] for i in range(len(x) - 1)):
+                raise ValueError('Shapes of list elements do not match.')
+            self.order = len(x)
+            self.row_dims = [c.shape[1] for c in x]
+            self.col_dims = [c.shape[2] for c in x]
+            self.ranks = [c.shape[0] for c in x] + [x[-1].shape[3]]
+            self.cores = x
+            if threshold != 0 or max_rank != np.inf:
+                self.ortho(threshold=threshold, max_rank=max_rank)
+        elif isinstance(x, np.ndarray):
+            if x.ndim % 2 != 0:
+                raise ValueError('Number of dimensions must be a multiple of 2.')
+            self.__init__(_tt_svd(x, threshold, max_rank))
+        else:
+            raise TypeError('Parameter must be either a list of cores or an ndarray.')
+
+    def __repr__(self):
+        return ('\n'
+                'Tensor train with order    = {d}, \n'
+                '                  row_dims = {m}, \n'
+                '                  col_dims = {n}, \n'
+                '                  ranks    = {r}'.format(d=self.order, m=self.row_dims, n=self.col_dims, r=self.ranks))
+
+    # ------------------------------------------------------------------ host algebra (problem statement)
+    def __add__(self, other):
+        if not isinstance(other, TT):
+            raise TypeError('Unsupported parameter.')
+        if self.row_dims != other.row_dims or self.col_dims != other.col_dims:
+            raise ValueError('Tensor trains must have the same dimensions')
+        d = self.order
+        out = []
+        for i in range(d):
+            a, b = self.cores[i], other.cores[i]
+            dt = complex if (np.iscomplexobj(a) or np.iscomplexobj(b)) else float
+            ra, rb = (0, 0) if i == 0 else (a.shape[0], b.shape[0])
+            sa, sb = (0, 0) if i == d - 1 else (a.shape[3], b.shape[3])
+            # boundary ranks stay 1: first core concatenates along the right rank, last along the left
+            c = np.zeros((max(ra + rb, 1), a.shape[1], a.shape[2], max(sa + sb, 1)), dtype=dt)
+            if d == 1:
+                c[...] = a + b
+            elif i == 0:
+                c[:, :, :, :a.shape[3]] = a
+                c[:, :, :, a.shape[3]:] = b
+            elif i == d - 1:
+                c[:a.shape[0]] = a
+                c[a.shape[0]:] = b
+            else:
+                c[:ra, :, :, :sa] = a
+                c[ra:, :, :, sa:] = b
+            out.append(c)
+        return TT(out)
+
+    def __sub__(self, other):
+        return self + (-1) * other
+
+    def __mul__(self, scalar):
+        if not isinstance(scalar, (int, float, complex, np.integer, np.floating, np.complexfloating)):
+            raise TypeError('Unsupported parameter.')
+        t = self.copy()
+        t.cores[0] = scalar * t.cores[0]
+        return t
+
+    def __rmul__(self, scalar):
+        return self * scalar
+
+    def __matmul__(self, other):
+        if not isinstance(other, TT):
+            raise TypeError('Unsupported argument.')
+        if self.col_dims != other.row_dims:
+            raise ValueError('Dimensions do not match.')
+        cores = []
+        for a, b in zip(self.cores, other.cores):
+            c = np.einsum('pmkq,sknt->psmnqt', a, b)
+            cores.append(c.reshape(a.shape[0] * b.shape[0], a.shape[1], b.shape[2], a.shape[3] * b.shape[3]))
+        t = TT(cores)
+        if np.prod(t.row_dims) == 1 and np.prod(t.col_dims) == 1:
+            return t.element([0] * (2 * t.order))
+        return t
+
+    def dot(self, other):
+        return self.__matmul__(other)
+
+    def transpose(self, cores=None, conjugate=False, overwrite=False):
+        which = range(self.order) if cores is None else cores
+        t = self if overwrite else self.copy()
+        for i in which:
+            c = np.transpose(t.cores[i], [0, 2, 1, 3])
+            t.cores[i] = np.conj(c) if conjugate else c
+            t.row_dims[i], t.col_dims[i] = t.col_dims[i], t.row_dims[i]
+        return t
+
+    def conj(self, overwrite=False):
+        t = self if overwrite else self.copy()
+        t.cores = [np.conj(c) for c in t.cores]
+        return t
+
+    def isoperator(self):
+        return not (all(m == 1 for m in self.row_dims) or all(n == 1 for n in self.col_dims))
+
+    def copy(self):
+        return TT([c.copy() for c in self.cores])
+
+    def element(self, indices):
+        if not isinstance(indices, list):
+            raise TypeError('Unsupported parameter.')
+        if len(indices) != 2 * self.order:
+            raise ValueError('Number of indices must be twice the order of the tensor train.')
+        if not all(_is_int(k) for k in indices):
+            raise TypeError('Indices must be integers.')
+        d = self.order
+        v = np.ones((1,))
+        for i in range(d):
+            if not (0 <= indices[i] < self.row_dims[i] and 0 <= indices[d + i] < self.col_dims[i]):
+                raise IndexError('Indices out of range.')
+            v = v @ self.cores[i][:, indices[i], indices[d + i], :]
+        return v[0]
+
+    def full(self):
+        d = self.order
+        t = self.cores[0].reshape(self.row_dims[0], self.col_dims[0], self.ranks[1]) if self.ranks[0] == 1 else None
+        if t is None:
+            raise ValueError('The first rank must be 1.')
+        for c in self.cores[1:]:
+            t = np.tensordot(t, c, axes=(t.ndim - 1, 0))
+        t = t.reshape(t.shape[:-1])
+        perm = [2 * i for i in range(d)] + [2 * i + 1 for i in range(d)]
+        return t.transpose(perm)
+
+    def matricize(self):
+        return self.full().reshape(int(np.prod(self.row_dims)), int(np.prod(self.col_dims)))
+
+    # ------------------------------------------------------------------ orthonormalisation (GPU path)
+    def _check_ortho_args(self, start_index, end_index, threshold, max_rank):
+        if not (_is_int(start_index) and _is_int(end_index)):
+            raise TypeError('Start and end indices must be integers.')
+        if not (isinstance(threshold, (int, float, np.integer, np.floating)) and threshold >= 0):
+            raise ValueError('Threshold must be greater or equal 0.')
+        ok = lambda v: (_is_int(v) and v > 0) or v == np.inf  # noqa: E731
+        if isinstance(max_rank, list):
+            if len(max_rank) == self.order + 1 and not all(ok(v) for v in max_rank):
+                raise ValueError('Maximum rank(s) must be positive integers.')
+            return max_rank
+        if not ok(max_rank):
+            raise ValueError('Maximum rank(s) must be positive integers.')
+        return [1] + [max_rank] * (self.order - 1) + [1]
+
+    def ortho_left(self, start_index=0, end_index=None, threshold=0.0, max_rank=np.inf, progress=False,
+                   string='Left-orthonormalization'):
+        """Left-orthonormalise cores start_index..end_index in place (tensor_train.py:1092-1205): per core
+        SVD of the (r m n) x r' unfolding on the device, rank rule s/s0 > threshold then max_rank, keep U,
+        push diag(s) V into the next core."""
+        if end_index is None:
+            end_index = self.order - 2
+        max_ranks = self._check_ortho_args(start_index, end_index, threshold, max_rank)
+        if end_index < start_index:
+            return self
+        dev = _device.get_device()
+        carry = None                                           # diag(s) V of the previous core, on the device
+        for i in range(start_index, end_index + 1):
+            m, n, r2 = self.row_dims[i], self.col_dims[i], self.ranks[i + 1]
+            mat = dev.to_device(self.cores[i]).reshape(self.ranks[i], m * n * r2)
+            if carry is not None:
+                carry, mat = _device.common_dtype(carry, mat)
+                mat = dev.matmul(carry, mat)
+            r = mat.shape[0]
+            mat = mat.reshape(r * m * n, r2)
+            u, s, vh, k = dev.svd(mat, threshold=threshold, max_rank=max_ranks[i + 1])
+            u = u[:, :k].contiguous()
+            self.cores[i] = _to_host(u).reshape(r, m, n, k)
+            self.ranks[i], self.ranks[i + 1] = r, k
+            carry = dev.matmul(u, mat, opa='C')                # U^H A = diag(s) V restricted to the kept rank
+        shp = self.cores[end_index + 1].shape
+        carry, nxt = _device.common_dtype(carry, dev.to_device(self.cores[end_index + 1]).reshape(shp[0], -1))
+        self.cores[end_index + 1] = _to_host(dev.matmul(carry, nxt)).reshape((carry.shape[0],) + shp[1:])
+        return self
+
+    def ortho_right(self, start_index=None, end_index=1, threshold=0, max_rank=np.inf):
+        """Right-orthonormalise cores start_index..end_index (descending) in place
+        (tensor_train.py:1207-1310): SVD of the r x (m n r') unfolding, keep V, push U diag(s) left."""
+        if start_index is None:
+            start_index = self.order - 1
+        max_ranks = self._check_ortho_args(start_index, end_index, threshold, max_rank)
+        if start_index < end_index:
+            return self
+        dev = _device.get_device()
+        carry = None                                           # U diag(s) of the core to the right
+        for i in range(start_index, end_index - 1, -1):
+            m, n, r = self.row_dims[i], self.col_dims[i], self.ranks[i]
+            mat = dev.to_device(self.cores[i]).reshape(r * m * n, self.ranks[i + 1])
+            if carry is not None:
+                mat, carry = _device.common_dtype(mat, carry)
+                mat = dev.matmul(mat, carry)
+            r2 = mat.shape[1]
+            mat = mat.reshape(r, m * n * r2)
+            u, s, vh, k = dev.svd(mat, threshold=threshold, max_rank=max_ranks[i])
+            vh = vh[:k, :].contiguous()
+            self.cores[i] = _to_host(vh).reshape(k, m, n, r2)
+            self.ranks[i], self.ranks[i + 1] = k, r2
+            carry = dev.matmul(mat, vh, opb='C')               # A V = U diag(s) restricted to the kept rank
+        shp = self.cores[end_index - 1].shape
+        prv, carry = _device.common_dtype(dev.to_device(self.cores[end_index - 1]).reshape(-1, shp[3]), carry)
+        self.cores[end_index - 1] = _to_host(dev.matmul(prv, carry)).reshape(shp[:3] + (carry.shape[1],))
+        return self
+
+    def ortho(self, threshold=0, max_rank=np.inf):
+        """tensor_train.py:1312-1332: left pass without rank cap, right pass with it."""
+        return self.ortho_left(threshold=threshold, max_rank=np.inf).ortho_right(threshold=threshold, max_rank=max_rank)
+
+    def norm(self, p=2):
+        """tensor_train.py:1334-1430.  p=2 goes through ortho_right on the device; p=1 (max column sum /
+        Manhattan norm of a non-negative train) is a product of small host matrices."""
+        if p == 1:
+            t = self.transpose() if all(m == 1 for m in self.row_dims) else self
+            # sum over the row index, then chain the resulting r x n x r' cores column by column
+            mats = [c.sum(axis=1) for c in t.cores]           # [r, n, r']
+            acc = mats[0].reshape(-1, mats[0].shape[2])       # [(n0), r1]  (r0 == 1)
+            for mcore in mats[1:]:
+                acc = np.tensordot(acc, mcore, axes=(1, 0)).reshape(-1, mcore.shape[2])
+            return np.max(acc)
+        if p == 2:
+            t = TT([c.reshape(c.shape[0], c.shape[1] * c.shape[2], 1, c.shape[3]).copy() for c in self.cores])
+            t.ortho_right()
+            return np.linalg.norm(t.cores[0].reshape(-1))
+        raise ValueError('p must be 1 or 2.')
+
+
+def _to_host(t):
+    return t.detach().cpu().numpy()
+
+
+def _tt_svd(x, threshold, max_rank):
+    """TT-SVD of a full array with interleaved (row, col) modes -- constructor path of the reference
+    (tensor_train.py:201-258); host numpy, not on the sweep hot path."""
+    d = x.ndim // 2
+    row_dims, col_dims = x.shape[:d], x.shape[d:]
+    y = np.transpose(x, [d * j + i for i in range(d) for j in range(2)]).copy()
+    cores, r = [], 1
+    for i in range(d - 1):
+        y = y.reshape(r * row_dims[i] * col_dims[i], -1)
+        u, s, v = np.linalg.svd(y, full_matrices=False)
+        if threshold != 0:
+            keep = np.where(s / s[0] > threshold)[0]
+            u, s, v = u[:, keep], s[keep], v[keep, :]
+        if max_rank != np.inf:
+            k = int(min(u.shape[1], max_rank))
+            u, s, v = u[:, :k], s[:k], v[:k, :]
+        cores.append(u.reshape(r, row_dims[i], col_dims[i], u.shape[1]))
+        r = u.shape[1]
+        y = s[:, None] * v
+    cores.append(y.reshape(r, row_dims[-1], col_dims[-1], 1))
+    return cores
+
+
+# ---------------------------------------------------------------------- factories (tensor_train.py:1806-2033)
+def zeros(row_dims, col_dims, ranks=1):
+    rk = _rank_list(len(row_dims), ranks)
+    return TT([np.zeros([rk[i], row_dims[i], col_dims[i], rk[i + 1]]) for i in range(len(row_dims))])
+
+
+def ones(row_dims, col_dims, ranks=1):
+    rk = _rank_list(len(row_dims), ranks)
+    return TT([np.ones([rk[i], row_dims[i], col_dims[i], rk[i + 1]]) for i in range(len(row_dims))])
+
+
+def eye(dims):
+    return TT([np.eye(k).reshape(1, k, k, 1) for k in dims])
+
+
+def unit(dims, inds):
+    t = zeros(dims, [1] * len(dims))
+    for i, j in enumerate(inds):
+        t.cores[i][0, j, 0, 0] = 1
+    return t
+
+
+def rand(row_dims, col_dims, ranks=1):
+    rk = _rank_list(len(row_dims), ranks)
+    return TT([np.random.rand(rk[i], row_dims[i], col_dims[i], rk[i + 1]) for i in range(len(row_dims))])
+
+
+def uniform(row_dims, ranks=1, norm=1):
+    d = len(row_dims)
+    rk = _rank_list(d, ranks)
+    factor = (norm / (np.sqrt(np.prod(row_dims)) * np.prod(rk))) ** (1.0 / d)
+    return TT([factor * np.ones([rk[i], row_dims[i], 1, rk[i + 1]]) for i in range(d)])
+
+
+def build_core(matrix_list, iscomplex=False):
+    """Core from a nested list of matrices (or scalars 0 / 1 standing for zero / identity blocks):
+    entry [i][j] becomes core[i, :, :, j] (tensor_train.py:2144-2263)."""
+    rows = matrix_list if isinstance(matrix_list[0], list) else [matrix_list]
+    shape = None
+    for row in rows:
+        for blk in row:
+            if isinstance(blk, np.ndarray):
+                shape = blk.shape
+    if shape is None:
+        raise ValueError('at least one block must be an array')
+    dt = complex if iscomplex or any(np.iscomplexobj(b) for row in rows for b in row) else float
+    core = np.zeros((len(rows), shape[0], shape[1], len(rows[0])), dtype=dt)
+    for i, row in enumerate(rows):
+        for j, blk in enumerate(row):
+            if isinstance(blk, np.ndarray):
+                core[i, :, :, j] = blk
+            elif blk == 1:
+                core[i, :, :, j] = np.eye(shape[0], shape[1])
+    return core
+
+
+def residual_error(operator, lhs, rhs):
+    """|| A x - b ||_2 evaluated core by core (tensor_train.py:2035-2074) without forming A x as a
+    train: the running factor is re-compressed by a QR-type factorisation at every core.  Host numpy
+    (verification helper either side of the hot path)."""
+    d = operator.order
+    carry = None
+    err = None
+    for i in range(d):
+        A, x, b = operator.cores[i], lhs.cores[i], rhs.cores[i]
+        ax = np.einsum('pmnq,rns->prmqs', A, x[:, :, 0, :]).reshape(A.shape[0] * x.shape[0], A.shape[1], A.shape[3] * x.shape[3])
+        bb = b.reshape(b.shape[0], b.shape[1], b.shape[3])
+        if d == 1:
+            return np.linalg.norm((ax - bb).ravel())
+        if i == 0:
+            core = np.concatenate([ax, -bb], axis=2)
+        elif i == d - 1:
+            core = np.concatenate([ax, bb], axis=0)
+        else:
+            top = np.concatenate([ax, np.zeros(ax.shape[:2] + (bb.shape[2],), dtype=ax.dtype)], axis=2)
+            bot = np.concatenate([np.zeros(bb.shape[:2] + (ax.shape[2],), dtype=ax.dtype), bb], axis=2)
+            core = np.concatenate([top, bot], axis=0)
+        if carry is not None:
+            core = np.tensordot(carry, core, axes=(1, 0))
+        if i == d - 1:
+            err = np.linalg.norm(core.ravel())
+        else:
+            carry = np.linalg.qr(core.reshape(-1, core.shape[2]), mode='r')
+    return err

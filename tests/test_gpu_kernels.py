@@ -1,0 +1,351 @@
+"""GPU: every entry point of the C-ABI (include/sktt_b200.h) against the numpy oracle on seeded inputs.
+
+Tolerances are relative Frobenius-norm errors in fp64; the contraction kernels are held to 1e-13,
+the factorisations to 1e-11 x a mild condition-number allowance written next to each check.
+"""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+import torch
+
+from oracle import kernels as K
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(rng, shape, cplx):
+    a = rng.standard_normal(shape)
+    if cplx:
+        a = a + 1j * rng.standard_normal(shape)
+    return a
+
+
+def relerr(a, ref):
+    ref = np.asarray(ref)
+    a = np.asarray(a)
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    return np.linalg.norm((a - ref).ravel()) / max(np.linalg.norm(ref.ravel()), 1e-300)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------ gemm
+GEMM_SHAPES = [(1, 1, 1), (3, 5, 7), (17, 33, 65), (64, 64, 64), (100, 130, 50), (192, 4096, 64), (4096, 192, 192),
+               (40, 24, 3000), (129, 257, 31)]
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_gemm2_plain_and_strided(dev, cplx, mode):
+    rng = np.random.default_rng(100 + mode + 10 * cplx)
+    dev.set_gemm_mode(mode)
+    try:
+        for (M, N, Kd) in GEMM_SHAPES:
+            A = rnd(rng, (M, Kd), cplx)
+            B = rnd(rng, (Kd, N), cplx)
+            C0 = rnd(rng, (M, N), cplx)
+            dA, dB, dC = dev.to_device(A), dev.to_device(B), dev.to_device(C0)
+            big = 1 << 40
+            # plain row-major, alpha/beta
+            dev.gemm2(M, N, Kd, dA, (big, 0, Kd), (big, 0, 1), dB, (big, 0, N), (big, 0, 1), dC, (big, 0, N), (big, 0, 1),
+                      alpha=(0.5, 0.0), beta=(2.0, 0.0))
+            assert relerr(host(dC), 0.5 * A @ B + 2.0 * C0) < 1e-13, (M, N, Kd)
+            # transposed operands through the strides + conjugation flags
+            dAt, dBt = dev.to_device(A.T.copy()), dev.to_device(B.T.copy())
+            dC2 = dev.empty((M, N), dA.dtype)
+            dev.gemm2(M, N, Kd, dAt, (big, 0, 1), (big, 0, M), dBt, (big, 0, 1), (big, 0, Kd), dC2, (big, 0, N), (big, 0, 1),
+                      conjA=1, conjB=1)
+            assert relerr(host(dC2), np.conj(A) @ np.conj(B)) < 1e-13, (M, N, Kd)
+        # two-level index maps: C[i1,j1,i2,j2] = sum_{k1,k2} A[k1,i1,k2,i2] B[j2,k2,k1,j1]
+        i1, i2, j1, j2, k1, k2 = 5, 7, 3, 6, 4, 9
+        A = rnd(rng, (k1, i1, k2, i2), cplx)
+        B = rnd(rng, (j2, k2, k1, j1), cplx)
+        dA, dB = dev.to_device(A), dev.to_device(B)
+        dC = dev.empty((i1, j1, i2, j2), dA.dtype)
+        dev.gemm2(i1 * i2, j1 * j2, k1 * k2, dA, (i2, k2 * i2, 1), (k2, i1 * k2 * i2, i2),
+                  dB, (k2, j1, k1 * j1), (j2, 1, k2 * k1 * j1), dC, (i2, j1 * i2 * j2, j2), (j2, i2 * j2, 1))
+        ref = np.einsum('aibj,dbac->icjd', A, B)
+        assert relerr(host(dC), ref) < 1e-13
+    finally:
+        dev.set_gemm_mode(0)
+
+
+# ------------------------------------------------------------------------------------------------ stacks
+STACK_SHAPES = [  # r, R, n, r2, R2
+    (1, 1, 3, 2, 2), (3, 2, 4, 5, 3), (4, 4, 64, 4, 4), (8, 21, 3, 8, 21), (16, 3, 16, 16, 3), (64, 3, 64, 64, 3),
+    (7, 5, 9, 1, 1)]
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", STACK_SHAPES)
+def test_stacks_and_micro_systems(dev, cplx, shape):
+    r, R, n, r2, R2 = shape
+    rng = np.random.default_rng(7 + r + 31 * R + 101 * cplx)
+    L, Rt = rnd(rng, (r, R, r), cplx), rnd(rng, (r2, R2, r2), cplx)
+    x, A = rnd(rng, (r, n, r2), cplx), rnd(rng, (R, n, n, R2), cplx)
+    p, p2 = 2, 3
+    bL, bR, b = rnd(rng, (p, r), cplx), rnd(rng, (p2, r2), cplx), rnd(rng, (p, n, p2), cplx)
+    dL, dR, dx, dA = map(dev.to_device, (L, Rt, x, A))
+    dbL, dbR, db = map(dev.to_device, (bL, bR, b))
+    tol = 2e-13
+    assert relerr(host(dev.stack_left_op(dL, dx, dA, 0)), K.stack_left_op(L, x, A)) < tol
+    assert relerr(host(dev.stack_left_op(dL, dx, dA, 1)), K.stack_left_op(L, x, A, conj_col=True)) < tol
+    assert relerr(host(dev.stack_right_op(dR, dx, dA)), K.stack_right_op(Rt, x, A)) < tol
+    assert relerr(host(dev.stack_left_rhs(dbL, db, dx)), K.stack_left_rhs(bL, b, x)) < tol
+    assert relerr(host(dev.stack_right_rhs(dbR, db, dx)), K.stack_right_rhs(bR, b, x)) < tol
+    assert relerr(host(dev.micro_rhs_als(dbL, db, dbR)), K.micro_rhs_als(bL, b, bR)) < tol
+    v = rnd(rng, (r, n, r2), cplx)
+    yref = K.micro_matvec_als(L, A, Rt, v)
+    assert relerr(host(dev.micro_matvec_als(dL, dA, dR, dev.to_device(v))), yref) < tol
+    if r * n * r2 <= 2048:
+        Mref = K.micro_matrix_als(L, A, Rt)
+        assert relerr(host(dev.micro_matrix_als(dL, dA, dR)), Mref) < tol
+        assert relerr((Mref @ v.reshape(-1)).reshape(yref.shape), yref) < 1e-12
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_two_site_micro_systems(dev, cplx):
+    rng = np.random.default_rng(23 + cplx)
+    for (r, R, n, R2, n2, R3, r3) in [(2, 2, 3, 3, 4, 2, 3), (1, 1, 2, 3, 2, 1, 1), (4, 3, 5, 3, 5, 3, 4),
+                                      (6, 2, 16, 2, 16, 2, 6)]:
+        L, Rt = rnd(rng, (r, R, r), cplx), rnd(rng, (r3, R3, r3), cplx)
+        A1, A2 = rnd(rng, (R, n, n, R2), cplx), rnd(rng, (R2, n2, n2, R3), cplx)
+        v = rnd(rng, (r, n, n2, r3), cplx)
+        p, p2, p3 = 2, 3, 2
+        bL, bR = rnd(rng, (p, r), cplx), rnd(rng, (p3, r3), cplx)
+        b1, b2 = rnd(rng, (p, n, p2), cplx), rnd(rng, (p2, n2, p3), cplx)
+        dL, dR, dA1, dA2, dv = map(dev.to_device, (L, Rt, A1, A2, v))
+        yref = K.micro_matvec_mals(L, A1, A2, Rt, v)
+        assert relerr(host(dev.micro_matvec_mals(dL, dA1, dA2, dR, dv)), yref) < 2e-13
+        assert relerr(host(dev.micro_rhs_mals(*map(dev.to_device, (bL, b1, b2, bR)))), K.micro_rhs_mals(bL, b1, b2, bR)) < 2e-13
+        if r * n * n2 * r3 <= 2400:
+            Mref = K.micro_matrix_mals(L, A1, A2, Rt)
+            assert relerr(host(dev.micro_matrix_mals(dL, dA1, dA2, dR)), Mref) < 2e-13
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_rank1_update(dev, cplx):
+    rng = np.random.default_rng(5)
+    N = 75
+    M, t = rnd(rng, (N, N), cplx), rnd(rng, (N,), cplx)
+    dM = dev.to_device(M)
+    dev.rank1_update(dM, dev.to_device(t), -0.7)
+    assert relerr(host(dM), M - 0.7 * np.outer(t, np.conj(t))) < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------ dense solves
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 100, 256, 257, 600, 1024])
+def test_lu_solve_matches_lapack(dev, cplx, N):
+    rng = np.random.default_rng(N + 1000 * cplx)
+    M = rnd(rng, (N, N), cplx)
+    f = rnd(rng, (N,), cplx)
+    xref = np.linalg.solve(M, f)
+    dM = dev.to_device(M)
+    ipiv, info = dev.lu_factor(dM)
+    assert info == 0
+    # same pivot sequence as LAPACK getrf (partial pivoting, first maximal entry) on generic input
+    _, piv_ref = sla.lu_factor(M)
+    assert np.array_equal(host(ipiv)[:N], piv_ref)
+    dx = dev.lu_solve(dM, ipiv, dev.to_device(f))
+    cond = np.linalg.cond(M)
+    assert relerr(host(dx), xref) < 1e-14 * cond + 1e-13
+    # several right-hand sides
+    F = rnd(rng, (N, 3), cplx)
+    dX = dev.lu_solve(dM, ipiv, dev.to_device(F))
+    assert relerr(host(dX), np.linalg.solve(M, F)) < 1e-14 * cond + 1e-13
+
+
+def test_lu_reports_singular(dev):
+    M = np.ones((40, 40))
+    M[:, 7] = 0.0
+    with pytest.raises(np.linalg.LinAlgError):
+        dev.solve(dev.to_device(M), dev.to_device(np.ones(40)))
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("N", [1, 5, 32, 70, 300, 1000])
+def test_cholesky(dev, cplx, N):
+    rng = np.random.default_rng(N + 7 * cplx)
+    G = rnd(rng, (N, N + 3), cplx)
+    M = G @ np.conj(G.T) + N * np.eye(N)
+    F = rnd(rng, (N, 2), cplx)
+    dM = dev.to_device(M)
+    assert dev.chol_factor(dM) == 0
+    assert relerr(np.tril(host(dM)), np.linalg.cholesky(M)) < 1e-12
+    dX = dev.chol_solve(dM, dev.to_device(F))
+    assert relerr(host(dX), np.linalg.solve(M, F)) < 1e-12
+    Mbad = M.copy()
+    Mbad[N // 2, N // 2] = -1.0
+    assert dev.chol_factor(dev.to_device(Mbad)) != 0
+
+
+# ------------------------------------------------------------------------------------------------ QR / RQ / SVD
+QR_SHAPES = [(256, 4), (16, 16), (5, 9), (1, 6), (7, 1), (1000, 64), (4096, 64), (40, 130), (300, 200)]
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", QR_SHAPES)
+def test_qr_rq_match_lapack(dev, cplx, shape):
+    m, n = shape
+    rng = np.random.default_rng(m * 131 + n + cplx)
+    A = rnd(rng, (m, n), cplx)
+    Q, R = dev.qr(dev.to_device(A), want_r=True)
+    Q, R = host(Q), host(R)
+    k = min(m, n)
+    assert relerr(Q @ R, A) < 1e-13
+    assert relerr(np.conj(Q.T) @ Q, np.eye(k)) < 1e-13
+    assert np.allclose(R, np.triu(R))
+    qref, rref = sla.qr(A, mode='economic')       # same Householder convention -> same gauge
+    assert relerr(Q, qref) < 1e-11 and relerr(R, rref) < 1e-11
+    # RQ on the transposed shape (the backward ALS step factors r x (n r2))
+    B = rnd(rng, (n, m), cplx)
+    Rr, Qr = dev.rq(dev.to_device(B), want_r=True)
+    Rr, Qr = host(Rr), host(Qr)
+    assert relerr(Rr @ Qr, B) < 1e-13
+    assert relerr(Qr @ np.conj(Qr.T), np.eye(k)) < 1e-13
+    rref, qref = sla.rq(B, mode='economic')
+    assert relerr(Qr, qref) < 1e-11 and relerr(Rr, rref) < 1e-11
+
+
+SVD_SHAPES = [(1, 1), (6, 4), (4, 6), (64, 64), (256, 12), (12, 256), (1000, 64), (192, 192), (4096, 64), (300, 260)]
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", SVD_SHAPES)
+def test_svd_values_vectors_and_rank_rule(dev, cplx, shape):
+    m, n = shape
+    rng = np.random.default_rng(m * 17 + n + cplx)
+    k = min(m, n)
+    # prescribed spectrum spanning 12 decades so that the strict threshold rule is exercised
+    U0, _ = np.linalg.qr(rnd(rng, (m, k), cplx))
+    V0, _ = np.linalg.qr(rnd(rng, (n, k), cplx))
+    s0 = np.logspace(0, -12, k) if k > 1 else np.ones(1)
+    A = (U0 * s0) @ np.conj(V0.T)
+    sref = sla.svd(A, compute_uv=False, lapack_driver='gesvd')
+    thr = 1e-6
+    U, S, Vh, rank = dev.svd(dev.to_device(A), threshold=thr, max_rank=0)
+    U, S, Vh = host(U), host(S), host(Vh)
+    assert np.max(np.abs(S - sref) / np.maximum(sref, 1e-16 * sref[0])) < 1e-3       # relative, even for tiny s
+    assert np.max(np.abs(S - sref)) < 1e-14 * sref[0] * max(m, n)
+    assert relerr((U * S) @ Vh, A) < 1e-13
+    assert relerr(np.conj(U.T) @ U, np.eye(k)) < 1e-12
+    assert relerr(Vh @ np.conj(Vh.T), np.eye(k)) < 1e-12
+    assert rank == int(np.sum(sref / sref[0] > thr))
+    _, _, _, rank2 = dev.svd(dev.to_device(A), threshold=0.0, max_rank=3)
+    assert rank2 == min(3, k)
+    _, _, _, rank3 = dev.svd(dev.to_device(A), threshold=0.0, max_rank=0)
+    assert rank3 == k
+
+
+def test_svd_rank_deficient_completion(dev):
+    # tt.ones(..., ranks=4) unfoldings are numerically rank 1: U must still be orthonormal
+    A = np.ones((12, 4))
+    U, S, Vh, rank = dev.svd(dev.to_device(A), threshold=0.0, max_rank=0)
+    U, S, Vh = host(U), host(S), host(Vh)
+    assert rank == 4
+    assert abs(S[0] - np.sqrt(48.0)) < 1e-13 and np.all(S[1:] < 1e-14)
+    assert relerr(U.T @ U, np.eye(4)) < 1e-13
+    assert relerr((U * S) @ Vh, A) < 1e-13
+
+
+# ------------------------------------------------------------------------------------------------ eigen
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("N", [1, 2, 24, 150, 400])
+def test_eigh(dev, cplx, N):
+    rng = np.random.default_rng(N + cplx)
+    G = rnd(rng, (N, N), cplx)
+    M = G + np.conj(G.T)
+    wref = sla.eigh(M, eigvals_only=True)
+    W, V = dev.eigh(dev.to_device(M))
+    W, V = host(W), host(V)
+    scale = max(np.abs(wref).max(), 1e-300)
+    assert np.max(np.abs(W - wref)) < 1e-13 * scale * max(N, 8)
+    assert relerr(M @ V, V * W) < 1e-12
+    assert relerr(np.conj(V.T) @ V, np.eye(N)) < 1e-12
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("N", [6, 60, 300])
+def test_eig_shift_invert(dev, cplx, N):
+    rng = np.random.default_rng(N + 3 * cplx)
+    M = rnd(rng, (N, N), cplx) / np.sqrt(N) + np.diag(np.linspace(0.0, 3.0, N))
+    sigma, k = 1.234, min(3, N - 1)
+    lref = sla.eigvals(M)
+    lref = lref[np.argsort(np.abs(lref - sigma))][:k]
+    lam, vecs = dev.eig_shift_invert(dev.to_device(M), sigma, k, ncv=min(N, 40))
+    lam, vecs = host(lam), host(vecs)
+    order = np.argsort(np.abs(lam - sigma))
+    lam, vecs = lam[order], vecs[:, order]
+    assert np.max(np.abs(lam - lref)) < 1e-10
+    for j in range(k):
+        v = vecs[:, j]
+        assert np.linalg.norm(M @ v - lam[j] * v) < 1e-9 * np.linalg.norm(v)
+    # generalised pencil
+    Bm = np.eye(N) + 0.1 * (lambda g: g @ np.conj(g.T))(rnd(rng, (N, N), cplx)) / N
+    lrefg = sla.eigvals(M, Bm)
+    lrefg = lrefg[np.argsort(np.abs(lrefg - sigma))][:k]
+    lam, vecs = dev.eig_shift_invert(dev.to_device(M), sigma, k, B=dev.to_device(Bm), ncv=min(N, 40))
+    lam = host(lam)
+    lam = lam[np.argsort(np.abs(lam - sigma))]
+    assert np.max(np.abs(lam - lrefg)) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ Krylov
+def spd_local(rng, r, R, n, r2, cplx):
+    """A Hermitian positive definite one-site local operator: L, Rt Hermitian PSD per operator index, A symmetric."""
+    def psd(k):
+        g = rnd(rng, (k, k), cplx)
+        return g @ np.conj(g.T) / k + np.eye(k)
+    L = np.stack([psd(r) for _ in range(R)], axis=1)           # [a, b, c], Hermitian in (a, c) -> conj layout below
+    Rt = np.stack([psd(r2) for _ in range(R)], axis=1)
+    A = np.zeros((R, n, n, R), dtype=L.dtype)
+    for b in range(R):
+        g = rnd(rng, (n, n), cplx)
+        A[b, :, :, b] = np.eye(n) + 0.05 * (g + np.conj(g.T))
+    # M[(c,m,g),(a,n,e)] = sum_b L[a,b,c] A[b,m,n,b] Rt[e,b,g]: Hermitian if L[a,b,c] = conj(L[c,b,a]) etc.
+    return L.transpose(2, 1, 0).copy(), A, Rt.transpose(2, 1, 0).copy()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("method", ["cg", "gmres"])
+def test_krylov_one_site(dev, cplx, method):
+    rng = np.random.default_rng(77 + cplx)
+    r, R, n, r2 = 5, 3, 7, 4
+    L, A, Rt = spd_local(rng, r, R, n, r2, cplx)
+    M = K.micro_matrix_als(L, A, Rt)
+    assert relerr(M, np.conj(M.T)) < 1e-14
+    f = rnd(rng, (r, n, r2), cplx)
+    uref = np.linalg.solve(M, f.reshape(-1)).reshape(f.shape)
+    dL, dA, dR = map(dev.to_device, (L, A, Rt))
+    op = dev.local_op(dL, dA, dR)
+    u = dev.to_device(np.zeros_like(f))
+    st, iters, relres = dev.krylov_solve(op, dev.to_device(f), u, method=method, tol=1e-13, max_iters=2000, restart=30)
+    assert st == 0 and relres <= 1e-13
+    assert relerr(host(u), uref) < 1e-11
+
+
+def test_krylov_two_site_and_nonsymmetric(dev):
+    rng = np.random.default_rng(99)
+    r, R, n, R2, n2, R3, r3 = 3, 2, 4, 2, 5, 2, 3
+    L, Rt = rnd(rng, (r, R, r), False), rnd(rng, (r3, R3, r3), False)
+    A1, A2 = rnd(rng, (R, n, n, R2), False), rnd(rng, (R2, n2, n2, R3), False)
+    M = K.micro_matrix_mals(L, A1, A2, Rt)
+    f = rnd(rng, (r, n, n2, r3), False)
+    uref = np.linalg.solve(M, f.reshape(-1)).reshape(f.shape)
+    dL, dA1, dA2, dR = map(dev.to_device, (L, A1, A2, Rt))
+    op = dev.local_op(dL, dA1, dR, A2=dA2)
+    u = dev.to_device(np.zeros_like(f))
+    N = f.size
+    st, iters, relres = dev.krylov_solve(op, dev.to_device(f), u, method="gmres", tol=1e-12, max_iters=4 * N, restart=N)
+    assert st == 0
+    assert relerr(host(u), uref) < 1e-9 * np.linalg.cond(M)
+
+
+def test_blas1_helpers(dev):
+    rng = np.random.default_rng(3)
+    for cplx in (False, True):
+        x = rnd(rng, (100003,), cplx)
+        assert abs(dev.nrm2(dev.to_device(x)) - np.linalg.norm(x)) < 1e-12 * np.linalg.norm(x)

@@ -1,0 +1,97 @@
+"""CPU: the host side of the drop-in surface -- TT container semantics, argument validation of ortho_*
+(tests/test_tensor_train.py:371-382, :411-422 of the reference), the C-ABI library loads and exports every
+symbol include/sktt_b200.h declares, and the product fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import scikit_tt_b200.tensor_train as tt
+from scikit_tt_b200 import TT, _lib
+from oracle import tt as ott
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "sktt_b200.h")).read()
+    declared = set(re.findall(r"\b(sktt_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"sktt_ctx", "sktt_idx2", "sktt_local_op"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().sktt_version() == 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from scikit_tt_b200.solvers import sle
+    t = tt.ones([2, 2], [1, 1])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sle.als(tt.eye([2, 2]), t, t)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        t.ortho_right()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "scikit_tt_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(base, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_tt_container_and_algebra():
+    rng = np.random.default_rng(0)
+    a = TT([rng.standard_normal(s) for s in ((1, 2, 3, 2), (2, 3, 2, 3), (3, 2, 2, 1))])
+    b = TT([rng.standard_normal(s) for s in ((1, 2, 3, 1), (1, 3, 2, 2), (2, 2, 2, 1))])
+    assert (a.order, a.row_dims, a.col_dims, a.ranks) == (3, [2, 3, 2], [3, 2, 2], [1, 2, 3, 1])
+    assert np.allclose((a + b).full(), a.full() + b.full())
+    assert np.allclose((a - b).full(), a.full() - b.full())
+    assert np.allclose((2.5 * a).full(), 2.5 * a.full()) and np.allclose((a * 2).full(), 2 * a.full())
+    assert (a + b).ranks == [1, 3, 5, 1]
+    x = TT([rng.standard_normal(s) for s in ((1, 3, 1, 2), (2, 2, 1, 2), (2, 2, 1, 1))])
+    assert np.allclose((a @ x).matricize(), a.matricize() @ x.matricize())
+    assert np.allclose(a.transpose().matricize(), a.matricize().T)
+    assert a.isoperator() and not x.isoperator()
+    c = a.copy()
+    c.cores[0][:] = 0
+    assert np.abs(a.cores[0]).sum() > 0
+    assert np.allclose(tt.eye([2, 3]).matricize(), np.eye(6))
+    assert tt.ones([2, 3], [1, 1], ranks=4).ranks == [1, 4, 1]
+    assert abs(np.linalg.norm(tt.uniform([2, 3, 4], ranks=3, norm=2.0).full()) - 2.0) < 1e-12
+    assert np.allclose(TT(a.full()).full(), a.full())
+    pos = TT([np.abs(c) for c in a.cores])
+    assert abs(pos.norm(p=1) - np.max(pos.matricize().sum(axis=0))) < 1e-10
+    v = TT([np.abs(c) for c in x.cores])
+    assert abs(v.norm(p=1) - v.full().sum()) < 1e-12
+    with pytest.raises(ValueError):
+        TT([np.zeros((1, 2, 2, 2)), np.zeros((3, 2, 2, 1))])
+    with pytest.raises(ValueError):
+        TT([np.zeros((2, 2, 2))])
+    with pytest.raises(TypeError):
+        TT("x")
+    res = tt.residual_error(a, x, a @ x)
+    assert res < 1e-12 * (a @ x).full().size
+    y = TT([rng.standard_normal(c.shape) for c in (a @ x).cores[:1]] + (a @ x).cores[1:])
+    dense = np.linalg.norm(a.matricize() @ x.matricize() - y.matricize())
+    assert abs(tt.residual_error(a, x, y) - dense) < 1e-10 * dense
+
+
+def test_ortho_argument_validation():
+    t = tt.ones([2, 2, 2], [1, 1, 1], ranks=2)
+    for fn in (t.ortho_left, t.ortho_right):
+        with pytest.raises(ValueError):
+            fn(max_rank=0)
+        with pytest.raises(ValueError):
+            fn(threshold=-1)
+        with pytest.raises(TypeError):
+            fn(start_index="a")
+        with pytest.raises(TypeError):
+            fn(end_index="b")
