@@ -50,7 +50,9 @@ def micro_matrix_als(L, A, Rt):
 
 def micro_matvec_als(L, A, Rt, v):
     """Matrix-free product with the matrix of micro_matrix_als (SURVEY.md a4'; not in the reference)."""
-    return np.einsum('abc,ane,bmnd,edg->cmg', L, v, A, Rt, optimize=True)
+    t = td(L, v, axes=(0, 0))                       # [b, c, n, e]
+    t = td(t, A, axes=([0, 2], [0, 2]))             # [c, e, m, d]
+    return td(t, Rt, axes=([1, 3], [0, 1])).transpose(0, 1, 2)   # [c, m, g]
 
 
 def micro_matrix_mals(L, A1, A2, Rt):
@@ -65,7 +67,10 @@ def micro_matrix_mals(L, A1, A2, Rt):
 
 def micro_matvec_mals(L, A1, A2, Rt, v):
     """Two-site matrix-free product; v [r, n, n2, r3] (not in the reference)."""
-    return np.einsum('abc,anje,bmnd,dkjf,efg->cmkg', L, v, A1, A2, Rt, optimize=True)
+    t = td(L, v, axes=(0, 0))                       # [b, c, n, j, e]
+    t = td(t, A1, axes=([0, 2], [0, 2]))            # [c, j, e, m, d]
+    t = td(t, A2, axes=([1, 4], [2, 0]))            # [c, e, m, k, f]
+    return td(t, Rt, axes=([1, 4], [0, 1]))         # [c, m, k, g]
 
 
 def micro_rhs_als(bL, b, bR):

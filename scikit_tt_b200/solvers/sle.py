@@ -49,6 +49,10 @@ class _State:
             self.Rop[i] = dev.stack_right_op(self.Rop[i + 1], self.x[i + 1], self.A[i + 1])
             self.Rrhs[i] = dev.stack_right_rhs(self.Rrhs[i + 1], self.b[i + 1], self.x[i + 1])
 
+    def reset(self, x_cores):
+        """Restart from another set of device solution cores (bench: same problem, timed repeatedly)."""
+        self.x[:] = list(x_cores)
+
     def result(self):
         return TT(_local.download_vector_cores(self.x))
 
@@ -61,6 +65,12 @@ def als(operator, initial_guess, right_hand_side, repeats=1, solver='solve'):
     'gmres' force one.  Returns a new TT; inputs are not modified.
     """
     st = _State(operator, initial_guess, right_hand_side)
+    _run_als(st, repeats, solver)
+    return st.result()
+
+
+def _run_als(st, repeats, solver):
+    """The device-resident part of `als`: everything between the upload of the inputs and the download of the result."""
     dev, d, x = st.dev, st.d, st.x
     for i in range(d - 1, -1, -1):                                        # sle.py:54-56
         st.right(i)
@@ -79,7 +89,6 @@ def als(operator, initial_guess, right_hand_side, repeats=1, solver='solve'):
                 x[i] = q.reshape(q.shape[0], n, r2)
             else:
                 x[i] = u.reshape(r, n, r2)                                # sle.py:546
-    return st.result()
 
 
 def _micro_als(st, i, solver):
@@ -96,6 +105,11 @@ def _micro_als(st, i, solver):
 def mals(operator, initial_guess, right_hand_side, repeats=1, solver='solve', threshold=1e-12, max_rank=np.inf):
     """MALS sweeps (two-site micro systems, truncated-SVD core splitting; sle.py:98-191)."""
     st = _State(operator, initial_guess, right_hand_side)
+    _run_mals(st, repeats, solver, threshold, max_rank)
+    return st.result()
+
+
+def _run_mals(st, repeats, solver, threshold, max_rank):
     dev, d, x = st.dev, st.d, st.x
     for i in range(d - 1, 0, -1):                                         # sle.py:148-151
         st.right(i)
@@ -115,7 +129,6 @@ def mals(operator, initial_guess, right_hand_side, repeats=1, solver='solve', th
             x[i + 1] = vh.reshape(k, n2, r3)                              # sle.py:645
             if i == 0:
                 x[i] = dev.matmul(mat, vh, opb='C').reshape(r, n, k)      # U diag(s), sle.py:647-650
-    return st.result()
 
 
 def _micro_mals(st, i, solver):
