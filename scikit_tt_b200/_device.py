@@ -349,6 +349,15 @@ class Device:
         self._check(self.lib.sktt_widen(self.h, x.numel(), _ptr(x.contiguous()), _ptr(out)))
         return out
 
+    def axpby(self, alpha, x, beta, y, out=None):
+        """out = alpha * x + beta * y (elementwise, real scalars)."""
+        if out is None:
+            out = torch.empty_like(x)
+        al = (C.c_double * 2)(float(alpha), 0.0)
+        be = (C.c_double * 2)(float(beta), 0.0)
+        self._check(self.lib.sktt_axpby(self.h, dtype_code(x), x.numel(), al, _ptr(x), be, _ptr(y), _ptr(out)))
+        return out
+
     def dotc(self, x, y):
         """sum conj(x) * y (host scalar)."""
         out = (C.c_double * 2)(0.0, 0.0)

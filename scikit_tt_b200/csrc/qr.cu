@@ -249,7 +249,9 @@ extern "C" int sktt_qr_left(sktt_ctx* ctx, int dtype, int64_t m, int64_t n, cons
     return sktt_qr_internal(ctx, dtype, (int)m, (int)n, A, Q_out, R_out);
 }
 
-// A (m x n) = R Q.  With C = (J_m A)^H (n x m) = Qc Rc:  Q = J_k Qc^H,  R = J_m Rc^H J_k.
+// A (m x n) = R Q with the sign convention of LAPACK gerqf (scipy.linalg.rq): the reflectors are generated from the
+// LAST row backwards and annihilate the LEADING part of each row.  With C = (J_m A J_n)^H (n x m, both index orders
+// reversed) = Qc Rc this is exactly Householder QR of C:  Q = J_k Qc^H J_n,  R = J_m Rc^H J_k.
 extern "C" int sktt_rq_right(sktt_ctx* ctx, int dtype, int64_t m64, int64_t n64, const void* A, void* Q_out,
                              void* R_out, void* work) {
     (void)work;
@@ -258,10 +260,10 @@ extern "C" int sktt_rq_right(sktt_ctx* ctx, int dtype, int64_t m64, int64_t n64,
     if (m64 <= 0 || n64 <= 0 || m64 > 0x7fffffff || n64 > 0x7fffffff)
         return sktt_fail(ctx, SKTT_ERR_ARG, "rq: bad extents");
     const int m = (int)m64, n = (int)n64, k = m < n ? m : n;
-    // C[i][j] = conj(A[m-1-j][i])                       (C is n x m)
-    QrView lv{(long long)(m - 1) * n, 1, -(long long)n, 1};
-    // Q[k-1-j][i] = conj(Qc[i][j])                       (Q is k x n, row-major)
-    QrView qv{(long long)(k - 1) * n, 1, -(long long)n, 1};
+    // C[i][j] = conj(A[m-1-j][n-1-i])                   (C is n x m)
+    QrView lv{(long long)(m - 1) * n + (n - 1), -1, -(long long)n, 1};
+    // Q[k-1-j][n-1-i] = conj(Qc[i][j])                   (Q is k x n, row-major)
+    QrView qv{(long long)(k - 1) * n + (n - 1), -1, -(long long)n, 1};
     // R[m-1-c][k-1-g] = conj(Rc[g][c])                   (Rc is k x m; R is m x k, row-major)
     QrView rv{(long long)(m - 1) * k + (k - 1), -1, -(long long)k, 1};
     if (dtype == SKTT_F64)

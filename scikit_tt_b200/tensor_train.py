@@ -192,8 +192,8 @@ class TT(object):
         dev = _device.get_device()
         carry = None                                           # diag(s) V of the previous core, on the device
         for i in range(start_index, end_index + 1):
-            m, n, r2 = self.row_dims[i], self.col_dims[i], self.ranks[i + 1]
-            mat = dev.to_device(self.cores[i]).reshape(self.ranks[i], m * n * r2)
+            r_old, m, n, r2 = self.cores[i].shape
+            mat = dev.to_device(self.cores[i]).reshape(r_old, m * n * r2)
             if carry is not None:
                 carry, mat = _device.common_dtype(carry, mat)
                 mat = dev.matmul(carry, mat)
@@ -220,8 +220,8 @@ class TT(object):
         dev = _device.get_device()
         carry = None                                           # U diag(s) of the core to the right
         for i in range(start_index, end_index - 1, -1):
-            m, n, r = self.row_dims[i], self.col_dims[i], self.ranks[i]
-            mat = dev.to_device(self.cores[i]).reshape(r * m * n, self.ranks[i + 1])
+            r, m, n, r2_old = self.cores[i].shape
+            mat = dev.to_device(self.cores[i]).reshape(r * m * n, r2_old)
             if carry is not None:
                 mat, carry = _device.common_dtype(mat, carry)
                 mat = dev.matmul(mat, carry)

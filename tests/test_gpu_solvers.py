@@ -25,8 +25,10 @@ def T(z, prefix):
 
 
 def check_residual(op, sol, rhs, ref):
+    """1e-10 agreement of the residual VALUE with the reference's; residuals that are themselves at rounding level
+    (<= 1e-11: the solution is exactly representable at this rank) can only be compared by magnitude."""
     res = osle.residual(op.cores, sol.cores, rhs.cores)
-    assert abs(res - ref) <= VAL_TOL * max(ref, 1e-300) + 1e-13, (res, ref)
+    assert abs(res - ref) <= VAL_TOL * max(ref, 1e-300) + 1e-11, (res, ref)
 
 
 def test_sle_toeplitz(dev):
