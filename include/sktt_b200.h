@@ -189,7 +189,24 @@ typedef struct {
     const void* A1;
     const void* A2;
     const void* Rst;
+    const void* image;      /* NULL, or the buffer filled by sktt_local_op_prepare for this (A1, Rst)        */
 } sktt_local_op;
+
+/* Prepared form of a one-site local operator.  For the shapes the TMA-staged two-kernel matvec covers (fp64,
+ * R2 == 3, r3 == 64, mode sizes multiple of 32) the operator core and the right stack are re-laid once into the
+ * padded shared-memory tile images that kernel copies in bulk; sktt_local_op_image_size returns the number of
+ * elements of that buffer (0: shape not covered, the generic contraction chain is used and no image is needed).
+ * sktt_local_op_prepare fills `image` and stores the pointer in op->image; it must be called again whenever Lst, A1
+ * or Rst change.  sktt_local_matvec applies the operator (prepared or not): y = M v, work as sktt_local_matvec_work.  */
+int64_t sktt_local_op_image_size(sktt_ctx* ctx, int dtype, const sktt_local_op* op);
+int sktt_local_op_prepare(sktt_ctx* ctx, int dtype, sktt_local_op* op, void* image);
+int64_t sktt_local_matvec_work(const sktt_local_op* op);
+int sktt_local_matvec(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* v, void* y, void* work);
+/* The Krylov solvers keep their vectors in the layout the prepared matvec consumes and produces directly -- "tiled":
+ * [n][a][r3 + 4] with zero padding, sktt_local_op_tiled_len elements (0 if the operator is not prepared / covered) --
+ * and call this entry point once per iteration (two kernel launches).  Exposed for benchmarking that inner step.    */
+int64_t sktt_local_op_tiled_len(sktt_ctx* ctx, int dtype, const sktt_local_op* op);
+int sktt_local_matvec_tiled(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* vt, void* yt, void* work);
 
 int64_t sktt_krylov_work(const sktt_local_op* op, int method, int restart);
 /* method 0: CG (Hermitian positive definite), 1: restarted GMRES(restart)                       */

@@ -230,7 +230,7 @@ class Device:
         return X
 
     # ------------------------------------------------------------------ Krylov
-    def local_op(self, Lst, A1, Rst, A2=None):
+    def local_op(self, Lst, A1, Rst, A2=None, prepare=False):
         op = LocalOp()
         op.sites = 1 if A2 is None else 2
         op.r = Lst.shape[0]
@@ -243,14 +243,42 @@ class Device:
         op.r3 = Rst.shape[0]
         op.Lst, op.A1, op.Rst = Lst.data_ptr(), A1.data_ptr(), Rst.data_ptr()
         op.A2 = A2.data_ptr() if A2 is not None else None
+        op.image = None
         op._keep = (Lst, A1, A2, Rst)
+        if prepare:
+            self.prepare_local_op(op)
+        return op
+
+    def prepare_local_op(self, op):
+        """Build the TMA tile images of a one-site local operator (no-op for shapes the fused matvec does not cover)."""
+        dt = op._keep[0].dtype
+        n = self.lib.sktt_local_op_image_size(self.h, dtype_code(op._keep[0]), C.byref(op))
+        if n > 0:
+            op._image = self.empty((n,), dt)
+            self._check(self.lib.sktt_local_op_prepare(self.h, dtype_code(op._keep[0]), C.byref(op), _ptr(op._image)))
         return op
 
     def local_matvec(self, op, v):
         Lst, A1, A2, Rst = op._keep
-        if A2 is None:
-            return self.micro_matvec_als(Lst, A1, Rst, v)
-        return self.micro_matvec_mals(Lst, A1, A2, Rst, v)
+        shape = (op.r, op.m, op.r3) if A2 is None else (op.r, op.m, op.m2, op.r3)
+        y = self.empty(shape, v.dtype)
+        w = self.work(self.lib.sktt_local_matvec_work(C.byref(op)), v.dtype)
+        self._check(self.lib.sktt_local_matvec(self.h, dtype_code(v), C.byref(op), _ptr(v), _ptr(y), _ptr(w)))
+        return y
+
+    def local_matvec_tiled(self, op, vt, yt=None):
+        """The Krylov inner step: y = M v on tiled-layout vectors of a prepared operator (two kernel launches)."""
+        n = self.lib.sktt_local_op_tiled_len(self.h, dtype_code(vt), C.byref(op))
+        if n <= 0:
+            raise ValueError("operator is not prepared for the tiled matvec")
+        if yt is None:
+            yt = torch.zeros(n, dtype=vt.dtype, device=self.device)
+        w = self.work(self.lib.sktt_local_matvec_work(C.byref(op)), vt.dtype)
+        self._check(self.lib.sktt_local_matvec_tiled(self.h, dtype_code(vt), C.byref(op), _ptr(vt), _ptr(yt), _ptr(w)))
+        return yt
+
+    def tiled_len(self, op):
+        return int(self.lib.sktt_local_op_tiled_len(self.h, dtype_code(op._keep[0]), C.byref(op)))
 
     def krylov_solve(self, op, f, u, method="cg", tol=1e-13, max_iters=5000, restart=40):
         """Solves the micro system matrix-free; u (initial guess) is overwritten. Returns (iters, relres)."""

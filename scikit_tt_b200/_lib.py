@@ -23,7 +23,7 @@ class Idx2(C.Structure):
 class LocalOp(C.Structure):
     _fields_ = [("sites", i32), ("r", i64), ("R", i64), ("m", i64), ("n", i64), ("R2", i64),
                 ("m2", i64), ("n2", i64), ("R3", i64), ("r3", i64),
-                ("Lst", vp), ("A1", vp), ("A2", vp), ("Rst", vp)]
+                ("Lst", vp), ("A1", vp), ("A2", vp), ("Rst", vp), ("image", vp)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check the exported symbol set
@@ -55,6 +55,12 @@ SIGNATURES = {
     "sktt_chol_factor": (i32, [vp, i32, i64, vp, pint]),
     "sktt_chol_solve": (i32, [vp, i32, i64, i64, vp, vp]),
     "sktt_chol_trsm": (i32, [vp, i32, i64, i64, vp, vp, i32]),
+    "sktt_local_op_image_size": (i64, [vp, i32, C.POINTER(LocalOp)]),
+    "sktt_local_op_prepare": (i32, [vp, i32, C.POINTER(LocalOp), vp]),
+    "sktt_local_matvec_work": (i64, [C.POINTER(LocalOp)]),
+    "sktt_local_matvec": (i32, [vp, i32, C.POINTER(LocalOp), vp, vp, vp]),
+    "sktt_local_op_tiled_len": (i64, [vp, i32, C.POINTER(LocalOp)]),
+    "sktt_local_matvec_tiled": (i32, [vp, i32, C.POINTER(LocalOp), vp, vp, vp]),
     "sktt_krylov_work": (i64, [C.POINTER(LocalOp), i32, i32]),
     "sktt_krylov_solve": (i32, [vp, i32, C.POINTER(LocalOp), i32, i32, vp, vp, dbl, i32, vp, pint, pdbl]),
     "sktt_qr_work": (i64, [i64, i64]),

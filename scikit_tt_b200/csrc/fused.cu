@@ -1,0 +1,499 @@
+// fused.cu -- the matrix-free micro-matvec of the ALS sweep (SURVEY.md row a4', the same contraction chain as the
+// stack updates sle.py:217-219 / :274-276) as two purpose-built fp64 tensor-core kernels instead of three generic
+// GEMM launches:
+//
+//   y[c,m,c2] = sum_{a,b,n,a2,b2} L[a,b,c] v[a,n,a2] A[b,m,n,b2] Rt[a2,b2,c2]
+//
+//   mv_stage1_kernel : T1[(b,c),(n,a2)] = sum_a L[a,(b,c)] v[a,(n,a2)]          ("TN" GEMM, K = r resident in smem)
+//   mv_stage23_kernel: one CTA per (c, block of 32 row-mode indices m).  The second contraction
+//                        T2[m,a2,b2] = sum_{b,n} A[b,m,n,b2] T1[b,c,n,a2]
+//                      and the third  y[c,m,c2] = sum_{a2,b2} T2[m,a2,b2] Rt[a2,b2,c2]
+//                      are independent across (c, m), so T2 never leaves the SM: accumulators -> shared memory ->
+//                      A-fragments of the last contraction.
+//
+// Operand staging: a producer warp moves every operand tile with TMA bulk copies (cp.async.bulk, SASS UBLKCP) that
+// complete on mbarriers; 16 consumer warps only issue LDS.64 + DMMA.8x8x4.  To make each tile ONE contiguous copy the
+// operator core and the right stack are re-laid once per local operator into "images" that are byte-for-byte the
+// padded shared-memory tiles (mv_prepare_kernel), and stage 1 writes T1 with the padded row pitch.  Leading dimensions
+// are = 4 (mod 16) doubles so the 64-bit fragment loads of a half-warp hit 16 distinct bank pairs.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled as transaction bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int CONSUMER_WARPS = 16;
+constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;   // + one producer warp
+
+// ------------------------------------------------------------------------------------------------ stage 1
+// T1[(b,c), n, a2] = sum_a L[a,(b,c)] v[a,n,a2].  One CTA per (n, tile of 96 rows (b,c)).  Both operand tiles are
+// contiguous in global memory: the L tile comes from the prepared image Limg[mtile][a][S1_LDA] and the v tile from the
+// TILED vector layout vt[n][a][S1_LDB] (S1_LDB = r2 + 4; padding is zero), so the producer warp needs two bulk copies
+// per K group.  Consumers: 8 warp tiles of 48 x 16, two warps per tile splitting the K range.
+constexpr int S1_BM = 96, S1_BN = 64, S1_LDA = S1_BM + 4, S1_LDB = S1_BN + 4, S1_GROUPS = 4;
+constexpr int S1_RED = 8 * 48 * 16;                       // doubles of the K-half reduction buffer
+
+__host__ __device__ inline size_t s1_smem_bytes(int K1) {
+    size_t tiles = (size_t)K1 * (S1_LDA + S1_LDB);
+    return (tiles > (size_t)S1_RED ? tiles : (size_t)S1_RED) * sizeof(double) + 64;
+}
+
+__global__ void __launch_bounds__(THREADS)
+mv_stage1_kernel(const double* __restrict__ Limg, const double* __restrict__ vt, double* __restrict__ T1p, int M1,
+                 int K1, int ntot) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);     // [K1][S1_LDA]
+    double* Bs = As + (size_t)K1 * S1_LDA;                 // [K1][S1_LDB]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + s1_smem_bytes(K1) - 64);   // [S1_GROUPS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nn = blockIdx.x, mt = blockIdx.y, m0 = mt * S1_BM;
+    const int kg = ((K1 + 4 * S1_GROUPS - 1) / (4 * S1_GROUPS)) * 4;   // K rows per group (multiple of 4)
+    if (tid == 0) {
+        for (int g = 0; g < S1_GROUPS; ++g) mbar_init(full + g, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == CONSUMER_WARPS) {
+        if (lane != 0) return;
+        const double* asrc = Limg + (size_t)mt * K1 * S1_LDA;
+        const double* bsrc = vt + (size_t)nn * K1 * S1_LDB;
+        for (int g = 0; g < S1_GROUPS; ++g) {
+            const int k_lo = min(K1, g * kg), k_hi = min(K1, k_lo + kg);
+            const unsigned rows = (unsigned)(k_hi - k_lo);
+            mbar_expect_tx(full + g, rows * (unsigned)((S1_LDA + S1_LDB) * sizeof(double)));
+            if (rows) {
+                bulk_g2s(As + (size_t)k_lo * S1_LDA, asrc + (size_t)k_lo * S1_LDA, rows * S1_LDA * sizeof(double), full + g);
+                bulk_g2s(Bs + (size_t)k_lo * S1_LDB, bsrc + (size_t)k_lo * S1_LDB, rows * S1_LDB * sizeof(double), full + g);
+            }
+        }
+        return;
+    }
+    const int tile = warp & 7, khalf = warp >> 3;
+    const int wm0 = (tile & 1) * 48, wn0 = (tile >> 1) * 16;
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[6][2][2];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int g = 0; g < S1_GROUPS; ++g) {
+        const int k_lo = min(K1, g * kg), k_hi = min(K1, k_lo + kg);
+        const int steps = (k_hi - k_lo) / 4, half = (steps + 1) / 2;
+        const int s_lo = khalf == 0 ? 0 : half, s_hi = khalf == 0 ? half : steps;
+        mbar_wait(full + g, 0);
+        for (int st = s_lo; st < s_hi; ++st) {
+            const int kk = k_lo + 4 * st;
+            const double* as = As + (kk + fk) * S1_LDA + wm0 + fr;
+            const double* bs = Bs + (kk + fk) * S1_LDB + wn0 + fr;
+            double af[6], bf[2];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) af[i] = as[8 * i];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) bf[j] = bs[8 * j];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    // reduce the two K-halves through shared memory (the operand tiles are dead once every consumer got here)
+    consumer_bar_sync();
+    double* red = As + (size_t)tile * (48 * 16);
+    if (khalf == 1) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<double2*>(red + (8 * i + fr) * 16 + 8 * j + 2 * fk) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+    consumer_bar_sync();
+    if (khalf == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int m = m0 + wm0 + 8 * i + fr;
+            if (m >= M1) continue;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double2 o = *reinterpret_cast<const double2*>(red + (8 * i + fr) * 16 + 8 * j + 2 * fk);
+                double* dst = T1p + ((size_t)m * ntot + nn) * S1_LDB + wn0 + 8 * j + 2 * fk;
+                *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0] + o.x, acc[i][j][1] + o.y);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stages 2 + 3
+// RB = R2 (right operator rank), NA = r2 (right solution rank), MB = rows of the mode index per CTA.
+template <int RB, int NA, int MB>
+struct S23 {
+    static constexpr int KC = 16;                          // contraction chunk
+    static constexpr int LDB = NA + 4;                     // T1 / Rt chunk rows  [KC][LDB]
+    static constexpr int LDA = KC + 4;                     // A chunk             [RB][MB][LDA]
+    static constexpr int K3 = NA * RB;                     // contraction length of the last stage
+    static constexpr int LDT = K3 + 4;                     // T2 in shared memory [MB][LDT]
+    static constexpr int STAGES = 4;
+    static constexpr int B_ELEMS = KC * LDB, A_ELEMS = RB * MB * LDA;
+    static constexpr int SLOT = B_ELEMS + A_ELEMS;         // doubles per ring slot
+    static constexpr size_t SMEM = ((size_t)STAGES * SLOT + (size_t)MB * LDT) * sizeof(double) + 2 * STAGES * 8;
+    static_assert(NA == 64 && MB == 32, "warp layout: 2 (m16) x 4 (n16) tiles x 2 K-halves = 16 consumer warps");
+    static_assert(LDB % 16 == 4 && LDA % 16 == 4 && LDT % 16 == 4, "bank-conflict-free leading dimensions");
+    static_assert((B_ELEMS * 8) % 16 == 0 && (A_ELEMS * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
+};
+
+// Images (built once per local operator): byte-for-byte the padded shared-memory tiles.
+//   Aimg[b][mblk][nchunk][q][mm][kk]  = A[b, mblk*MB + mm, nchunk*KC + kk, q]   (kk >= KC: zero padding)
+//   Rimg[chunk][k][col]               = Rt[(chunk*KC + k) * NA + col]            (col >= NA: zero padding)
+//   Limg[mtile][a][mm]                = L[a, mtile*S1_BM + mm]  (row index (b,c) of stage 1; mm beyond M1 / S1_BM: zero)
+template <int RB, int NA, int MB>
+__global__ void mv_prepare_kernel(const double* __restrict__ A, const double* __restrict__ Rt, const double* __restrict__ L,
+                                  double* __restrict__ Aimg, double* __restrict__ Rimg, double* __restrict__ Limg, int r,
+                                  int R, int mtot, int ntot) {
+    using P = S23<RB, NA, MB>;
+    const long long na = (long long)R * (mtot / MB) * (ntot / P::KC) * P::A_ELEMS;
+    const long long nr = (long long)(P::K3 / P::KC) * P::B_ELEMS;
+    const int M1 = R * r;
+    const long long nl = (long long)((M1 + S1_BM - 1) / S1_BM) * r * S1_LDA;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < na + nr + nl;
+         e += (long long)gridDim.x * blockDim.x) {
+        if (e >= na + nr) {
+            long long f = e - na - nr;
+            int mm = (int)(f % S1_LDA);
+            long long t = f / S1_LDA;
+            int a = (int)(t % r), mt = (int)(t / r);
+            int m = mt * S1_BM + mm;
+            Limg[f] = (mm < S1_BM && m < M1) ? L[(size_t)a * M1 + m] : 0.0;
+        } else if (e < na) {
+            int kk = (int)(e % P::LDA);
+            long long t = e / P::LDA;
+            int mm = (int)(t % MB);
+            t /= MB;
+            int q = (int)(t % RB);
+            t /= RB;
+            int nc = (int)(t % (ntot / P::KC));
+            t /= (ntot / P::KC);
+            int mblk = (int)(t % (mtot / MB));
+            int b = (int)(t / (mtot / MB));
+            double v = 0.0;
+            if (kk < P::KC) v = A[(((size_t)b * mtot + mblk * MB + mm) * ntot + nc * P::KC + kk) * RB + q];
+            Aimg[e] = v;
+        } else {
+            long long f = e - na;
+            int col = (int)(f % P::LDB);
+            long long row = f / P::LDB;
+            Rimg[f] = col < NA ? Rt[(size_t)row * NA + col] : 0.0;
+        }
+    }
+}
+
+// natural [a][n][NA]  <->  tiled [n][a][NA + 4] (padding columns zero)
+template <int NA>
+__global__ void to_tiled_kernel(const double* __restrict__ src, double* __restrict__ dst, int r, int ntot) {
+    const long long total = (long long)ntot * r * (NA + 4);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        int col = (int)(e % (NA + 4));
+        long long t = e / (NA + 4);
+        int a = (int)(t % r), nn = (int)(t / r);
+        dst[e] = col < NA ? src[((size_t)a * ntot + nn) * NA + col] : 0.0;
+    }
+}
+template <int NA>
+__global__ void from_tiled_kernel(const double* __restrict__ src, double* __restrict__ dst, int r, int ntot) {
+    const long long total = (long long)r * ntot * NA;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        int col = (int)(e % NA);
+        long long t = e / NA;
+        int nn = (int)(t % ntot), a = (int)(t / ntot);
+        dst[e] = src[((size_t)nn * r + a) * (NA + 4) + col];
+    }
+}
+
+template <int RB, int NA, int MB>
+__global__ void __launch_bounds__(THREADS)
+mv_stage23_kernel(const double* __restrict__ T1p, const double* __restrict__ Aimg, const double* __restrict__ Rimg,
+                  double* __restrict__ Y, int r, int R, int mtot, int ntot) {
+    using P = S23<RB, NA, MB>;
+    constexpr int KC = P::KC, LDB = P::LDB, LDA = P::LDA, LDT = P::LDT, STAGES = P::STAGES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    double* T2s = ring + (size_t)STAGES * P::SLOT;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(T2s + (size_t)MB * LDT);
+    unsigned long long* empty = full + STAGES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x, mblk = blockIdx.y, m0 = mblk * MB;
+    const int nchunks_n = ntot / KC;
+    const int T2n = R * nchunks_n;                         // chunks of the second contraction: (b, n-chunk)
+    const int T3n = P::K3 / KC;                            // chunks of the third contraction
+    const int total = T2n + T3n;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == CONSUMER_WARPS) {
+        if (lane != 0) return;
+        for (int t = 0; t < total; ++t) {
+            const int s = t % STAGES;
+            if (t >= STAGES) mbar_wait(empty + s, ((t / STAGES) & 1) ^ 1);
+            double* slot = ring + (size_t)s * P::SLOT;
+            if (t < T2n) {
+                const int b = t / nchunks_n, nc = t % nchunks_n;
+                mbar_expect_tx(full + s, (unsigned)(P::SLOT * sizeof(double)));
+                bulk_g2s(slot, T1p + (((size_t)b * r + c) * ntot + (size_t)nc * KC) * LDB, P::B_ELEMS * sizeof(double),
+                         full + s);
+                bulk_g2s(slot + P::B_ELEMS,
+                         Aimg + (((size_t)b * (mtot / MB) + mblk) * nchunks_n + nc) * P::A_ELEMS,
+                         P::A_ELEMS * sizeof(double), full + s);
+            } else {
+                mbar_expect_tx(full + s, (unsigned)(P::B_ELEMS * sizeof(double)));
+                bulk_g2s(slot, Rimg + (size_t)(t - T2n) * P::B_ELEMS, P::B_ELEMS * sizeof(double), full + s);
+            }
+        }
+        return;
+    }
+
+    // consumers: tile (16 rows of m) x (16 columns of a2 / c2), two warps per tile splitting every chunk's K range
+    const int tile = warp & 7, khalf = warp >> 3;
+    const int wm0 = (tile & 1) * 16, wn0 = (tile >> 1) * 16;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int kbeg = khalf * (KC / 2);
+    double acc2[RB][2][2][2];
+    double acc3[2][2][2];
+#pragma unroll
+    for (int q = 0; q < RB; ++q)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc2[q][i][j][0] = acc2[q][i][j][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc3[i][j][0] = acc3[i][j][1] = 0.0;
+
+    for (int t = 0; t < total; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(full + s, (t / STAGES) & 1);
+        const double* slot = ring + (size_t)s * P::SLOT;
+        const double* bs = slot + wn0 + fr;
+        if (t < T2n) {
+            const double* as = slot + P::B_ELEMS + (size_t)(wm0 + fr) * LDA + fk;
+#pragma unroll
+            for (int kk = kbeg; kk < kbeg + KC / 2; kk += 4) {
+                double bf[2], af[RB][2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) bf[j] = bs[(kk + fk) * LDB + 8 * j];
+#pragma unroll
+                for (int q = 0; q < RB; ++q)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) af[q][i] = as[((size_t)q * MB + 8 * i) * LDA + kk];
+#pragma unroll
+                for (int q = 0; q < RB; ++q)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) dmma(acc2[q][i][j][0], acc2[q][i][j][1], af[q][i], bf[j]);
+            }
+        } else {
+            const int k0 = (t - T2n) * KC;
+            const double* ts = T2s + (size_t)(wm0 + fr) * LDT + k0 + fk;
+#pragma unroll
+            for (int kk = kbeg; kk < kbeg + KC / 2; kk += 4) {
+                double bf[2], af[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) bf[j] = bs[(kk + fk) * LDB + 8 * j];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) af[i] = ts[(size_t)(8 * i) * LDT + kk];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) dmma(acc3[i][j][0], acc3[i][j][1], af[i], bf[j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);             // this warp is done with the slot
+        if (t == T2n - 1) {
+            // T2[m, a2, b2] = sum of the two K-halves -> T2s[m][a2 * RB + b2]
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (khalf == h) {
+#pragma unroll
+                    for (int q = 0; q < RB; ++q)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const int mm = wm0 + 8 * i + fr, a2 = wn0 + 8 * j + 2 * fk;
+                                double* d0 = T2s + (size_t)mm * LDT + (size_t)a2 * RB + q;
+                                double* d1 = d0 + RB;
+                                if (h == 0) {
+                                    *d0 = acc2[q][i][j][0];
+                                    *d1 = acc2[q][i][j][1];
+                                } else {
+                                    *d0 += acc2[q][i][j][0];
+                                    *d1 += acc2[q][i][j][1];
+                                }
+                            }
+                }
+                consumer_bar_sync();
+            }
+        }
+    }
+    // reduce the two K-halves of the last contraction through shared memory (ring slot 0 is free by now) and store
+    consumer_bar_sync();
+    double* red = ring;                                    // [8 tiles][16][16]
+    if (khalf == 1) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                double* d = red + (size_t)tile * 256 + (size_t)(8 * i + fr) * 16 + 8 * j + 2 * fk;
+                *reinterpret_cast<double2*>(d) = make_double2(acc3[i][j][0], acc3[i][j][1]);
+            }
+    }
+    consumer_bar_sync();
+    if (khalf == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int m = m0 + wm0 + 8 * i + fr;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c2 = wn0 + 8 * j + 2 * fk;
+                const double2 o = *reinterpret_cast<const double2*>(red + (size_t)tile * 256 + (size_t)(8 * i + fr) * 16 +
+                                                                    8 * j + 2 * fk);
+                *reinterpret_cast<double2*>(Y + ((size_t)m * r + c) * LDB + c2) =      // tiled vector layout
+                    make_double2(acc3[i][j][0] + o.x, acc3[i][j][1] + o.y);
+            }
+        }
+    }
+}
+
+using Cfg = S23<3, 64, 32>;
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host side
+// Shapes covered by the fused path (everything else runs the generic three-GEMM chain of stacks.cu).
+bool sktt_fused_supported(const sktt_ctx* ctx, int dtype, long long r, long long R, long long m, long long n,
+                          long long r2, long long R2) {
+    if (dtype != SKTT_F64 || ctx->gemm_mode == 1) return false;
+    if (m != n || n % 16 != 0 || m % 32 != 0) return false;
+    if (r % 4 != 0 || r > 128 || R > 14) return false;
+    if (!(R2 == 3 && r2 == 64)) return false;
+    return s1_smem_bytes((int)r) <= 200 * 1024;
+}
+
+static long long img_a_elems(long long R, long long m, long long n) { return R * (m / 32) * (n / Cfg::KC) * Cfg::A_ELEMS; }
+static long long img_r_elems() { return (long long)(Cfg::K3 / Cfg::KC) * Cfg::B_ELEMS; }
+static long long img_l_elems(long long r, long long R) { return ((R * r + S1_BM - 1) / S1_BM) * r * S1_LDA; }
+
+long long sktt_fused_image_elems(long long r, long long R, long long m, long long n) {
+    return img_a_elems(R, m, n) + img_r_elems() + img_l_elems(r, R);
+}
+// length of a vector of the micro system in the tiled layout [n][a][r2 + 4]
+long long sktt_fused_tiled_len(long long r, long long n) { return n * r * Cfg::LDB; }
+
+static inline int ew_grid(const sktt_ctx* ctx, long long total) {
+    long long b = (total + 255) / 256;
+    return (int)(b < 1 ? 1 : (b > 4LL * ctx->sm_count ? 4LL * ctx->sm_count : b));
+}
+
+// image = [Aimg | Rimg | Limg]
+int sktt_fused_prepare(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* Lst,
+                       const double* A, const double* Rst, double* image) {
+    const long long na = img_a_elems(R, m, n), nr = img_r_elems();
+    const long long total = sktt_fused_image_elems(r, R, m, n);
+    mv_prepare_kernel<3, 64, 32><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(A, Rst, Lst, image, image + na,
+                                                                                image + na + nr, (int)r, (int)R, (int)m,
+                                                                                (int)n);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int sktt_fused_to_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst) {
+    to_tiled_kernel<64><<<ew_grid(ctx, sktt_fused_tiled_len(r, n)), 256, 0, ctx->stream>>>(src, dst, (int)r, (int)n);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int sktt_fused_from_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst) {
+    from_tiled_kernel<64><<<ew_grid(ctx, r * n * 64), 256, 0, ctx->stream>>>(src, dst, (int)r, (int)n);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// yt = M vt on vectors in the tiled layout; T1p: R * r * n * (r2 + 4) doubles of scratch.
+int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                            const double* vt, double* yt, double* T1p) {
+    const int M1 = (int)(R * r), K1 = (int)r;
+    const size_t smem1 = s1_smem_bytes(K1);
+    static bool configured = false;
+    if (!configured) {
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(mv_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(mv_stage23_kernel<3, 64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)Cfg::SMEM));
+        configured = true;
+    }
+    const long long na = img_a_elems(R, m, n), nr = img_r_elems();
+    dim3 g1((unsigned)n, (unsigned)((M1 + S1_BM - 1) / S1_BM));
+    mv_stage1_kernel<<<g1, THREADS, smem1, ctx->stream>>>(image + na + nr, vt, T1p, M1, K1, (int)n);
+    SKTT_LAUNCH_CHECK(ctx);
+    dim3 g2((unsigned)r, (unsigned)(m / 32));
+    mv_stage23_kernel<3, 64, 32><<<g2, THREADS, Cfg::SMEM, ctx->stream>>>(T1p, image, image + na, yt, (int)r, (int)R,
+                                                                           (int)m, (int)n);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// natural-layout wrapper: v [r][n][64] -> y [r][m][64]; work holds T1p followed by the two tiled vectors
+int sktt_fused_matvec(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                      const double* v, double* y, double* work) {
+    double* T1p = work;
+    double* vt = T1p + R * r * n * Cfg::LDB;
+    double* yt = vt + sktt_fused_tiled_len(r, n);
+    SKTT_TRY(sktt_fused_to_tiled(ctx, r, n, v, vt));
+    SKTT_TRY(sktt_fused_matvec_tiled(ctx, r, R, m, n, image, vt, yt, T1p));
+    return sktt_fused_from_tiled(ctx, r, m, yt, y);
+}

@@ -8,28 +8,58 @@
 #include "common.cuh"
 #include "blas1.cuh"
 
-static int local_matvec(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* v, void* y, void* work) {
-    if (op->sites == 1)
-        return sktt_micro_matvec_als(ctx, dtype, op->r, op->R, op->m, op->n, op->r3, op->R2, op->Lst, op->A1, op->Rst, v,
-                                     y, work);
-    return sktt_micro_matvec_mals(ctx, dtype, op->r, op->R, op->m, op->n, op->R2, op->m2, op->n2, op->R3, op->r3,
-                                  op->Lst, op->A1, op->A2, op->Rst, v, y, work);
+// fused.cu: TMA-staged matvec on vectors in the tiled layout [n][a][r2 + 4]
+long long sktt_fused_tiled_len(long long r, long long n);
+int sktt_fused_to_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst);
+int sktt_fused_from_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst);
+int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                            const double* vt, double* yt, double* T1p);
+
+// The operator as the Krylov loops see it: either the generic contraction chain on natural-layout vectors, or the
+// prepared fused matvec on tiled-layout vectors (all Krylov vectors then live in that layout; padding stays zero).
+struct KOp {
+    sktt_local_op op;
+    bool tiled;
+    long long N;   // vector length the solver iterates on
+};
+
+static int kop_matvec(sktt_ctx* ctx, int dtype, const KOp& k, const void* v, void* y, void* work) {
+    if (k.tiled)
+        return sktt_fused_matvec_tiled(ctx, k.op.r, k.op.R, k.op.m, k.op.n, (const double*)k.op.image, (const double*)v,
+                                       (double*)y, (double*)work);
+    return sktt_local_matvec(ctx, dtype, &k.op, v, y, work);
 }
 
 static int64_t local_dim(const sktt_local_op* op) {
     return op->sites == 1 ? op->r * op->n * op->r3 : op->r * op->n * op->n2 * op->r3;
+}
+// bound of the vector length in either layout
+static int64_t local_dim_bound(const sktt_local_op* op) {
+    return op->sites == 1 ? op->r * op->n * (op->r3 + 4) : local_dim(op);
 }
 static int64_t local_mv_work(const sktt_local_op* op) {
     if (op->sites == 1) return sktt_stack_op_work(op->r, op->R, op->m, op->n, op->r3, op->R2);
     return sktt_micro_matvec_mals_work(op->r, op->R, op->m, op->n, op->R2, op->m2, op->n2, op->R3, op->r3);
 }
 
+// upper bound of the prepared-operator image (fused.cu) for one-site operators, 0 otherwise
+static int64_t local_image_bound(const sktt_local_op* op) {
+    if (op->sites != 1 || op->image) return 0;
+    return op->R * ((op->m + 31) / 32) * ((op->n + 15) / 16) * 1920 + 12 * 16 * 68 + ((op->R * op->r + 95) / 96) * op->r * 100 + 64;
+}
+
+// elements used by the solver proper (vectors of length Nb + small state), excluding matvec scratch
+static int64_t solver_core_work(int method, int restart, int64_t Nb) {
+    if (method == 0) return 3 * Nb + 64;                                  // r, p, Ap
+    int64_t m = restart > 0 ? restart : 40;
+    return (m + 2) * Nb + (m + 1) * (m + 4) + 4 * (m + 2) + 64;            // V, w, H, givens, g, y, h2
+}
+
 extern "C" int64_t sktt_krylov_work(const sktt_local_op* op, int method, int restart) {
     if (!op) return -1;
-    int64_t N = local_dim(op), mv = local_mv_work(op);
-    if (method == 0) return mv + 3 * N + 64;                       // r, p, Ap
-    int64_t m = restart > 0 ? restart : 40;
-    return mv + (m + 2) * N + (m + 1) * (m + 4) + 4 * (m + 2) + 64;  // V, w, H, givens, g, y
+    int64_t Nb = local_dim_bound(op);
+    // matvec scratch | solver | f and u in the tiled layout | operator image
+    return local_mv_work(op) + solver_core_work(method, restart, Nb) + 2 * Nb + 64 + local_image_bound(op);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -102,11 +132,11 @@ static inline int ew_blocks(sktt_ctx* ctx, long long n) {
 }
 
 template <typename T>
-static int cg_impl(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const T* f, T* u, double tol, int max_iters,
+static int cg_impl(sktt_ctx* ctx, int dtype, const KOp& op, const T* f, T* u, double tol, int max_iters,
                    T* work, int* iters_host, double* relres_host) {
-    const long long N = local_dim(op);
+    const long long N = op.N;
     T* mvwork = work;
-    T* r = work + local_mv_work(op);
+    T* r = work + local_mv_work(&op.op);
     T* p = r + N;
     T* Ap = p + N;
     double* slots = (double*)ctx->scratch;  // [0..1] rr ping-pong, [2..3] pAp, [4] flag, [5] |f|^2
@@ -117,7 +147,7 @@ static int cg_impl(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const T* f
     SKTT_CUDA(ctx, cudaMemsetAsync(slots, 0, 8 * sizeof(double), ctx->stream));
     SKTT_TRY(blas1_dot(ctx, dtype, N, f, f, slots + 5));
     // +6 is scratch for the imaginary part written by blas1_dot at [5]+1
-    SKTT_TRY(local_matvec(ctx, dtype, op, u, Ap, mvwork));
+    SKTT_TRY(kop_matvec(ctx, dtype, op, u, Ap, mvwork));
     residual_init_kernel<T><<<nb, 256, 0, ctx->stream>>>(N, f, Ap, r, p);
     SKTT_LAUNCH_CHECK(ctx);
     double* rr_init = (double*)((char*)ctx->scratch + 256);  // 2 doubles (re, im)
@@ -146,7 +176,7 @@ static int cg_impl(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const T* f
         for (int b = 0; b < batch && launched < max_iters; ++b, ++launched) {
             double* rr_old = slots + (launched & 1);
             double* rr_new = slots + ((launched + 1) & 1);
-            status = local_matvec(ctx, dtype, op, p, Ap, mvwork);
+            status = kop_matvec(ctx, dtype, op, p, Ap, mvwork);
             if (status) break;
             status = blas1_dot(ctx, dtype, N, p, Ap, slots + 2);
             if (status) break;
@@ -264,12 +294,12 @@ __global__ void gmres_init_g_kernel(int m, T* g, const double* beta2) {
 }
 
 template <typename T>
-static int gmres_impl(sktt_ctx* ctx, int dtype, const sktt_local_op* op, int restart, const T* f, T* u, double tol,
+static int gmres_impl(sktt_ctx* ctx, int dtype, const KOp& op, int restart, const T* f, T* u, double tol,
                       int max_iters, T* work, int* iters_host, double* relres_host) {
-    const long long N = local_dim(op);
+    const long long N = op.N;
     const int m = restart > 0 ? restart : 40;
     T* mvwork = work;
-    T* V = work + local_mv_work(op);     // [(m+1)][N]
+    T* V = work + local_mv_work(&op.op);     // [(m+1)][N]
     T* w = V + (size_t)(m + 1) * N;      // [N]
     T* H = w + N;                        // [(m+1)*m]
     T* cs = H + (size_t)(m + 1) * m;
@@ -295,7 +325,7 @@ static int gmres_impl(sktt_ctx* ctx, int dtype, const sktt_local_op* op, int res
     const double one[2] = {1.0, 0.0}, minus_one[2] = {-1.0, 0.0};
     while (total < max_iters) {
         // r0 = f - A u -> V[0] (normalised), g = beta e1
-        SKTT_TRY(local_matvec(ctx, dtype, op, u, w, mvwork));
+        SKTT_TRY(kop_matvec(ctx, dtype, op, u, w, mvwork));
         residual_init_kernel<T><<<nb, 256, 0, ctx->stream>>>(N, f, w, w, (T*)nullptr);
         SKTT_LAUNCH_CHECK(ctx);
         SKTT_TRY(blas1_dot(ctx, dtype, N, w, w, slots));
@@ -312,7 +342,7 @@ static int gmres_impl(sktt_ctx* ctx, int dtype, const sktt_local_op* op, int res
         for (int j = 0; j < m && total < max_iters; ++j) {
             T* vj = V + (size_t)j * N;
             T* hcol = H + (size_t)j * (m + 1);
-            SKTT_TRY(local_matvec(ctx, dtype, op, vj, w, mvwork));
+            SKTT_TRY(kop_matvec(ctx, dtype, op, vj, w, mvwork));
             for (int pass = 0; pass < 2; ++pass) {
                 T* hdst = pass == 0 ? hcol : h2;
                 // h = V_{0..j}^H w
@@ -359,25 +389,48 @@ static int gmres_impl(sktt_ctx* ctx, int dtype, const sktt_local_op* op, int res
     return 0;
 }
 
+template <typename T>
+static int krylov_dispatch(sktt_ctx* ctx, int dtype, const sktt_local_op* op_in, int method, int restart, const T* f, T* u,
+                           double tol, int max_iters, T* work, int* iters_host, double* relres_host) {
+    KOp k;
+    k.op = *op_in;
+    k.tiled = false;
+    k.N = local_dim(op_in);
+    const int64_t Nb = local_dim_bound(op_in);
+    int64_t off = local_mv_work(op_in) + solver_core_work(method, restart, Nb);
+    off += off & 1;                                          // keep 16-byte alignment of what follows
+    T* ft = work + off;
+    T* ut = ft + Nb + (Nb & 1);
+    T* image = ut + Nb + (Nb & 1) + 16;
+    if (!k.op.image) SKTT_TRY(sktt_local_op_prepare(ctx, dtype, &k.op, (void*)image));
+    if (k.op.image && k.op.sites == 1 && dtype == SKTT_F64) {
+        // iterate on tiled-layout vectors: convert the right-hand side and the initial guess, convert the result back
+        k.tiled = true;
+        k.N = sktt_fused_tiled_len(k.op.r, k.op.n);
+        SKTT_TRY(sktt_fused_to_tiled(ctx, k.op.r, k.op.n, (const double*)f, (double*)ft));
+        SKTT_TRY(sktt_fused_to_tiled(ctx, k.op.r, k.op.n, (const double*)u, (double*)ut));
+    }
+    const T* fs = k.tiled ? ft : f;
+    T* us = k.tiled ? ut : u;
+    int st = method == 0 ? cg_impl<T>(ctx, dtype, k, fs, us, tol, max_iters, work, iters_host, relres_host)
+                         : gmres_impl<T>(ctx, dtype, k, restart, fs, us, tol, max_iters, work, iters_host, relres_host);
+    if (k.tiled) {
+        int st2 = sktt_fused_from_tiled(ctx, k.op.r, k.op.n, (const double*)us, (double*)u);
+        if (st == 0) st = st2;
+    }
+    return st;
+}
+
 extern "C" int sktt_krylov_solve(sktt_ctx* ctx, int dtype, const sktt_local_op* op, int method, int restart,
                                  const void* f, void* u, double tol, int max_iters, void* work, int* iters_host,
                                  double* relres_host) {
     if (!ctx || !op || !f || !u || !work) return SKTT_ERR_ARG;
     SKTT_TRY(check_dtype(ctx, dtype));
     if (op->sites != 1 && op->sites != 2) return sktt_fail(ctx, SKTT_ERR_ARG, "krylov: sites must be 1 or 2");
-    if (method == 0) {
-        if (dtype == SKTT_F64)
-            return cg_impl<double>(ctx, dtype, op, (const double*)f, (double*)u, tol, max_iters, (double*)work,
-                                   iters_host, relres_host);
-        return cg_impl<cplx>(ctx, dtype, op, (const cplx*)f, (cplx*)u, tol, max_iters, (cplx*)work, iters_host,
-                             relres_host);
-    }
-    if (method == 1) {
-        if (dtype == SKTT_F64)
-            return gmres_impl<double>(ctx, dtype, op, restart, (const double*)f, (double*)u, tol, max_iters,
-                                      (double*)work, iters_host, relres_host);
-        return gmres_impl<cplx>(ctx, dtype, op, restart, (const cplx*)f, (cplx*)u, tol, max_iters, (cplx*)work,
-                                iters_host, relres_host);
-    }
-    return sktt_fail(ctx, SKTT_ERR_ARG, "krylov: unknown method");
+    if (method != 0 && method != 1) return sktt_fail(ctx, SKTT_ERR_ARG, "krylov: unknown method");
+    if (dtype == SKTT_F64)
+        return krylov_dispatch<double>(ctx, dtype, op, method, restart, (const double*)f, (double*)u, tol, max_iters,
+                                       (double*)work, iters_host, relres_host);
+    return krylov_dispatch<cplx>(ctx, dtype, op, method, restart, (const cplx*)f, (cplx*)u, tol, max_iters, (cplx*)work,
+                                 iters_host, relres_host);
 }

@@ -4,6 +4,19 @@
 //   a, c : left solution rank (column side / row side)      a2, c2 : right solution rank
 //   b, b2: operator ranks                                    n, m   : column / row mode index
 #include "common.cuh"
+#include "blas1.cuh"
+
+// fused.cu
+bool sktt_fused_supported(const sktt_ctx* ctx, int dtype, long long r, long long R, long long m, long long n,
+                          long long r2, long long R2);
+long long sktt_fused_image_elems(long long r, long long R, long long m, long long n);
+int sktt_fused_prepare(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* Lst,
+                       const double* A, const double* Rst, double* image);
+int sktt_fused_matvec(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                      const double* v, double* y, double* work);
+long long sktt_fused_tiled_len(long long r, long long n);
+int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                            const double* vt, double* yt, double* T1p);
 
 static inline Idx2 two(long long d, long long s_hi, long long s_lo) { return mk_idx(d, s_hi, s_lo); }
 
@@ -147,6 +160,14 @@ extern "C" int sktt_micro_matvec_als(sktt_ctx* ctx, int dtype, int64_t r, int64_
     size_t es = dtype_size(dtype);
     char* T1 = (char*)work;
     char* T2 = T1 + (size_t)(R * r * n * r2) * es;
+    if (sktt_fused_supported(ctx, dtype, r, R, m, n, r2, R2)) {
+        // stateless call: build the tile images in context scratch, then the two TMA-staged kernels (fused.cu)
+        const size_t img_bytes = (size_t)sktt_fused_image_elems(r, R, m, n) * sizeof(double);
+        SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + img_bytes));
+        double* image = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
+        SKTT_TRY(sktt_fused_prepare(ctx, r, R, m, n, (const double*)Lst, (const double*)A, (const double*)Rst, image));
+        return sktt_fused_matvec(ctx, r, R, m, n, image, (const double*)v, (double*)y, (double*)work);
+    }
     SKTT_TRY(left_step1(ctx, dtype, r, R, n * r2, Lst, v, 0, T1));
     SKTT_TRY(left_step2(ctx, dtype, r, R, m, n, r2, R2, T1, A, T2));
     // y[(c,m),c2] = sum_{(a2,b2)} T2[(c,m),(a2,b2)] Rst[(a2,b2),c2]
@@ -303,4 +324,62 @@ extern "C" int sktt_rank1_update(sktt_ctx* ctx, int dtype, int64_t N, double shi
     else rank1_kernel<cplx><<<blocks, 256, 0, ctx->stream>>>(N, shift, (const cplx*)t, (cplx*)M);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+// ---------------------------------------------------------------------------------- prepared local operators
+extern "C" int64_t sktt_local_matvec_work(const sktt_local_op* op) {
+    if (!op) return -1;
+    if (op->sites == 1) return sktt_stack_op_work(op->r, op->R, op->m, op->n, op->r3, op->R2);
+    return sktt_micro_matvec_mals_work(op->r, op->R, op->m, op->n, op->R2, op->m2, op->n2, op->R3, op->r3);
+}
+
+extern "C" int64_t sktt_local_op_image_size(sktt_ctx* ctx, int dtype, const sktt_local_op* op) {
+    if (!ctx || !op) return -1;
+    if (op->sites != 1) return 0;
+    if (!sktt_fused_supported(ctx, dtype, op->r, op->R, op->m, op->n, op->r3, op->R2)) return 0;
+    return sktt_fused_image_elems(op->r, op->R, op->m, op->n);
+}
+
+extern "C" int sktt_local_op_prepare(sktt_ctx* ctx, int dtype, sktt_local_op* op, void* image) {
+    if (!ctx || !op) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    op->image = nullptr;
+    if (sktt_local_op_image_size(ctx, dtype, op) <= 0) return 0;      // nothing to prepare for this shape
+    if (!image) return sktt_fail(ctx, SKTT_ERR_ARG, "local_op_prepare: image buffer is null");
+    SKTT_TRY(sktt_fused_prepare(ctx, op->r, op->R, op->m, op->n, (const double*)op->Lst, (const double*)op->A1,
+                                (const double*)op->Rst, (double*)image));
+    op->image = image;
+    return 0;
+}
+
+extern "C" int sktt_local_matvec(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* v, void* y, void* work) {
+    if (!ctx || !op || !v || !y || !work) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    if (op->sites == 1) {
+        if (op->image && sktt_fused_supported(ctx, dtype, op->r, op->R, op->m, op->n, op->r3, op->R2))
+            return sktt_fused_matvec(ctx, op->r, op->R, op->m, op->n, (const double*)op->image, (const double*)v,
+                                     (double*)y, (double*)work);
+        return sktt_micro_matvec_als(ctx, dtype, op->r, op->R, op->m, op->n, op->r3, op->R2, op->Lst, op->A1, op->Rst, v,
+                                     y, work);
+    }
+    if (op->sites == 2)
+        return sktt_micro_matvec_mals(ctx, dtype, op->r, op->R, op->m, op->n, op->R2, op->m2, op->n2, op->R3, op->r3,
+                                      op->Lst, op->A1, op->A2, op->Rst, v, y, work);
+    return sktt_fail(ctx, SKTT_ERR_ARG, "local_matvec: sites must be 1 or 2");
+}
+
+extern "C" int64_t sktt_local_op_tiled_len(sktt_ctx* ctx, int dtype, const sktt_local_op* op) {
+    if (!ctx || !op) return -1;
+    if (op->sites != 1 || !op->image) return 0;
+    if (!sktt_fused_supported(ctx, dtype, op->r, op->R, op->m, op->n, op->r3, op->R2)) return 0;
+    return sktt_fused_tiled_len(op->r, op->n);
+}
+
+extern "C" int sktt_local_matvec_tiled(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* vt, void* yt,
+                                       void* work) {
+    if (!ctx || !op || !vt || !yt || !work) return SKTT_ERR_ARG;
+    if (sktt_local_op_tiled_len(ctx, dtype, op) <= 0)
+        return sktt_fail(ctx, SKTT_ERR_ARG, "local_matvec_tiled: operator is not prepared for the tiled path");
+    return sktt_fused_matvec_tiled(ctx, op->r, op->R, op->m, op->n, (const double*)op->image, (const double*)vt,
+                                   (double*)yt, (double*)work);
 }

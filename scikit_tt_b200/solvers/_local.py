@@ -14,14 +14,38 @@ from .. import _device
 # The reference always assembles the dense micro matrix (sle.py:339-345) and LU-factorises it.  We do
 # exactly that while the matrix is small enough to be worth it; beyond DENSE_LIMIT unknowns the same
 # micro system is solved matrix-free (CG when the local operator is Hermitian, GMRES otherwise) to
-# KRYLOV_TOL relative residual.  The reference cannot run in that regime at all.
-DENSE_LIMIT = 8192
+# KRYLOV_TOL true relative residual (residual replacement).  The reference cannot run far beyond this size at all
+# (SURVEY.md 8a, row a4); between 2048 and ~16384 unknowns both routes exist and agree to 1e-8
+# (tests/test_gpu_solvers.py); 'dense' / 'cg' / 'gmres' as `solver` force one of them.
+DENSE_LIMIT = 2048
 KRYLOV_TOL = 1e-14          # target TRUE relative residual of the matrix-free micro solves
 KRYLOV_ACCEPT = 1e-10       # a solve that stagnates above this raises (LU gives no better guarantee on such systems)
 KRYLOV_MAX_ITERS = 20000
 KRYLOV_MAX_CYCLES = 5
 GMRES_RESTART = 60
 _TRACE = bool(int(os.environ.get("SKTT_TRACE", "0")))
+PROFILE = None              # set to a dict to accumulate synchronised wall time per sweep phase (diagnostics only)
+
+
+class phase:
+    """with phase(dev, 'qr'): ...  -- accumulates synchronised wall time into PROFILE when profiling is on."""
+
+    def __init__(self, dev, name):
+        self.dev, self.name = dev, name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            import time
+            self.dev.sync()
+            self.t0 = time.perf_counter()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            import time
+            self.dev.sync()
+            PROFILE[self.name] = PROFILE.get(self.name, 0.0) + time.perf_counter() - self.t0
+            PROFILE[self.name + "#"] = PROFILE.get(self.name + "#", 0) + 1
 
 
 def any_complex(*trains):
@@ -96,7 +120,7 @@ def _krylov_refined(dev, op, f, u, method):
     return relres, total
 
 
-def solve_micro(dev, solver, dense_builder, op, f, guess):
+def solve_micro(dev, solver, dense_builder, op, f, guess, cache=None):
     """Solve the micro system M u = f.  `dense_builder()` returns the dense matrix (destroyed by the LU),
     `op` is the matrix-free description of the same M, `f` / `guess` have the unknown's tensor shape.
     Returns the flat solution [N]."""
@@ -110,14 +134,25 @@ def solve_micro(dev, solver, dense_builder, op, f, guess):
             print(f"  [micro] N={N} dense LU", flush=True)
         return dev.solve(M, f)
     u = guess.reshape(-1).clone() if (guess is not None and guess.numel() == N) else torch.zeros(N, dtype=f.dtype, device=dev.device)
+    dev.prepare_local_op(op)                                  # TMA tile images of (A, Rt) for the fused matvec, once per solve
     method = mode
     if mode == 'krylov':
-        method = 'cg' if is_hermitian_local(dev, op, tuple(f.shape), f.dtype) else 'gmres'
+        # Hermitian-ness of the local operators is inherited from the global operator (the stacks are built with the
+        # conjugate core on the row side): probe the first Krylov micro system of a solver call, reuse the verdict
+        herm = cache.get('hermitian') if cache is not None else None
+        if herm is None:
+            with phase(dev, 'probe'):
+                herm = is_hermitian_local(dev, op, tuple(f.shape), f.dtype)
+            if cache is not None:
+                cache['hermitian'] = herm
+        method = 'cg' if herm else 'gmres'
     if _TRACE:
         print(f"  [micro] N={N} {method}", flush=True)
     relres, iters = _krylov_refined(dev, op, f, u, method)
     if method == 'cg' and mode == 'krylov' and not relres <= KRYLOV_ACCEPT:
         u.zero_()                                             # Hermitian but not definite: CG broke down, use GMRES
+        if cache is not None:
+            cache['hermitian'] = False
         relres, iters = _krylov_refined(dev, op, f, u, 'gmres')
     if not relres <= KRYLOV_ACCEPT:
         raise np.linalg.LinAlgError(f"{method} micro solve did not converge (relative residual {relres:.2e} after {iters} iterations)")

@@ -30,6 +30,7 @@ class _State:
         self.Lrhs, self.Rrhs = [None] * d, [None] * d
         self.one3 = _local.ones(dev, (1, 1, 1), self.dtype)
         self.one2 = _local.ones(dev, (1, 1), self.dtype)
+        self.cache = {}                                  # per-call verdicts shared by the micro solves (see _local.solve_micro)
 
     # sle.py:194-247
     def left(self, i):
@@ -37,8 +38,9 @@ class _State:
         if i == 0:
             self.Lop[i], self.Lrhs[i] = self.one3, self.one2
         else:
-            self.Lop[i] = dev.stack_left_op(self.Lop[i - 1], self.x[i - 1], self.A[i - 1])
-            self.Lrhs[i] = dev.stack_left_rhs(self.Lrhs[i - 1], self.b[i - 1], self.x[i - 1])
+            with _local.phase(dev, 'stacks'):
+                self.Lop[i] = dev.stack_left_op(self.Lop[i - 1], self.x[i - 1], self.A[i - 1])
+                self.Lrhs[i] = dev.stack_left_rhs(self.Lrhs[i - 1], self.b[i - 1], self.x[i - 1])
 
     # sle.py:250-305
     def right(self, i):
@@ -46,8 +48,9 @@ class _State:
         if i == self.d - 1:
             self.Rop[i], self.Rrhs[i] = self.one3, self.one2
         else:
-            self.Rop[i] = dev.stack_right_op(self.Rop[i + 1], self.x[i + 1], self.A[i + 1])
-            self.Rrhs[i] = dev.stack_right_rhs(self.Rrhs[i + 1], self.b[i + 1], self.x[i + 1])
+            with _local.phase(dev, 'stacks'):
+                self.Rop[i] = dev.stack_right_op(self.Rop[i + 1], self.x[i + 1], self.A[i + 1])
+                self.Rrhs[i] = dev.stack_right_rhs(self.Rrhs[i + 1], self.b[i + 1], self.x[i + 1])
 
     def reset(self, x_cores):
         """Restart from another set of device solution cores (bench: same problem, timed repeatedly)."""
@@ -79,13 +82,15 @@ def _run_als(st, repeats, solver):
             st.left(i)
             if i < d - 1:
                 u, (r, n, r2) = _micro_als(st, i, solver)
-                q = dev.qr(u.reshape(r * n, r2))                          # sle.py:517-525
+                with _local.phase(dev, 'qr'):
+                    q = dev.qr(u.reshape(r * n, r2))                      # sle.py:517-525
                 x[i] = q.reshape(r, n, q.shape[1])
         for i in range(d - 1, -1, -1):                                    # second half sweep, sle.py:80-90
             st.right(i)
             u, (r, n, r2) = _micro_als(st, i, solver)
             if i > 0:
-                q = dev.rq(u.reshape(r, n * r2))                          # sle.py:533-541
+                with _local.phase(dev, 'qr'):
+                    q = dev.rq(u.reshape(r, n * r2))                      # sle.py:533-541
                 x[i] = q.reshape(q.shape[0], n, r2)
             else:
                 x[i] = u.reshape(r, n, r2)                                # sle.py:546
@@ -94,11 +99,13 @@ def _run_als(st, repeats, solver):
 def _micro_als(st, i, solver):
     dev = st.dev
     L, R, A = st.Lop[i], st.Rop[i], st.A[i]
-    f = dev.micro_rhs_als(st.Lrhs[i], st.b[i], st.Rrhs[i])                # sle.py:424-428
+    with _local.phase(dev, 'micro_rhs'):
+        f = dev.micro_rhs_als(st.Lrhs[i], st.b[i], st.Rrhs[i])            # sle.py:424-428
     r, n, r2 = L.shape[0], A.shape[2], R.shape[0]
     op = dev.local_op(L, A, R)
     guess = st.x[i] if tuple(st.x[i].shape) == (r, n, r2) else None
-    u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_als(L, A, R), op, f, guess)
+    with _local.phase(dev, 'solve'):
+        u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_als(L, A, R), op, f, guess, st.cache)
     return u, (r, n, r2)
 
 
@@ -142,5 +149,6 @@ def _micro_mals(st, i, solver):
     if xi.dim() == 3 and xj.dim() == 3 and xi.shape[0] == r and xj.shape[2] == r3 and xi.shape[2] == xj.shape[0] \
             and r * n * n2 * r3 > _local.DENSE_LIMIT:
         guess = dev.matmul(xi.reshape(r * n, xi.shape[2]), xj.reshape(xj.shape[0], n2 * r3))
-    u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_mals(L, A1, A2, R), op, f.reshape(r, n, n2, r3), guess)
+    u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_mals(L, A1, A2, R), op, f.reshape(r, n, n2, r3), guess,
+                           st.cache)
     return u, (r, n, n2, r3)

@@ -105,6 +105,40 @@ def test_stacks_and_micro_systems(dev, cplx, shape):
         assert relerr((Mref @ v.reshape(-1)).reshape(yref.shape), yref) < 1e-12
 
 
+@pytest.mark.parametrize("shape", [(64, 3, 64, 64, 3), (32, 3, 64, 64, 3), (8, 2, 32, 64, 3), (4, 5, 96, 64, 3),
+                                   (128, 3, 32, 64, 3), (20, 1, 64, 64, 3)])
+def test_fused_matvec_path_matches_generic_chain_and_oracle(dev, shape):
+    """Shapes covered by the two-kernel fused matvec (fused.cu): against the oracle and against the generic chain."""
+    r, R, n, r2, R2 = shape
+    rng = np.random.default_rng(5 + r + n)
+    L, Rt = rnd(rng, (r, R, r), False), rnd(rng, (r2, R2, r2), False)
+    v, A = rnd(rng, (r, n, r2), False), rnd(rng, (R, n, n, R2), False)
+    dL, dR, dv, dA = map(dev.to_device, (L, Rt, v, A))
+    yref = K.micro_matvec_als(L, A, Rt, v)
+    l0 = dev.launches()
+    y_fused = host(dev.micro_matvec_als(dL, dA, dR, dv))
+    assert dev.launches() - l0 == 5                      # stateless: image build, to-tiled, 2 fused kernels, from-tiled
+    op = dev.local_op(dL, dA, dR, prepare=True)
+    assert op.image is not None
+    y_prepared = host(dev.local_matvec(op, dv))
+    assert relerr(y_prepared, yref) < 2e-13
+    # the Krylov inner step: vectors in the tiled layout [n][a][r2 + 4], two kernel launches
+    vt = np.zeros((n, r, r2 + 4))
+    vt[:, :, :r2] = v.transpose(1, 0, 2)
+    l0 = dev.launches()
+    yt = host(dev.local_matvec_tiled(op, dev.to_device(vt.reshape(-1)))).reshape(n, r, r2 + 4)
+    assert dev.launches() - l0 == 2
+    assert relerr(yt[:, :, :r2].transpose(1, 0, 2), yref) < 2e-13
+    assert np.all(yt[:, :, r2:] == 0.0)
+    dev.set_gemm_mode(1)
+    try:
+        y_generic = host(dev.micro_matvec_als(dL, dA, dR, dv))
+    finally:
+        dev.set_gemm_mode(0)
+    assert relerr(y_fused, yref) < 2e-13
+    assert relerr(y_generic, yref) < 2e-13
+
+
 @pytest.mark.parametrize("cplx", [False, True])
 def test_two_site_micro_systems(dev, cplx):
     rng = np.random.default_rng(23 + cplx)
