@@ -100,6 +100,11 @@ def _krylov_refined(dev, op, f, u, method):
         relres = dev.nrm2(res) / fnorm
         if _TRACE:
             print(f"    [krylov] {method} cycle {cycle}: true relres {relres:.3e} after {total} iterations", flush=True)
+        if cycle == 0 and not relres < 1.0:
+            # a warm start that is worse than the zero vector (e.g. a guess core carrying the norm of a random tensor,
+            # 1e57 at the bench shape) would make the Krylov solver spend its accuracy on cancelling the guess
+            u.zero_()
+            relres, res = 1.0, f.reshape(-1)
         if relres <= KRYLOV_TOL or relres > 0.5 * prev:
             break
         prev = relres
