@@ -59,6 +59,10 @@ const char* sktt_last_error(sktt_ctx* ctx);
 int64_t sktt_launch_count(sktt_ctx* ctx);
 /* force a kernel family: 0 auto, 1 SIMT DFMA tiles only, 2 DMMA tensor tiles where legal */
 int sktt_ctx_set_gemm_mode(sktt_ctx* ctx, int mode);
+/* diagnostics (tools/ only): kernels that support it leave per-phase %globaltimer stamps in the context's scalar
+ * scratch area; sktt_scratch_peek synchronises the stream and copies a piece of that area to the host           */
+int sktt_ctx_set_debug(sktt_ctx* ctx, int on);
+int sktt_scratch_peek(sktt_ctx* ctx, int64_t byte_offset, int64_t bytes, void* out_host);
 
 /* ------------------------------------------------------------------ generic contraction ------
  * C[cm(i) + cn(j)] = alpha * sum_k opA(A[am(i) + ak(k)]) * opB(B[bk(k) + bn(j)]) + beta * C[..]
@@ -213,6 +217,13 @@ int64_t sktt_krylov_work(const sktt_local_op* op, int method, int restart);
 int sktt_krylov_solve(sktt_ctx* ctx, int dtype, const sktt_local_op* op, int method, int restart,
                       const void* f, void* u, double tol, int max_iters, void* work,
                       int* iters_host, double* relres_host);
+/* The whole micro solve of sle.__update_core_als (scikit_tt/solvers/sle.py:505-509) in one call for operators the
+ * fused matvec covers (f64, one site; SKTT_ERR_ARG otherwise): warm start u (dropped if worse than zero), CG, true
+ * residual f - M u recomputed and CG restarted from it until |f - M u| <= tol |f| or it stops improving.
+ * relres_host receives the TRUE relative residual; work as for sktt_krylov_solve (method 0).                      */
+int sktt_krylov_solve_refined(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* f, void* u,
+                              double tol, int max_iters, int max_cycles, void* work, int* iters_host,
+                              double* relres_host, int* cycles_host);
 
 /* ------------------------------------------------------------------ orthonormalisation -------
  * scipy.linalg.qr(mode='economic') in sle.__update_core_als (scikit_tt/solvers/sle.py:517-525):

@@ -64,6 +64,15 @@ class Device:
     def sync(self):
         torch.cuda.synchronize(self.device)
 
+    def set_debug(self, on):
+        self._check(self.lib.sktt_ctx_set_debug(self.h, int(bool(on))))
+
+    def scratch_peek(self, byte_offset, count, ctype=C.c_uint64):
+        """Diagnostics: `count` items of `ctype` from the scalar scratch area of the context (synchronises)."""
+        buf = (ctype * count)()
+        self._check(self.lib.sktt_scratch_peek(self.h, int(byte_offset), C.sizeof(buf), buf))
+        return list(buf)
+
     def work(self, n, dtype, tag="w"):
         """Reusable scratch tensor of at least n elements."""
         key = (tag, dtype)
@@ -289,6 +298,17 @@ class Device:
         st = self.lib.sktt_krylov_solve(self.h, dtype_code(f), C.byref(op), meth, restart, _ptr(f), _ptr(u), float(tol),
                                         int(max_iters), _ptr(w), C.byref(iters), C.byref(relres))
         return st, iters.value, relres.value
+
+    def krylov_solve_refined(self, op, f, u, tol=1e-14, max_iters=20000, max_cycles=5):
+        """The whole matrix-free micro solve in one C call (prepared one-site f64 operators only): warm start, CG, true
+        residual checks with restarts.  u is overwritten.  Returns (status, iterations, true relres, cycles)."""
+        nwork = self.lib.sktt_krylov_work(C.byref(op), 0, 0)
+        w = self.work(nwork, f.dtype, tag="krylov")
+        iters, relres, cycles = C.c_int(0), C.c_double(0.0), C.c_int(0)
+        st = self.lib.sktt_krylov_solve_refined(self.h, dtype_code(f), C.byref(op), _ptr(f), _ptr(u), float(tol),
+                                                int(max_iters), int(max_cycles), _ptr(w), C.byref(iters), C.byref(relres),
+                                                C.byref(cycles))
+        return st, iters.value, relres.value, cycles.value
 
     # ------------------------------------------------------------------ orthonormalisation
     def qr(self, A, want_r=False):

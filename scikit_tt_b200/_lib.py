@@ -35,6 +35,8 @@ SIGNATURES = {
     "sktt_last_error": (C.c_char_p, [vp]),
     "sktt_launch_count": (i64, [vp]),
     "sktt_ctx_set_gemm_mode": (i32, [vp, i32]),
+    "sktt_ctx_set_debug": (i32, [vp, i32]),
+    "sktt_scratch_peek": (i32, [vp, i64, i64, vp]),
     "sktt_gemm2": (i32, [vp, i32, i64, i64, i64, pdbl, vp, Idx2, Idx2, i32, vp, Idx2, Idx2, i32, pdbl, vp, Idx2, Idx2]),
     "sktt_stack_op_work": (i64, [i64] * 6),
     "sktt_stack_left_op": (i32, [vp, i32] + [i64] * 6 + [vp] * 5 + [i32]),
@@ -63,6 +65,7 @@ SIGNATURES = {
     "sktt_local_matvec_tiled": (i32, [vp, i32, C.POINTER(LocalOp), vp, vp, vp]),
     "sktt_krylov_work": (i64, [C.POINTER(LocalOp), i32, i32]),
     "sktt_krylov_solve": (i32, [vp, i32, C.POINTER(LocalOp), i32, i32, vp, vp, dbl, i32, vp, pint, pdbl]),
+    "sktt_krylov_solve_refined": (i32, [vp, i32, C.POINTER(LocalOp), vp, vp, dbl, i32, i32, vp, pint, pdbl, pint]),
     "sktt_qr_work": (i64, [i64, i64]),
     "sktt_qr_left": (i32, [vp, i32, i64, i64, vp, vp, vp, vp]),
     "sktt_rq_right": (i32, [vp, i32, i64, i64, vp, vp, vp, vp]),

@@ -14,6 +14,7 @@ struct sktt_ctx {
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
     int gemm_mode = 0;
+    int debug = 0;          // kernels that support it leave phase time stamps in the scalar scratch area
     int sm_count = 148;
     char err[512] = {0};
     // small persistent device scratch (scalars, flags, split-K partials)
@@ -21,6 +22,8 @@ struct sktt_ctx {
     size_t scratch_bytes = 0;
     // pinned host mailbox for scalar read-backs
     void* mailbox = nullptr;
+    // two reusable events for the lagged convergence checks of the Krylov loops
+    cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 
 static inline int sktt_fail(sktt_ctx* ctx, int code, const char* fmt, const char* a = "") {

@@ -28,6 +28,11 @@ extern "C" int sktt_ctx_create(int device, void* cuda_stream, sktt_ctx** out) {
         delete ctx;
         return SKTT_ERR_CUDA;
     }
+    for (int i = 0; i < 2; ++i)
+        if (cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return SKTT_ERR_CUDA;
+        }
     *out = ctx;
     return sktt_scratch_reserve(ctx, 8 << 20);
 }
@@ -38,6 +43,8 @@ extern "C" int sktt_ctx_destroy(sktt_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
     return 0;
 }
@@ -53,6 +60,20 @@ extern "C" int64_t sktt_launch_count(sktt_ctx* ctx) { return ctx ? ctx->launches
 extern "C" int sktt_ctx_set_gemm_mode(sktt_ctx* ctx, int mode) {
     if (!ctx || mode < 0 || mode > 2) return SKTT_ERR_ARG;
     ctx->gemm_mode = mode;
+    return 0;
+}
+
+// diagnostics: switch kernel time stamps on/off, read a piece of the scalar scratch area (after a stream sync)
+extern "C" int sktt_ctx_set_debug(sktt_ctx* ctx, int on) {
+    if (!ctx) return SKTT_ERR_ARG;
+    ctx->debug = on ? 1 : 0;
+    return 0;
+}
+extern "C" int sktt_scratch_peek(sktt_ctx* ctx, int64_t byte_offset, int64_t bytes, void* out_host) {
+    if (!ctx || !out_host || byte_offset < 0 || bytes < 0 || (size_t)(byte_offset + bytes) > ctx->scratch_bytes)
+        return SKTT_ERR_ARG;
+    SKTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SKTT_CUDA(ctx, cudaMemcpy(out_host, (char*)ctx->scratch + byte_offset, (size_t)bytes, cudaMemcpyDeviceToHost));
     return 0;
 }
 

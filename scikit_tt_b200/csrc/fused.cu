@@ -64,6 +64,19 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 constexpr int CONSUMER_WARPS = 16;
 constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;   // + one producer warp
 
+}  // namespace
+
+// optional fused reductions / early exit of the Krylov step that owns the matvec (see sktt_fused_matvec_tiled_dots)
+struct MvDots {
+    const double* d;       // vector (tiled layout) to reduce against, or nullptr
+    double* part;          // [2 * CTAs] per-CTA partials
+    unsigned* counter;     // arrival counter (zero between launches)
+    double* out;           // out[0] = <y, d>, out[1] = <d, d>
+    const int* skip;       // if non-null and *skip != 0 the kernels return at once
+};
+
+namespace {
+
 // ------------------------------------------------------------------------------------------------ stage 1
 // T1[(b,c), n, a2] = sum_a L[a,(b,c)] v[a,n,a2].  One CTA per (n, tile of 96 rows (b,c)).  Both operand tiles are
 // contiguous in global memory: the L tile comes from the prepared image Limg[mtile][a][S1_LDA] and the v tile from the
@@ -79,8 +92,9 @@ __host__ __device__ inline size_t s1_smem_bytes(int K1) {
 
 __global__ void __launch_bounds__(THREADS)
 mv_stage1_kernel(const double* __restrict__ Limg, const double* __restrict__ vt, double* __restrict__ T1p, int M1,
-                 int K1, int ntot) {
+                 int K1, int ntot, const int* __restrict__ skip) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (skip && *skip) return;                              // Krylov loop already converged (uniform over the grid)
     double* As = reinterpret_cast<double*>(smem_raw);     // [K1][S1_LDA]
     double* Bs = As + (size_t)K1 * S1_LDA;                 // [K1][S1_LDB]
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + s1_smem_bytes(K1) - 64);   // [S1_GROUPS]
@@ -251,10 +265,11 @@ __global__ void from_tiled_kernel(const double* __restrict__ src, double* __rest
 template <int RB, int NA, int MB>
 __global__ void __launch_bounds__(THREADS)
 mv_stage23_kernel(const double* __restrict__ T1p, const double* __restrict__ Aimg, const double* __restrict__ Rimg,
-                  double* __restrict__ Y, int r, int R, int mtot, int ntot) {
+                  double* __restrict__ Y, int r, int R, int mtot, int ntot, MvDots dots) {
     using P = S23<RB, NA, MB>;
     constexpr int KC = P::KC, LDB = P::LDB, LDA = P::LDA, LDT = P::LDT, STAGES = P::STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (dots.skip && *dots.skip) return;
     double* ring = reinterpret_cast<double*>(smem_raw);
     double* T2s = ring + (size_t)STAGES * P::SLOT;
     unsigned long long* full = reinterpret_cast<unsigned long long*>(T2s + (size_t)MB * LDT);
@@ -395,6 +410,7 @@ mv_stage23_kernel(const double* __restrict__ T1p, const double* __restrict__ Aim
             }
     }
     consumer_bar_sync();
+    double s_yd = 0.0, s_dd = 0.0;
     if (khalf == 0) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -404,8 +420,64 @@ mv_stage23_kernel(const double* __restrict__ T1p, const double* __restrict__ Aim
                 const int c2 = wn0 + 8 * j + 2 * fk;
                 const double2 o = *reinterpret_cast<const double2*>(red + (size_t)tile * 256 + (size_t)(8 * i + fr) * 16 +
                                                                     8 * j + 2 * fk);
-                *reinterpret_cast<double2*>(Y + ((size_t)m * r + c) * LDB + c2) =      // tiled vector layout
-                    make_double2(acc3[i][j][0] + o.x, acc3[i][j][1] + o.y);
+                const double2 y = make_double2(acc3[i][j][0] + o.x, acc3[i][j][1] + o.y);
+                const size_t idx = ((size_t)m * r + c) * LDB + c2;                       // tiled vector layout
+                *reinterpret_cast<double2*>(Y + idx) = y;
+                if (dots.d) {
+                    const double2 dv = *reinterpret_cast<const double2*>(dots.d + idx);
+                    s_yd = fma(y.x, dv.x, fma(y.y, dv.y, s_yd));
+                    s_dd = fma(dv.x, dv.x, fma(dv.y, dv.y, s_dd));
+                }
+            }
+        }
+    }
+    // fused reductions of the Krylov step: out[0] = <y, d>, out[1] = <d, d>; per-CTA partials are combined in a fixed
+    // order by the last CTA to finish, so the sums are bit-reproducible
+    if (dots.d) {
+        double* wred = ring + 8 * 256;                     // [8 warps][2], disjoint from the K-half buffer above
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s_yd += __shfl_xor_sync(0xffffffffu, s_yd, o);
+            s_dd += __shfl_xor_sync(0xffffffffu, s_dd, o);
+        }
+        if (khalf == 0 && lane == 0) {
+            wred[2 * tile] = s_yd;
+            wred[2 * tile + 1] = s_dd;
+        }
+        consumer_bar_sync();
+        if (warp == 0) {
+            const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+            unsigned done = 0;
+            if (lane == 0) {
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    a += wred[2 * t];
+                    b += wred[2 * t + 1];
+                }
+                dots.part[2 * cta] = a;
+                dots.part[2 * cta + 1] = b;
+                __threadfence();
+                done = atomicAdd(dots.counter, 1u);
+            }
+            done = __shfl_sync(0xffffffffu, done, 0);
+            if (done == (unsigned)ncta - 1) {
+                __threadfence();
+                double a = 0.0, b = 0.0;
+                for (int t = lane; t < ncta; t += 32) {
+                    a += __ldcg(dots.part + 2 * t);
+                    b += __ldcg(dots.part + 2 * t + 1);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                }
+                if (lane == 0) {
+                    dots.out[0] = a;
+                    dots.out[1] = b;
+                    *dots.counter = 0;
+                }
             }
         }
     }
@@ -464,9 +536,12 @@ int sktt_fused_from_tiled(sktt_ctx* ctx, long long r, long long n, const double*
     return 0;
 }
 
-// yt = M vt on vectors in the tiled layout; T1p: R * r * n * (r2 + 4) doubles of scratch.
-int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
-                            const double* vt, double* yt, double* T1p) {
+// yt = M vt on vectors in the tiled layout; T1p: R * r * n * (r2 + 4) doubles of scratch.  With dvec the second kernel
+// also leaves <yt, dvec> and <dvec, dvec> in dots_out[0..1] (dot_part: 2 * r * m / 32 doubles, counter zeroed once);
+// with skip the launches are no-ops once *skip != 0.
+int sktt_fused_matvec_tiled_dots(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                                 const double* vt, double* yt, double* T1p, const double* dvec, double* dot_part,
+                                 unsigned* counter, double* dots_out, const int* skip) {
     const int M1 = (int)(R * r), K1 = (int)r;
     const size_t smem1 = s1_smem_bytes(K1);
     static bool configured = false;
@@ -478,13 +553,19 @@ int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m
     }
     const long long na = img_a_elems(R, m, n), nr = img_r_elems();
     dim3 g1((unsigned)n, (unsigned)((M1 + S1_BM - 1) / S1_BM));
-    mv_stage1_kernel<<<g1, THREADS, smem1, ctx->stream>>>(image + na + nr, vt, T1p, M1, K1, (int)n);
+    mv_stage1_kernel<<<g1, THREADS, smem1, ctx->stream>>>(image + na + nr, vt, T1p, M1, K1, (int)n, skip);
     SKTT_LAUNCH_CHECK(ctx);
     dim3 g2((unsigned)r, (unsigned)(m / 32));
+    MvDots dots{dvec, dot_part, counter, dots_out, skip};
     mv_stage23_kernel<3, 64, 32><<<g2, THREADS, Cfg::SMEM, ctx->stream>>>(T1p, image, image + na, yt, (int)r, (int)R,
-                                                                           (int)m, (int)n);
+                                                                           (int)m, (int)n, dots);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                            const double* vt, double* yt, double* T1p) {
+    return sktt_fused_matvec_tiled_dots(ctx, r, R, m, n, image, vt, yt, T1p, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 // natural-layout wrapper: v [r][n][64] -> y [r][m][64]; work holds T1p followed by the two tiled vectors

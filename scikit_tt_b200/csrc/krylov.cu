@@ -14,6 +14,9 @@ int sktt_fused_to_tiled(sktt_ctx* ctx, long long r, long long n, const double* s
 int sktt_fused_from_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst);
 int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
                             const double* vt, double* yt, double* T1p);
+int sktt_fused_matvec_tiled_dots(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                                 const double* vt, double* yt, double* T1p, const double* dvec, double* dot_part,
+                                 unsigned* counter, double* dots_out, const int* skip);
 
 // The operator as the Krylov loops see it: either the generic contraction chain on natural-layout vectors, or the
 // prepared fused matvec on tiled-layout vectors (all Krylov vectors then live in that layout; padding stays zero).
@@ -50,7 +53,7 @@ static int64_t local_image_bound(const sktt_local_op* op) {
 
 // elements used by the solver proper (vectors of length Nb + small state), excluding matvec scratch
 static int64_t solver_core_work(int method, int restart, int64_t Nb) {
-    if (method == 0) return 3 * Nb + 64;                                  // r, p, Ap
+    if (method == 0) return 4 * Nb + 64;                                  // r, p, Ap (+ s of the fused variant)
     int64_t m = restart > 0 ? restart : 40;
     return (m + 2) * Nb + (m + 1) * (m + 4) + 4 * (m + 2) + 64;            // V, w, H, givens, g, y, h2
 }
@@ -212,6 +215,195 @@ static int cg_impl(sktt_ctx* ctx, int dtype, const KOp& op, const T* f, T* u, do
     if (iters_host) *iters_host = launched;
     if (relres_host) *relres_host = sqrt(rr / fnorm2);
     if (!(rr <= target2)) return sktt_fail(ctx, SKTT_ERR_NOCONV, "cg: no convergence within max_iters");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CG on the prepared (tiled) operator in the Chronopoulos-Gear form: ONE synchronisation point per iteration.  The matvec
+// w = A r leaves delta = <w, r> and gamma = <r, r> behind (fused into the epilogue of its second kernel), and one vector
+// kernel derives alpha, beta from them and updates p, s = A p, x, r.  Three launches per iteration; a converged solve
+// raises a device flag that turns every later launch of the batch into a no-op, so the host only looks at a pinned
+// mailbox one batch behind.
+//   state (doubles in ctx->scratch): [8] delta, [9] gamma (matvec output) | [12 + 2 k] gamma_old, alpha_old ping-pong
+//   ints at byte 192: [0] done, [1] iterations, [2] breakdown
+// ------------------------------------------------------------------------------------------------
+__global__ void cgear_update_kernel(long long n, double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
+                                    double* __restrict__ s, const double* __restrict__ w, const double* dots,
+                                    const double* st_cur, double* st_next, int* flags, double target2) {
+    if (flags[0]) return;
+    const double delta = dots[0], gamma = dots[1];
+    const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+    if (gamma <= target2) {                       // x already solves the system to the requested accuracy
+        if (lead) flags[0] = 1;
+        return;
+    }
+    const double gamma_old = st_cur[0], alpha_old = st_cur[1];
+    const bool first = gamma_old < 0.0;
+    const double beta = first ? 0.0 : gamma / gamma_old;
+    const double denom = first ? delta : delta - beta * gamma / alpha_old;
+    if (!(denom > 0.0)) {                         // p^H A p <= 0: not Hermitian positive definite
+        if (lead) {
+            flags[2] = 1;
+            flags[0] = 1;
+        }
+        return;
+    }
+    const double alpha = gamma / denom;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double ri = r[i];
+        const double pi = fma(beta, p[i], ri);
+        const double si = fma(beta, s[i], w[i]);
+        p[i] = pi;
+        s[i] = si;
+        x[i] = fma(alpha, pi, x[i]);
+        r[i] = fma(-alpha, si, ri);
+    }
+    if (lead) {
+        st_next[0] = gamma;
+        st_next[1] = alpha;
+        flags[1] += 1;
+    }
+}
+
+// Work layout of the tiled CG (doubles): matvec scratch | r | p | w | s
+struct CgTiledBufs {
+    double *mvwork, *r, *p, *w, *s;
+};
+static CgTiledBufs cg_tiled_bufs(const KOp& op, double* work) {
+    CgTiledBufs b;
+    b.mvwork = work;
+    b.r = work + local_mv_work(&op.op);
+    b.p = b.r + op.N;
+    b.w = b.p + op.N;
+    b.s = b.w + op.N;
+    return b;
+}
+
+// The CG loop proper: on entry b.r holds the residual of u (tiled layout); iterates until <r, r> <= target2 by the
+// recurrence, u updated in place.  iters_host accumulates.
+static int cg_tiled_core(sktt_ctx* ctx, const KOp& op, const CgTiledBufs& b, double* u, double target2, int max_iters,
+                         int* iters_host, double* rr_host) {
+    const long long N = op.N;
+    double* slots = (double*)ctx->scratch;
+    double* dots = slots + 8;
+    double* st = slots + 12;                                   // [2][2]
+    int* flags = (int*)((char*)ctx->scratch + 192);
+    unsigned* counter = (unsigned*)((char*)ctx->scratch + SKTT_SCRATCH_COUNTER_OFF) + 8;
+    double* dpart = (double*)((char*)ctx->scratch + SKTT_SCRATCH_PARTIAL_OFF) + 2 * SKTT_DOT_MAX_BLOCKS;
+    double* mbox = (double*)ctx->mailbox;
+    const int nb = ew_blocks(ctx, N);
+    const sktt_local_op& o = op.op;
+    SKTT_CUDA(ctx, cudaMemsetAsync(b.p, 0, (size_t)3 * N * sizeof(double), ctx->stream));      // p, w, s
+    const double init_state[4] = {-1.0, 0.0, -1.0, 0.0};
+    memcpy(mbox + 32, init_state, sizeof(init_state));
+    SKTT_CUDA(ctx, cudaMemcpyAsync(st, mbox + 32, sizeof(init_state), cudaMemcpyHostToDevice, ctx->stream));
+    SKTT_CUDA(ctx, cudaMemsetAsync(flags, 0, 4 * sizeof(int), ctx->stream));
+    const int batch = 4;
+    int status = 0, launched = 0, batches = 0;
+    bool finished = false;
+    int* mflags = (int*)(mbox + 16);                           // [2][4] ints
+    while (!finished && launched <= max_iters) {
+        const int slot = batches & 1;
+        for (int q = 0; q < batch && launched <= max_iters; ++q, ++launched) {
+            status = sktt_fused_matvec_tiled_dots(ctx, o.r, o.R, o.m, o.n, (const double*)o.image, b.r, b.w, b.mvwork, b.r,
+                                                  dpart, counter, dots, flags);
+            if (status) break;
+            cgear_update_kernel<<<nb, 256, 0, ctx->stream>>>(N, u, b.r, b.p, b.s, b.w, dots, st + 2 * (launched & 1),
+                                                             st + 2 * ((launched + 1) & 1), flags, target2);
+            ctx->launches++;
+        }
+        if (status) break;
+        cudaMemcpyAsync(mflags + 4 * slot, flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(ctx->ev[slot], ctx->stream);
+        if (batches >= 1) {                                    // look at the batch queued before this one
+            const int prev = (batches - 1) & 1;
+            cudaEventSynchronize(ctx->ev[prev]);
+            if (mflags[4 * prev]) finished = true;
+        }
+        ++batches;
+    }
+    if (status) return status;
+    SKTT_CUDA(ctx, cudaMemcpyAsync(mbox, dots, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SKTT_CUDA(ctx, cudaMemcpyAsync(mflags, flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SKTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (iters_host) *iters_host += mflags[1];
+    if (rr_host) *rr_host = mbox[1];
+    if (mflags[2]) return sktt_fail(ctx, SKTT_ERR_NOCONV, "cg: operator is not Hermitian positive definite (p^H A p <= 0)");
+    if (!mflags[0]) return sktt_fail(ctx, SKTT_ERR_NOCONV, "cg: no convergence within max_iters");
+    return 0;
+}
+
+// r = f - A u and the two squared norms the drivers need, one host synchronisation: returns |f|^2 and |r|^2
+static int cg_tiled_residual(sktt_ctx* ctx, const KOp& op, const CgTiledBufs& b, const double* f, const double* u,
+                             double* fnorm2, double* rr) {
+    const long long N = op.N;
+    const sktt_local_op& o = op.op;
+    double* slots = (double*)ctx->scratch;
+    double* mbox = (double*)ctx->mailbox;
+    const int nb = ew_blocks(ctx, N);
+    if (fnorm2) SKTT_TRY(blas1_dot(ctx, SKTT_F64, N, f, f, slots + 5));
+    SKTT_TRY(sktt_fused_matvec_tiled(ctx, o.r, o.R, o.m, o.n, (const double*)o.image, u, b.w, b.mvwork));
+    residual_init_kernel<double><<<nb, 256, 0, ctx->stream>>>(N, f, b.w, b.r, (double*)nullptr);
+    SKTT_LAUNCH_CHECK(ctx);
+    SKTT_TRY(blas1_dot(ctx, SKTT_F64, N, b.r, b.r, slots + 2));
+    SKTT_CUDA(ctx, cudaMemcpyAsync(mbox, slots, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SKTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (fnorm2) *fnorm2 = mbox[5];
+    *rr = mbox[2];
+    return 0;
+}
+
+static int cg_tiled_impl(sktt_ctx* ctx, const KOp& op, const double* f, double* u, double tol, int max_iters,
+                         double* work, int* iters_host, double* relres_host) {
+    const CgTiledBufs b = cg_tiled_bufs(op, work);
+    double fnorm2 = 0.0, rr = 0.0;
+    SKTT_TRY(cg_tiled_residual(ctx, op, b, f, u, &fnorm2, &rr));
+    if (iters_host) *iters_host = 0;
+    if (fnorm2 == 0.0) {
+        SKTT_CUDA(ctx, cudaMemsetAsync(u, 0, (size_t)op.N * sizeof(double), ctx->stream));
+        if (relres_host) *relres_host = 0.0;
+        return 0;
+    }
+    int st = cg_tiled_core(ctx, op, b, u, tol * tol * fnorm2, max_iters, iters_host, &rr);
+    if (relres_host) *relres_host = sqrt(rr / fnorm2);
+    return st;
+}
+
+// Whole micro solve on the prepared operator: warm start (dropped when it is worse than the zero vector), CG, then the
+// TRUE residual f - A u is recomputed and CG restarted from it until that residual is below tol * |f| or stops improving
+// (the eps * cond floor any backward-stable solver, LU included, ends at).  A handful of host synchronisations per solve.
+static int cg_tiled_refined(sktt_ctx* ctx, const KOp& op, const double* f, double* u, double tol, int max_iters,
+                            int max_cycles, double* work, int* iters_host, double* relres_host, int* cycles_host) {
+    const CgTiledBufs b = cg_tiled_bufs(op, work);
+    const long long N = op.N;
+    double fnorm2 = 0.0, rr = 0.0;
+    SKTT_TRY(cg_tiled_residual(ctx, op, b, f, u, &fnorm2, &rr));
+    if (iters_host) *iters_host = 0;
+    if (cycles_host) *cycles_host = 0;
+    if (fnorm2 == 0.0) {
+        SKTT_CUDA(ctx, cudaMemsetAsync(u, 0, (size_t)N * sizeof(double), ctx->stream));
+        if (relres_host) *relres_host = 0.0;
+        return 0;
+    }
+    if (!(rr < fnorm2)) {                                      // the warm start is no better than zero: drop it
+        SKTT_CUDA(ctx, cudaMemsetAsync(u, 0, (size_t)N * sizeof(double), ctx->stream));
+        SKTT_CUDA(ctx, cudaMemcpyAsync(b.r, f, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        rr = fnorm2;
+    }
+    double prev = 1e300, relres = sqrt(rr / fnorm2);
+    int status = 0;
+    for (int cycle = 0; cycle < max_cycles; ++cycle) {
+        if (relres <= tol || relres > 0.5 * prev) break;
+        prev = relres;
+        double rr_rec = 0.0;
+        status = cg_tiled_core(ctx, op, b, u, 0.25 * tol * tol * fnorm2, max_iters, iters_host, &rr_rec);
+        if (status != 0 && status != SKTT_ERR_NOCONV) return status;
+        SKTT_TRY(cg_tiled_residual(ctx, op, b, f, u, nullptr, &rr));
+        relres = sqrt(rr / fnorm2);
+        if (cycles_host) *cycles_host = cycle + 1;
+        if (status == SKTT_ERR_NOCONV) break;                  // breakdown / iteration limit: judged by the true residual
+    }
+    if (relres_host) *relres_host = relres;
     return 0;
 }
 
@@ -412,7 +604,11 @@ static int krylov_dispatch(sktt_ctx* ctx, int dtype, const sktt_local_op* op_in,
     }
     const T* fs = k.tiled ? ft : f;
     T* us = k.tiled ? ut : u;
-    int st = method == 0 ? cg_impl<T>(ctx, dtype, k, fs, us, tol, max_iters, work, iters_host, relres_host)
+    int st;
+    if (method == 0 && k.tiled)
+        st = cg_tiled_impl(ctx, k, (const double*)fs, (double*)us, tol, max_iters, (double*)work, iters_host, relres_host);
+    else
+        st = method == 0 ? cg_impl<T>(ctx, dtype, k, fs, us, tol, max_iters, work, iters_host, relres_host)
                          : gmres_impl<T>(ctx, dtype, k, restart, fs, us, tol, max_iters, work, iters_host, relres_host);
     if (k.tiled) {
         int st2 = sktt_fused_from_tiled(ctx, k.op.r, k.op.n, (const double*)us, (double*)u);
@@ -433,4 +629,32 @@ extern "C" int sktt_krylov_solve(sktt_ctx* ctx, int dtype, const sktt_local_op* 
                                        (double*)work, iters_host, relres_host);
     return krylov_dispatch<cplx>(ctx, dtype, op, method, restart, (const cplx*)f, (cplx*)u, tol, max_iters, (cplx*)work,
                                  iters_host, relres_host);
+}
+
+// One-call micro solve for operators the fused matvec covers (real, one-site, prepared shapes): see cg_tiled_refined.
+// Returns SKTT_ERR_ARG with "unsupported" when the operator is not covered; the caller then drives sktt_krylov_solve.
+extern "C" int sktt_krylov_solve_refined(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* f, void* u,
+                                         double tol, int max_iters, int max_cycles, void* work, int* iters_host,
+                                         double* relres_host, int* cycles_host) {
+    if (!ctx || !op || !f || !u || !work) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    if (dtype != SKTT_F64 || op->sites != 1) return sktt_fail(ctx, SKTT_ERR_ARG, "krylov_solve_refined: unsupported operator");
+    KOp k;
+    k.op = *op;
+    const int64_t Nb = local_dim_bound(op);
+    int64_t off = local_mv_work(op) + solver_core_work(0, 0, Nb);
+    off += off & 1;
+    double* w = (double*)work;
+    double* ft = w + off;
+    double* ut = ft + Nb + (Nb & 1);
+    double* image = ut + Nb + (Nb & 1) + 16;
+    if (!k.op.image) SKTT_TRY(sktt_local_op_prepare(ctx, dtype, &k.op, (void*)image));
+    if (!k.op.image) return sktt_fail(ctx, SKTT_ERR_ARG, "krylov_solve_refined: unsupported operator");
+    k.tiled = true;
+    k.N = sktt_fused_tiled_len(k.op.r, k.op.n);
+    SKTT_TRY(sktt_fused_to_tiled(ctx, k.op.r, k.op.n, (const double*)f, ft));
+    SKTT_TRY(sktt_fused_to_tiled(ctx, k.op.r, k.op.n, (const double*)u, ut));
+    int st = cg_tiled_refined(ctx, k, ft, ut, tol, max_iters, max_cycles, w, iters_host, relres_host, cycles_host);
+    int st2 = sktt_fused_from_tiled(ctx, k.op.r, k.op.n, ut, (double*)u);
+    return st ? st : st2;
 }

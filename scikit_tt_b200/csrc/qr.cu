@@ -8,6 +8,16 @@
 // available everywhere after that single barrier.  Q is then formed in place (LAPACK org2r order).
 // The loader/storer take signed strides + conjugation so that RQ is QR of the row-reversed
 // conjugate transpose without any HBM-side permutation.
+//
+// Fast path for tall matrices with few columns (the ALS unfoldings: 4096 x 64 at the bench shape): cholqr_kernel, an
+// adaptive (shifted) CholeskyQR in ONE cooperative launch -- rows stay in shared memory, per pass a Gram matrix
+// (deterministic two-level reduction, two grid barriers), its Cholesky factor and triangular inverse (computed
+// redundantly and bit-identically by every CTA), and the multiplication of the local rows.  Passes repeat until the Gram
+// matrix of the current Q is the identity to working precision; a Cholesky breakdown adds the shift of Fukaya et al.
+// (sCholQR3).  The economic Q of a full-rank matrix is unique up to the signs of its columns, so this Q equals LAPACK's
+// Householder Q up to a diagonal +-1 (an exact symmetry of every later step of the sweep).  If the passes do not
+// converge (numerically rank-deficient input) a device flag makes the Householder kernel below run instead; with the
+// flag clear that kernel exits at once, so the host never waits on the decision.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -33,8 +43,10 @@ struct QrShared {
 template <typename T>
 __global__ void __launch_bounds__(QR_THREADS)
 qr_householder_kernel(const T* __restrict__ src, QrView lv, int m, int n, int rows_per_cta, T* __restrict__ qdst,
-                      QrView qv, T* __restrict__ rdst, QrView rv, T* part, T* rowbuf, int cooperative) {
+                      QrView qv, T* __restrict__ rdst, QrView rv, T* part, T* rowbuf, int cooperative,
+                      const int* __restrict__ run_flag) {
     extern __shared__ unsigned char smem_raw[];
+    if (run_flag && *run_flag == 0) return;      // uniform over the grid: the fast path already produced Q (and R)
     const int ld = n + 1;
     T* Arows = (T*)smem_raw;                 // [rows_per_cta][ld]
     T* wvec = Arows + (size_t)rows_per_cta * ld;  // [n]  (w = v^H A, or staging)
@@ -187,7 +199,8 @@ qr_householder_kernel(const T* __restrict__ src, QrView lv, int m, int n, int ro
 }
 
 template <typename T>
-static int qr_launch(sktt_ctx* ctx, int m, int n, const T* src, QrView lv, T* qdst, QrView qv, T* rdst, QrView rv) {
+static int qr_launch(sktt_ctx* ctx, int m, int n, const T* src, QrView lv, T* qdst, QrView qv, T* rdst, QrView rv,
+                     const int* run_flag = nullptr, size_t scratch_off = 0) {
     const size_t budget = 200 * 1024;
     const size_t per_row = (size_t)(n + 1) * sizeof(T);
     const size_t fixed = (size_t)3 * n * sizeof(T) + 256;
@@ -206,8 +219,8 @@ static int qr_launch(sktt_ctx* ctx, int m, int n, const T* src, QrView lv, T* qd
     G = (m + rows_per_cta - 1) / rows_per_cta;
     size_t smem = (size_t)rows_per_cta * per_row + fixed;
     size_t part_bytes = ((size_t)2 * G * n + 2 * n) * sizeof(T);
-    SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + part_bytes));
-    T* part = (T*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
+    SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + scratch_off + part_bytes));
+    T* part = (T*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF + scratch_off);
     T* rowbuf = part + (size_t)2 * G * n;
     static size_t configured = 0;
     if (smem > configured) {
@@ -216,7 +229,7 @@ static int qr_launch(sktt_ctx* ctx, int m, int n, const T* src, QrView lv, T* qd
         configured = budget;
     }
     int coop = G > 1 ? 1 : 0;
-    void* args[] = {&src, &lv, &m, &n, &rows_per_cta, &qdst, &qv, &rdst, &rv, &part, &rowbuf, &coop};
+    void* args[] = {&src, &lv, &m, &n, &rows_per_cta, &qdst, &qv, &rdst, &rv, &part, &rowbuf, &coop, &run_flag};
     if (coop)
         SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)qr_householder_kernel<T>, dim3(G), dim3(QR_THREADS), args, smem,
                                                    ctx->stream));
@@ -227,17 +240,471 @@ static int qr_launch(sktt_ctx* ctx, int m, int n, const T* src, QrView lv, T* qd
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Adaptive (shifted) CholeskyQR for tall matrices with few columns, one cooperative launch.
+// ------------------------------------------------------------------------------------------------
+#define CQ_THREADS 256
+#define CQ_MAX_PASSES 8
+#define CQ_STATUS_OFF 1024   // byte offset of {fail flag, passes} in the scalar area of the context scratch
+
+template <typename T>
+__device__ __forceinline__ T shfl_xor_num(T v, int o);
+template <>
+__device__ __forceinline__ double shfl_xor_num<double>(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+template <>
+__device__ __forceinline__ cplx shfl_xor_num<cplx>(cplx v, int o) {
+    return make_cplx(__shfl_xor_sync(0xffffffffu, v.re, o), __shfl_xor_sync(0xffffffffu, v.im, o));
+}
+
+// NN = 16 NT >= n is the padded column count; padded columns of the row tile are zero.
+//
+// Per pass: G = T^H T (T = current rows), scaled to unit diagonal; Cholesky G = R^H R with pivots floored at CQ_FLOOR
+// (a floored pivot only under-normalises its column: no information is dropped, the next pass amplifies it again by up to
+// 1 / sqrt(CQ_FLOOR)); T <- T R^-1 by row-wise forward substitution.  A column whose pivot still hits the floor after the
+// first pass carries less than ~1e-19 of the matrix and is replaced by a unit vector, which the following passes
+// orthogonalise against the rest -- the deterministic counterpart of the arbitrary null-space completion LAPACK's
+// Householder QR returns for numerically rank-deficient unfoldings (the usual case for converged ALS cores).
+// Passes end when ||G - I||_F <= 1e-8 before a pass (that pass squares the defect) or <= 1e-13 (nothing left to do).
+#define CQ_FLOOR 1e-13
+#define CQ_DEBUG_OFF 1536    // byte offset of the optional phase time stamps (globaltimer, CTA 0) in the scalar area
+
+__device__ __forceinline__ unsigned long long cq_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Cholesky G = R^H R (upper, in place, [NN][LD] in shared memory) with floored pivots, blocked by 16: the diagonal block
+// is factored by one warp in registers (lane c owns column c; shuffles instead of barriers), then a panel solve and a
+// rank-16 trailing update by the whole CTA.  A floored pivot decouples its row (R_jc = 0 for c > j): the column is only
+// amplified by 1 / sqrt(CQ_FLOOR) in this pass and orthogonalised in the next one.  Kept out of line (one copy per
+// element type instead of one per column-count instantiation; the unrolled register code is slow to compile).
+template <typename T>
+__device__ __noinline__ void cq_cholesky(T* Gs, const int LD, const int NN, const int n, double* dinv, int* flr, int* repl,
+                                         const int pass) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ty = tid >> 4, tx = tid & 15;
+    for (int k0 = 0; k0 < NN; k0 += 16) {                      // the padding block is the identity: no edge cases
+        if (k0 >= n) break;
+        if (warp == 0) {
+            T col[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) col[i] = Gs[(k0 + i) * LD + k0 + (lane & 15)];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                double piv = Num<T>::real(lane_bcast<T>(col[j], j));
+                const bool fl = !(piv > CQ_FLOOR);
+                if (fl) piv = CQ_FLOOR;
+                const double inv = rsqrt(piv), rjj = piv * inv;
+                T rjc = Num<T>::zero();
+                if (lane == j) rjc = Num<T>::from(rjj, 0.0);
+                else if (lane > j && lane < 16 && !fl) rjc = Num<T>::scale(col[j], inv);
+                col[j] = rjc;
+#pragma unroll
+                for (int i = j + 1; i < 16; ++i) {
+                    const T rji = lane_bcast<T>(rjc, i);
+                    col[i] = Num<T>::sub(col[i], Num<T>::mul(Num<T>::conj(rji), rjc));   // rows i > lane: unused garbage
+                }
+                if (lane == 0) {
+                    dinv[k0 + j] = inv;
+                    flr[k0 + j] = fl ? 1 : 0;
+                    if (fl && pass > 0 && k0 + j < n) repl[k0 + j] = 1;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (lane < 16 && i <= lane) Gs[(k0 + i) * LD + k0 + lane] = col[i];
+        }
+        __syncthreads();
+        const int c0 = k0 + 16;
+        // panel R11^H X = S12: four threads per column split the inner sums; x_i goes back to shared memory at once
+        {
+            const int quad = tid >> 2, ql = tid & 3;
+            for (int cb = c0; cb < NN; cb += CQ_THREADS / 4) {
+                const int c = cb + quad;
+                const bool act = c < NN;
+                const int cc = act ? c : c0;
+#pragma unroll 1
+                for (int i = 0; i < 16; ++i) {
+                    T sacc = Num<T>::zero();
+#pragma unroll
+                    for (int k = 0; k < 16; k += 4)
+                        if (k + ql < i)
+                            Num<T>::fma(sacc, Num<T>::conj(Gs[(k0 + k + ql) * LD + k0 + i]), Gs[(k0 + k + ql) * LD + cc]);
+                    sacc = Num<T>::add(sacc, shfl_xor_num<T>(sacc, 1));
+                    sacc = Num<T>::add(sacc, shfl_xor_num<T>(sacc, 2));
+                    const T x = flr[k0 + i] ? Num<T>::zero()
+                                            : Num<T>::scale(Num<T>::sub(Gs[(k0 + i) * LD + cc], sacc), dinv[k0 + i]);
+                    __syncwarp();
+                    if (act && ql == 0) Gs[(k0 + i) * LD + c] = x;
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = c0 + ty; i < NN; i += 16)                  // trailing update S22 -= R12^H R12
+            for (int c = c0 + tx; c < NN; c += 16)
+                if (c >= i) {
+                    T sacc = Gs[i * LD + c];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        sacc = Num<T>::sub(sacc, Num<T>::mul(Num<T>::conj(Gs[(k0 + k) * LD + i]), Gs[(k0 + k) * LD + c]));
+                    Gs[i * LD + c] = sacc;
+                }
+        __syncthreads();
+    }
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(CQ_THREADS)
+cholqr_kernel(const T* __restrict__ src, QrView lv, int m, int n, int rows_per_cta, T* __restrict__ qdst, QrView qv,
+              T* __restrict__ rdst, QrView rv, T* part, T* gfull, T* rstack, int* status, unsigned long long* dbg) {
+    constexpr int NN = 16 * NT, LD = NN + 1, E = NN * NN;
+    extern __shared__ unsigned char smem_raw[];
+    T* tile = (T*)smem_raw;                         // [rows_per_cta][LD]
+    T* Gs = tile + (size_t)rows_per_cta * LD;       // [NN][LD]  Gram matrix -> Cholesky factor R (upper)
+    T* Xs = Gs + (size_t)NN * LD;                   // [NN][LD]  second buffer of the R product (only when R is wanted)
+    __shared__ double red[32];
+    __shared__ double dinv[NN];                     // 1 / R_jj
+    __shared__ double csc[NN];                      // column scaling 1 / sqrt(G_jj)
+    __shared__ int repl[NN];                        // column is replaced by a unit vector in this pass
+    __shared__ int flr[NN];                         // pivot was floored in this pass
+    cg::grid_group grid = cg::this_grid();
+    const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int row_begin = cta * rows_per_cta;
+    const int nrows = max(0, min(rows_per_cta, m - row_begin));
+    const bool row_fast = llabs(lv.si) < llabs(lv.sj);      // which index is contiguous in memory
+    int ndbg = 0;
+    auto stamp = [&]() {
+        if (dbg && cta == 0 && tid == 0 && ndbg < 60) dbg[1 + ndbg++] = cq_now();
+    };
+    stamp();
+    for (int e = tid; e < nrows * NN; e += CQ_THREADS) tile[(e / NN) * LD + e % NN] = Num<T>::zero();
+    __syncthreads();
+    for (int e = tid; e < nrows * n; e += CQ_THREADS) {
+        const int rr = row_fast ? e % nrows : e / n, cc = row_fast ? e / nrows : e % n;
+        T v = src[lv.off + (long long)(row_begin + rr) * lv.si + (long long)cc * lv.sj];
+        tile[rr * LD + cc] = lv.conj ? Num<T>::conj(v) : v;
+    }
+    __syncthreads();
+    stamp();
+
+    int fail = 0, passes = 0;
+    bool done = false;
+    for (int pass = 0; pass < CQ_MAX_PASSES && !done; ++pass) {
+        // ---- partial Gram matrix of the local rows: P[j1][j2] = sum_i conj(t[i][j1]) t[i][j2]
+        {
+            T acc[NT][NT];
+#pragma unroll
+            for (int a = 0; a < NT; ++a)
+#pragma unroll
+                for (int b = 0; b < NT; ++b) acc[a][b] = Num<T>::zero();
+            for (int rr = 0; rr < nrows; ++rr) {
+                T av[NT], bv[NT];
+#pragma unroll
+                for (int a = 0; a < NT; ++a) av[a] = Num<T>::conj(tile[rr * LD + ty + 16 * a]);
+#pragma unroll
+                for (int b = 0; b < NT; ++b) bv[b] = tile[rr * LD + tx + 16 * b];
+#pragma unroll
+                for (int a = 0; a < NT; ++a)
+#pragma unroll
+                    for (int b = 0; b < NT; ++b) Num<T>::fma(acc[a][b], av[a], bv[b]);
+            }
+            T* mypart = part + (size_t)cta * E;
+#pragma unroll
+            for (int a = 0; a < NT; ++a)
+#pragma unroll
+                for (int b = 0; b < NT; ++b) mypart[(ty + 16 * a) * NN + tx + 16 * b] = acc[a][b];
+        }
+        __threadfence();
+        stamp();
+        grid.sync();
+        stamp();
+        // ---- every CTA reduces a slice of the entries over all partials (fixed order: deterministic)
+        {
+            const int chunk = (E + G - 1) / G;
+            const int e_lo = cta * chunk, e_hi = min(E, e_lo + chunk);
+            for (int e0 = e_lo; e0 < e_hi; e0 += CQ_THREADS / 8) {
+                const int e = e0 + (tid >> 3), sub = tid & 7;
+                T sacc = Num<T>::zero();
+                if (e < e_hi)
+                    for (int g = sub; g < G; g += 8) sacc = Num<T>::add(sacc, ld_cg<T>(part + (size_t)g * E + e));
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) sacc = Num<T>::add(sacc, shfl_xor_num<T>(sacc, o));
+                if (e < e_hi && sub == 0) gfull[e] = sacc;
+            }
+        }
+        __threadfence();
+        stamp();
+        grid.sync();
+        stamp();
+        // ---- G -> shared memory; distance from the identity (identical in every CTA)
+        double dl = 0.0;
+        for (int e = tid; e < E; e += CQ_THREADS) {
+            const int i = e / NN, c = e % NN;
+            const T g = ld_cg<T>(gfull + e);
+            Gs[i * LD + c] = g;
+            if (i < n && c < n) dl += Num<T>::abs2(Num<T>::sub(g, i == c ? Num<T>::one() : Num<T>::zero()));
+        }
+        dl = block_sum<double>(dl, red);
+        __syncthreads();
+        if (!isfinite(dl)) { fail = 1; break; }
+        const double delta = sqrt(dl);
+        if (pass > 0 && delta <= 1e-13) break;               // the current rows are orthonormal to working precision
+        bool last = pass > 0 && delta <= 1e-8;                // one more pass squares the defect: enough
+        if (pass > 0 && !rdst && delta <= 0.1) {
+            // Nearly orthonormal already and no triangular factor wanted: one Newton-Schulz step of the polar iteration,
+            // rows <- rows (I - E/2 + 3 E^2 / 8) with E = G - I, cubically convergent and free of the serial Cholesky /
+            // substitution chains (a tiny rotation of the basis, irrelevant to the sweep)
+            for (int e = tid; e < E; e += CQ_THREADS) {
+                const int i = e / NN, c = e % NN;
+                Gs[i * LD + c] = (i < n && c < n) ? Num<T>::sub(Gs[i * LD + c], i == c ? Num<T>::one() : Num<T>::zero())
+                                                  : Num<T>::zero();
+            }
+            __syncthreads();
+            constexpr int NQ = (NN + 31) / 32;
+            for (int rr = warp; rr < nrows; rr += CQ_THREADS / 32) {
+                T y[NQ], z[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) y[q] = z[q] = Num<T>::zero();
+                for (int k = 0; k < n; ++k) {
+                    const T t = tile[rr * LD + k];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        if (lane + 32 * q < NN) Num<T>::fma(y[q], t, Gs[k * LD + lane + 32 * q]);
+                }
+                for (int k = 0; k < n; ++k) {
+                    T yk = y[0];
+#pragma unroll
+                    for (int q = 1; q < NQ; ++q)
+                        if ((k >> 5) == q) yk = y[q];
+                    yk = lane_bcast<T>(yk, k & 31);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        if (lane + 32 * q < NN) Num<T>::fma(z[q], yk, Gs[k * LD + lane + 32 * q]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const int c = lane + 32 * q;
+                    if (c < n)
+                        tile[rr * LD + c] = Num<T>::add(tile[rr * LD + c],
+                                                        Num<T>::add(Num<T>::scale(y[q], -0.5), Num<T>::scale(z[q], 0.375)));
+                }
+            }
+            __syncthreads();
+            stamp();
+            ++passes;
+            if (delta <= 1e-5) done = true;
+            else if (pass == CQ_MAX_PASSES - 1) fail = 1;
+            continue;
+        }
+        // ---- unit-diagonal scaling
+        if (tid < NN) {
+            const double gjj = tid < n ? Num<T>::real(Gs[tid * LD + tid]) : 0.0;
+            csc[tid] = gjj > 0.0 ? rsqrt(gjj) : 0.0;
+            repl[tid] = (tid < n && !(gjj > 0.0)) ? 1 : 0;   // zero column: nothing to normalise
+        }
+        __syncthreads();
+        for (int e = tid; e < E; e += CQ_THREADS) {
+            const int i = e / NN, c = e % NN;
+            if (i >= n || c >= n) Gs[i * LD + c] = i == c ? Num<T>::one() : Num<T>::zero();
+            else if (c >= i) Gs[i * LD + c] = i == c ? Num<T>::from(csc[i] > 0.0 ? 1.0 : 0.0, 0.0)
+                                                     : Num<T>::scale(Gs[i * LD + c], csc[i] * csc[c]);
+        }
+        __syncthreads();
+        stamp();
+        cq_cholesky<T>(Gs, LD, NN, n, dinv, flr, repl, pass);
+        stamp();
+        const int nrepl = __syncthreads_count(tid < n && repl[tid]);
+        if (nrepl > 0) last = false;
+        // ---- local rows <- rows * diag(csc) * R^-1 by forward substitution (row-wise backward stable, unlike a product
+        //      with an explicit inverse): a warp owns rows warp, warp + 8, ...; lanes own columns lane + 32 q
+        {
+            constexpr int NQ = (NN + 31) / 32, RB = 4, NW = CQ_THREADS / 32;
+            for (int r0 = warp; r0 < nrows; r0 += NW * RB) {
+                T a[RB][NQ];
+#pragma unroll
+                for (int b2 = 0; b2 < RB; ++b2)
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int rr = r0 + NW * b2, c = lane + 32 * q;
+                        a[b2][q] = (rr < nrows && c < n) ? Num<T>::scale(tile[rr * LD + c], csc[c]) : Num<T>::zero();
+                    }
+                for (int j = 0; j < n; ++j) {
+                    const int owner = j & 31, qj = j >> 5;
+                    const double di = dinv[j];
+                    T rj[NQ];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int c = lane + 32 * q;
+                        rj[q] = (c > j && c < n) ? Gs[j * LD + c] : Num<T>::zero();
+                    }
+#pragma unroll
+                    for (int b2 = 0; b2 < RB; ++b2) {
+                        T piv = a[b2][0];
+#pragma unroll
+                        for (int q = 1; q < NQ; ++q)
+                            if (qj == q) piv = a[b2][q];
+                        const T x = Num<T>::scale(lane_bcast<T>(piv, owner), di);
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            const int c = lane + 32 * q;
+                            if (c == j) a[b2][q] = x;
+                            else a[b2][q] = Num<T>::sub(a[b2][q], Num<T>::mul(x, rj[q]));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int b2 = 0; b2 < RB; ++b2)
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int rr = r0 + NW * b2, c = lane + 32 * q;
+                        if (rr < nrows && c < n) {
+                            T v = a[b2][q];
+                            if (nrepl > 0 && repl[c]) {      // unit vector e_h, h spread over the rows and moved per pass
+                                const long long h = ((long long)c * (m / n) + 7LL * pass + 1) % m;
+                                v = (row_begin + rr == h) ? Num<T>::one() : Num<T>::zero();
+                            }
+                            tile[rr * LD + c] = v;
+                        }
+                    }
+            }
+        }
+        if (rdst && cta == 0)                                  // R of this pass in the unscaled columns; replaced rows drop out
+            for (int e = tid; e < E; e += CQ_THREADS) {
+                const int i = e / NN, c = e % NN;
+                T v = Num<T>::zero();
+                if (i < n && c < n && c >= i && !repl[i] && csc[c] > 0.0) v = Num<T>::scale(Gs[i * LD + c], 1.0 / csc[c]);
+                rstack[(size_t)pass * E + e] = v;
+            }
+        __syncthreads();
+        stamp();
+        ++passes;
+        if (last) done = true;
+        else if (pass == CQ_MAX_PASSES - 1) fail = 1;
+    }
+
+    if (!fail) {
+        for (int e = tid; e < nrows * n; e += CQ_THREADS) {
+            const int rr = row_fast ? e % nrows : e / n, cc = row_fast ? e / nrows : e % n;
+            T v = tile[rr * LD + cc];
+            if (qv.conj) v = Num<T>::conj(v);
+            qdst[qv.off + (long long)(row_begin + rr) * qv.si + (long long)cc * qv.sj] = v;
+        }
+        if (rdst && cta == 0) {
+            // R = R_{passes-1} ... R_0, accumulated in shared memory (Gs <- Xs * Gs)
+            __threadfence();
+            __syncthreads();
+            for (int e = tid; e < E; e += CQ_THREADS) Gs[(e / NN) * LD + e % NN] = rstack[e];
+            __syncthreads();
+            for (int p = 1; p < passes; ++p) {
+                for (int e = tid; e < E; e += CQ_THREADS) Xs[(e / NN) * LD + e % NN] = rstack[(size_t)p * E + e];
+                __syncthreads();
+                T acc[NT][NT];
+#pragma unroll
+                for (int a = 0; a < NT; ++a)
+#pragma unroll
+                    for (int b = 0; b < NT; ++b) acc[a][b] = Num<T>::zero();
+                for (int k = 0; k < n; ++k) {
+#pragma unroll
+                    for (int a = 0; a < NT; ++a) {
+                        const T xa = Xs[(ty + 16 * a) * LD + k];
+#pragma unroll
+                        for (int b = 0; b < NT; ++b) Num<T>::fma(acc[a][b], xa, Gs[k * LD + tx + 16 * b]);
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int a = 0; a < NT; ++a)
+#pragma unroll
+                    for (int b = 0; b < NT; ++b) Gs[(ty + 16 * a) * LD + tx + 16 * b] = acc[a][b];
+                __syncthreads();
+            }
+            for (int e = tid; e < n * n; e += CQ_THREADS) {
+                const int i = e / n, c = e % n;
+                T v = c >= i ? Gs[i * LD + c] : Num<T>::zero();
+                if (rv.conj) v = Num<T>::conj(v);
+                rdst[rv.off + (long long)i * rv.si + (long long)c * rv.sj] = v;
+            }
+        }
+    }
+    stamp();
+    if (cta == 0 && tid == 0) {
+        status[0] = fail;
+        status[1] = passes;
+        if (dbg) dbg[0] = (unsigned long long)ndbg;
+    }
+}
+
+template <typename T, int NT>
+static int cholqr_launch_nt(sktt_ctx* ctx, int m, int n, const T* src, QrView lv, T* qdst, QrView qv, T* rdst, QrView rv,
+                            bool* used) {
+    constexpr int NN = 16 * NT, LD = NN + 1, E = NN * NN;
+    const size_t budget = 200 * 1024;
+    int G = (m + 31) / 32;
+    if (G > ctx->sm_count) G = ctx->sm_count;
+    int rows_per_cta = (m + G - 1) / G;
+    G = (m + rows_per_cta - 1) / rows_per_cta;
+    const size_t smem = ((size_t)rows_per_cta * LD + (size_t)(rdst ? 2 : 1) * NN * LD) * sizeof(T);
+    if (smem > budget) return 0;                                          // not for this kernel: Householder path
+    // scratch: partial Gram matrices | reduced Gram matrix | R factors of the passes; sized for the fallback as well
+    const size_t mine = ((size_t)G * E + E + (size_t)CQ_MAX_PASSES * E) * sizeof(T);
+    const size_t theirs = ((size_t)2 * QR_MAX_CTAS * n + 2 * n) * sizeof(T);
+    SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (mine > theirs ? mine : theirs) + 4096));
+    T* part = (T*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
+    T* gfull = part + (size_t)G * E;
+    T* rstack = gfull + E;
+    int* status = (int*)((char*)ctx->scratch + CQ_STATUS_OFF);
+    static bool configured = false;
+    if (!configured) {
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(cholqr_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        configured = true;
+    }
+    unsigned long long* dbg = ctx->debug ? (unsigned long long*)((char*)ctx->scratch + CQ_DEBUG_OFF) : nullptr;
+    void* args[] = {&src, &lv, &m, &n, &rows_per_cta, &qdst, &qv, &rdst, &rv, &part, &gfull, &rstack, &status, &dbg};
+    SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)cholqr_kernel<T, NT>, dim3(G), dim3(CQ_THREADS), args, smem,
+                                               ctx->stream));
+    ctx->launches++;
+    *used = true;
+    return 0;
+}
+
+// Orthonormal factor of a tall matrix: CholeskyQR first, Householder behind its failure flag.
+template <typename T>
+static int qr_dispatch(sktt_ctx* ctx, int m, int n, const T* src, QrView lv, T* qdst, QrView qv, T* rdst, QrView rv,
+                       bool allow_chol) {
+    bool used = false;
+    if (allow_chol && m >= 2 * n && m >= 64 && ctx->gemm_mode != 1) {
+        const int nt = (n + 15) / 16;
+        if (nt <= 1) SKTT_TRY((cholqr_launch_nt<T, 1>(ctx, m, n, src, lv, qdst, qv, rdst, rv, &used)));
+        else if (nt <= 2) SKTT_TRY((cholqr_launch_nt<T, 2>(ctx, m, n, src, lv, qdst, qv, rdst, rv, &used)));
+        else if (nt <= 4) SKTT_TRY((cholqr_launch_nt<T, 4>(ctx, m, n, src, lv, qdst, qv, rdst, rv, &used)));
+        else if (nt <= 6) SKTT_TRY((cholqr_launch_nt<T, 6>(ctx, m, n, src, lv, qdst, qv, rdst, rv, &used)));
+        else if (nt <= 8 && !Num<T>::is_complex)
+            SKTT_TRY((cholqr_launch_nt<double, 8>(ctx, m, n, (const double*)src, lv, (double*)qdst, qv, (double*)rdst, rv,
+                                                  &used)));
+    }
+    const int* flag = used ? (const int*)((char*)ctx->scratch + CQ_STATUS_OFF) : nullptr;
+    return qr_launch<T>(ctx, m, n, src, lv, qdst, qv, rdst, rv, flag);
+}
+
 extern "C" int64_t sktt_qr_work(int64_t m, int64_t n) {
     (void)m;
     (void)n;
     return 1;  // the kernel works out of shared memory + context scratch; kept for ABI stability
 }
 
-int sktt_qr_internal(sktt_ctx* ctx, int dtype, int m, int n, const void* A, void* Q, void* R) {
+// allow_chol = 0 keeps the Householder kernel (the SVD driver wants its R to column-wise relative accuracy)
+static int qr_any(sktt_ctx* ctx, int dtype, int m, int n, const void* A, void* Q, void* R, bool allow_chol) {
     int k = m < n ? m : n;
     QrView lv{0, n, 1, 0}, qv{0, k, 1, 0}, rv{0, n, 1, 0};
-    if (dtype == SKTT_F64) return qr_launch<double>(ctx, m, n, (const double*)A, lv, (double*)Q, qv, (double*)R, rv);
-    return qr_launch<cplx>(ctx, m, n, (const cplx*)A, lv, (cplx*)Q, qv, (cplx*)R, rv);
+    if (dtype == SKTT_F64)
+        return qr_dispatch<double>(ctx, m, n, (const double*)A, lv, (double*)Q, qv, (double*)R, rv, allow_chol);
+    return qr_dispatch<cplx>(ctx, m, n, (const cplx*)A, lv, (cplx*)Q, qv, (cplx*)R, rv, allow_chol);
+}
+int sktt_qr_internal(sktt_ctx* ctx, int dtype, int m, int n, const void* A, void* Q, void* R) {
+    return qr_any(ctx, dtype, m, n, A, Q, R, false);
 }
 
 extern "C" int sktt_qr_left(sktt_ctx* ctx, int dtype, int64_t m, int64_t n, const void* A, void* Q_out, void* R_out,
@@ -246,7 +713,7 @@ extern "C" int sktt_qr_left(sktt_ctx* ctx, int dtype, int64_t m, int64_t n, cons
     if (!ctx || !A || !Q_out) return SKTT_ERR_ARG;
     SKTT_TRY(check_dtype(ctx, dtype));
     if (m <= 0 || n <= 0 || m > 0x7fffffff || n > 0x7fffffff) return sktt_fail(ctx, SKTT_ERR_ARG, "qr: bad extents");
-    return sktt_qr_internal(ctx, dtype, (int)m, (int)n, A, Q_out, R_out);
+    return qr_any(ctx, dtype, (int)m, (int)n, A, Q_out, R_out, true);
 }
 
 // A (m x n) = R Q with the sign convention of LAPACK gerqf (scipy.linalg.rq): the reflectors are generated from the
@@ -267,6 +734,6 @@ extern "C" int sktt_rq_right(sktt_ctx* ctx, int dtype, int64_t m64, int64_t n64,
     // R[m-1-c][k-1-g] = conj(Rc[g][c])                   (Rc is k x m; R is m x k, row-major)
     QrView rv{(long long)(m - 1) * k + (k - 1), -1, -(long long)k, 1};
     if (dtype == SKTT_F64)
-        return qr_launch<double>(ctx, n, m, (const double*)A, lv, (double*)Q_out, qv, (double*)R_out, rv);
-    return qr_launch<cplx>(ctx, n, m, (const cplx*)A, lv, (cplx*)Q_out, qv, (cplx*)R_out, rv);
+        return qr_dispatch<double>(ctx, n, m, (const double*)A, lv, (double*)Q_out, qv, (double*)R_out, rv, true);
+    return qr_dispatch<cplx>(ctx, n, m, (const cplx*)A, lv, (cplx*)Q_out, qv, (cplx*)R_out, rv, true);
 }

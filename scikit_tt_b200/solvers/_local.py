@@ -153,7 +153,16 @@ def solve_micro(dev, solver, dense_builder, op, f, guess, cache=None):
         method = 'cg' if herm else 'gmres'
     if _TRACE:
         print(f"  [micro] N={N} {method}", flush=True)
-    relres, iters = _krylov_refined(dev, op, f, u, method)
+    if method == 'cg' and f.dtype == torch.float64 and dev.tiled_len(op) > 0:
+        # prepared operator: the whole solve (warm start, CG, true-residual restarts) is one C call
+        st, iters, relres, cycles = dev.krylov_solve_refined(op, f, u, tol=KRYLOV_TOL, max_iters=KRYLOV_MAX_ITERS,
+                                                             max_cycles=KRYLOV_MAX_CYCLES)
+        if st != 0:
+            raise _device.SkttError(st, "krylov_solve_refined failed")
+        if _TRACE:
+            print(f"    [krylov] cg (one call): true relres {relres:.3e} after {iters} iterations, {cycles} cycles", flush=True)
+    else:
+        relres, iters = _krylov_refined(dev, op, f, u, method)
     if method == 'cg' and mode == 'krylov' and not relres <= KRYLOV_ACCEPT:
         u.zero_()                                             # Hermitian but not definite: CG broke down, use GMRES
         if cache is not None:

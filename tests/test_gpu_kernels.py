@@ -223,6 +223,9 @@ QR_SHAPES = [(256, 4), (16, 16), (5, 9), (1, 6), (7, 1), (1000, 64), (4096, 64),
 @pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("shape", QR_SHAPES)
 def test_qr_rq_match_lapack(dev, cplx, shape):
+    """Q, R against scipy.linalg.qr / rq.  The economic Q of a full-rank matrix is unique up to the sign of each column
+    (row for RQ); tall unfoldings go through the CholeskyQR kernel (R with a positive diagonal), the others through the
+    Householder kernel (LAPACK's signs), so the comparison fixes the signs from the diagonals of R."""
     m, n = shape
     rng = np.random.default_rng(m * 131 + n + cplx)
     A = rnd(rng, (m, n), cplx)
@@ -232,8 +235,10 @@ def test_qr_rq_match_lapack(dev, cplx, shape):
     assert relerr(Q @ R, A) < 1e-13
     assert relerr(np.conj(Q.T) @ Q, np.eye(k)) < 1e-13
     assert np.allclose(R, np.triu(R))
-    qref, rref = sla.qr(A, mode='economic')       # same Householder convention -> same gauge
-    assert relerr(Q, qref) < 1e-11 and relerr(R, rref) < 1e-11
+    qref, rref = sla.qr(A, mode='economic')
+    sg = np.sign(np.real(np.diag(R))) * np.sign(np.real(np.diag(rref)))
+    assert np.max(np.abs(np.imag(np.diag(R)))) < 1e-12 * np.abs(R).max()
+    assert relerr(Q * sg, qref) < 1e-11 and relerr(sg[:, None] * R, rref) < 1e-11
     # RQ on the transposed shape (the backward ALS step factors r x (n r2))
     B = rnd(rng, (n, m), cplx)
     Rr, Qr = dev.rq(dev.to_device(B), want_r=True)
@@ -241,7 +246,39 @@ def test_qr_rq_match_lapack(dev, cplx, shape):
     assert relerr(Rr @ Qr, B) < 1e-13
     assert relerr(Qr @ np.conj(Qr.T), np.eye(k)) < 1e-13
     rref, qref = sla.rq(B, mode='economic')
-    assert relerr(Qr, qref) < 1e-11 and relerr(Rr, rref) < 1e-11
+    sg = np.sign(np.real(np.diag(Rr[-k:, :] if Rr.shape[0] > k else Rr))) * \
+        np.sign(np.real(np.diag(rref[-k:, :] if rref.shape[0] > k else rref)))
+    assert relerr(sg[:, None] * Qr, qref) < 1e-11 and relerr(Rr * sg, rref) < 1e-11
+
+
+QR_HARD = [(4096, 64, 1e6), (4096, 64, 1e12), (1024, 48, 1e15), (512, 96, 1e10), (4096, 64, np.inf), (256, 4, np.inf)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", QR_HARD)
+def test_qr_ill_conditioned_and_rank_deficient(dev, case):
+    """CholeskyQR passes / shift / Householder fallback: orthonormal Q and a backward-stable factorisation whatever the
+    conditioning (inf = exactly rank-deficient: duplicated and zero columns)."""
+    m, n, cond = case
+    rng = np.random.default_rng(m + n)
+    U0, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    V0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    if np.isinf(cond):
+        A = rng.standard_normal((m, n))
+        A[:, 1] = A[:, 0]
+        A[:, -1] = 0.0
+    else:
+        A = (U0 * np.logspace(0, -np.log10(cond), n)) @ V0.T
+    Q, R = dev.qr(dev.to_device(A), want_r=True)
+    Q, R = host(Q), host(R)
+    assert np.all(np.isfinite(Q)) and np.all(np.isfinite(R))
+    assert relerr(Q.T @ Q, np.eye(n)) < 1e-13
+    assert relerr(Q @ R, A) < 1e-13
+    assert np.allclose(R, np.triu(R))
+    Rr, Qr = dev.rq(dev.to_device(np.ascontiguousarray(A.T)), want_r=True)
+    Rr, Qr = host(Rr), host(Qr)
+    assert relerr(Qr @ Qr.T, np.eye(n)) < 1e-13
+    assert relerr(Rr @ Qr, A.T) < 1e-13
 
 
 SVD_SHAPES = [(1, 1), (6, 4), (4, 6), (64, 64), (256, 12), (12, 256), (1000, 64), (192, 192), (4096, 64), (300, 260)]

@@ -26,12 +26,12 @@ def wrap(name):
         out = f(*a, **k)
         torch.cuda.synchronize()
         info = dict(fn=name, ms=round((time.perf_counter() - t) * 1e3, 3), launches=dev.launches() - l0)
-        if name == 'krylov_solve':
+        if name in ('krylov_solve', 'krylov_solve_refined'):
             info.update(N=a[1].numel(), iters=out[1], relres=out[2], status=out[0])
         rec.append(info)
         return out
     setattr(dev, name, g)
-for n in ('krylov_solve', 'local_matvec', 'prepare_local_op', 'qr', 'rq', 'nrm2', 'axpby', 'dotc'):
+for n in ('krylov_solve', 'krylov_solve_refined', 'local_matvec', 'prepare_local_op', 'qr', 'rq', 'nrm2', 'axpby', 'dotc'):
     wrap(n)
 t = time.perf_counter(); st.reset(x0_dev); sle._run_als(st, 1, 'solve'); torch.cuda.synchronize()
 print("traced step", time.perf_counter() - t)
@@ -41,5 +41,5 @@ for x in rec:
     a['calls'] += 1; a['ms'] += x['ms']; a['launches'] += x['launches']; a['iters'] += x.get('iters', 0)
 print(json.dumps(agg))
 for x in rec:
-    if x['fn'] == 'krylov_solve':
+    if x['fn'].startswith('krylov_solve'):
         print(json.dumps(x))
