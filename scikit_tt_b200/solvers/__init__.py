@@ -1,1 +1,1 @@
-from . import sle, evp, ode  # noqa: F401
+from . import sle, evp, ode, multi  # noqa: F401

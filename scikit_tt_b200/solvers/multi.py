@@ -1,0 +1,183 @@
+"""Multi-GPU forms of the ALS hot path, one process per GPU under torch.distributed.
+
+Two partitions, and only these two, because the sweep itself is sequential in the core index and in time:
+
+1. Independent systems (BASELINE config 5: a sweep over co_oxidation CO pressures; several right-hand sides; separate
+   trajectories).  `map_sharded` gives every rank a contiguous block of the work list, runs the unchanged single-GPU
+   solver on it (no data-path collective) and gathers the results once at the end.  `evp_als_batch` / `sle_als_batch`
+   are the two front ends; the reference has no counterpart (it would loop: examples/co_oxidation.py:100-104).
+
+2. One system at very large rank (config 4): the micro-matvec
+       y[c,m,c2] = sum L[a,b,c] v[a,n,a2] A[b,m,n,b2] Rt[a2,b2,c2]
+   is sharded over the OUTPUT solution-rank index `c` (sharding the contracted index `a` would only shrink the first of
+   the three contractions: the partial T1 is full-size).  Rank g computes y[c_g] with the strided GEMM engine (no slice
+   copies: the shard is an offset and an extent of the left stack), then one collective over NVLink (NCCL all_gather,
+   or all_reduce for ragged blocks) assembles y everywhere.  `sharded_micro_matvec` is that step; `cg_sharded` iterates it.
+
+Both work with any initialised process group; the CPU tests run them over gloo with world size 2 (tests/test_multi.py).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..tensor_train import TT
+
+
+# ------------------------------------------------------------------------------------------------ partition 1
+def shard_bounds(n_items, world, rank):
+    """Contiguous block partition: the first n_items % world ranks get one extra item.  Returns (lo, hi)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad world / rank")
+    base, extra = divmod(int(n_items), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def map_sharded(fn, items, group=None, gather=True):
+    """results[i] = fn(items[i]) with the items block-partitioned over the ranks of `group`.
+
+    No communication while the items are processed; one all_gather_object of the (picklable, host-side) results at the
+    end.  With gather=False every rank only returns its own block [(index, result), ...]."""
+    world, rank = _world(group)
+    lo, hi = shard_bounds(len(items), world, rank)
+    mine = [(i, fn(items[i])) for i in range(lo, hi)]
+    if not gather:
+        return mine
+    if world == 1:
+        return [r for _, r in mine]
+    parts = [None] * world
+    dist.all_gather_object(parts, mine, group=group)
+    out = [None] * len(items)
+    for part in parts:
+        for i, r in part:
+            out[i] = r
+    return out
+
+
+def _pack(t):
+    return [np.ascontiguousarray(c) for c in t.cores]
+
+
+def evp_als_batch(operators, initial_guesses, group=None, **kwargs):
+    """evp.als on a list of independent operators, one block of the list per GPU.  `initial_guesses` is one TT (shared)
+    or a list.  Returns a list of (eigenvalue(s), eigentensor(s), iterations) in input order on every rank."""
+    from . import evp
+    guesses = initial_guesses if isinstance(initial_guesses, (list, tuple)) else [initial_guesses] * len(operators)
+
+    def one(i):
+        lam, vec, it = evp.als(operators[i], guesses[i], **kwargs)
+        vec = [_pack(v) for v in vec] if isinstance(vec, list) else _pack(vec)
+        return lam, vec, it
+
+    res = map_sharded(one, list(range(len(operators))), group=group)
+    out = []
+    for lam, vec, it in res:
+        tens = [TT(v) for v in vec] if vec and isinstance(vec[0], list) else TT(vec)
+        out.append((lam, tens, it))
+    return out
+
+
+def sle_als_batch(operators, initial_guesses, right_hand_sides, group=None, mals=False, **kwargs):
+    """sle.als (or sle.mals) on independent systems; `operators` / `initial_guesses` may be single TTs shared by all
+    right-hand sides.  Returns the list of solution TTs in input order on every rank."""
+    from . import sle
+    n = len(right_hand_sides)
+    ops = operators if isinstance(operators, (list, tuple)) else [operators] * n
+    guesses = initial_guesses if isinstance(initial_guesses, (list, tuple)) else [initial_guesses] * n
+    solver = sle.mals if mals else sle.als
+    res = map_sharded(lambda i: _pack(solver(ops[i], guesses[i], right_hand_sides[i], **kwargs)), list(range(n)), group=group)
+    return [TT(c) for c in res]
+
+
+# ------------------------------------------------------------------------------------------------ partition 2
+def matvec_rows_device(dev, L, A, Rt, v, lo, hi):
+    """y[lo:hi, :, :] of the micro-matvec through three strided GEMMs of the contraction engine (device tensors).
+
+    Only the rows c in [lo, hi) of the left stack enter, so all three contractions shrink with the shard:
+      T1[b,cs,n,a2]  = sum_a  L[a,b,lo+cs] v[a,n,a2]
+      T2[cs,m,a2,b2] = sum_bn A[b,m,n,b2] T1[b,cs,n,a2]
+      y[cs,m,c2]     = sum    T2[cs,m,a2,b2] Rt[a2,b2,c2]
+    The shard of L is an offset into the same buffer (two-level index map), never a copy."""
+    big = 1 << 40
+    r, R, _ = L.shape
+    _, m, n, R2 = A.shape
+    r2 = Rt.shape[0]
+    rc = hi - lo
+    T1 = dev.empty((R * rc, n * r2), v.dtype)
+    dev.gemm2(R * rc, n * r2, r, L.reshape(-1)[lo:], (rc, r, 1), (big, 0, R * r), v, (big, 0, n * r2), (big, 0, 1),
+              T1, (big, 0, n * r2), (big, 0, 1))
+    T2 = dev.empty((rc * m, r2 * R2), v.dtype)
+    dev.gemm2(rc * r2, m * R2, R * n, T1, (r2, n * r2, 1), (n, rc * n * r2, r2), A, (n, m * n * R2, R2), (R2, n * R2, 1),
+              T2, (r2, m * r2 * R2, R2), (R2, r2 * R2, 1))
+    y = dev.empty((rc, m, r2), v.dtype)
+    dev.gemm2(rc * m, r2, r2 * R2, T2, (big, 0, r2 * R2), (big, 0, 1), Rt, (big, 0, r2), (big, 0, 1),
+              y, (big, 0, r2), (big, 0, 1))
+    return y
+
+
+def sharded_micro_matvec(L, A, Rt, v, group=None, rows=None, dev=None):
+    """y = M v with the OUTPUT solution-rank index c sharded over `group`: every rank holds the (small) operands and the
+    full vector v, computes the rows [lo, hi) of y, and one collective over NVLink assembles y on every rank
+    (all_gather when the blocks are equal, all_reduce of the zero-padded blocks otherwise).
+
+    `rows(L, A, Rt, v, lo, hi)` computes one block; it defaults to the CUDA contraction engine on `dev`."""
+    world, rank = _world(group)
+    r = L.shape[0]
+    lo, hi = shard_bounds(r, world, rank)
+    if rows is None:
+        if dev is None:
+            from .. import _device
+            dev = _device.get_device()
+        rows = lambda *a: matvec_rows_device(dev, *a)
+    mine = rows(L, A, Rt, v, lo, hi) if hi > lo else None
+    if world == 1:
+        return mine
+    as_tensor = (lambda t: t) if torch.is_tensor(v) else torch.from_numpy
+    m, r2 = A.shape[1], Rt.shape[0]
+    ref = as_tensor(v)
+    y = torch.zeros((r, m, r2), dtype=ref.dtype, device=ref.device)
+    if r % world == 0:
+        dist.all_gather_into_tensor(y, as_tensor(mine).contiguous(), group=group)
+    else:
+        if mine is not None:
+            y[lo:hi] = as_tensor(mine)
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+    return y if torch.is_tensor(v) else y.numpy()
+
+
+def cg_sharded(L, A, Rt, f, u0=None, tol=1e-13, max_iters=2000, group=None, dev=None):
+    """CG on the micro system with the sharded matvec; every rank carries the full Krylov vectors and runs identical
+    scalar recurrences (the assembled y is bit-identical on all ranks), so the only collective is the one inside the
+    matvec.  Device tensors; returns (u, iterations, relative residual)."""
+    if dev is None:
+        from .. import _device
+        dev = _device.get_device()
+    mv = lambda x: sharded_micro_matvec(L, A, Rt, x.reshape(f.shape), group=group, dev=dev).reshape(-1)
+    fv = f.reshape(-1)
+    u = torch.zeros_like(fv) if u0 is None else u0.reshape(-1).clone()
+    res = dev.axpby(-1.0, mv(u), 1.0, fv) if u0 is not None else fv.clone()
+    p = res.clone()
+    rr = dev.dotc(res, res).real if f.dtype == torch.complex128 else dev.dotc(res, res)
+    f2 = dev.dotc(fv, fv).real if f.dtype == torch.complex128 else dev.dotc(fv, fv)
+    it = 0
+    while it < max_iters and rr > tol * tol * f2:
+        Ap = mv(p)
+        pAp = dev.dotc(p, Ap)
+        pAp = pAp.real if isinstance(pAp, complex) else pAp
+        if not pAp > 0.0:
+            raise np.linalg.LinAlgError("cg_sharded: operator is not Hermitian positive definite")
+        alpha = rr / pAp
+        dev.axpby(alpha, p, 1.0, u, out=u)
+        dev.axpby(-alpha, Ap, 1.0, res, out=res)
+        rr_new = dev.dotc(res, res)
+        rr_new = rr_new.real if isinstance(rr_new, complex) else rr_new
+        dev.axpby(rr_new / rr, p, 1.0, res, out=p)
+        rr = rr_new
+        it += 1
+    return u.reshape(f.shape), it, float(np.sqrt(rr / f2)) if f2 > 0 else 0.0
