@@ -215,3 +215,34 @@ def test_ortho(dev):
         m = c.reshape(c.shape[0], -1)
         assert np.linalg.norm(m @ m.T - np.eye(m.shape[0])) < 1e-12
     assert abs(o.norm() - tt.ones([3, 4, 5], [1, 1, 1], ranks=4).norm()) < 1e-9
+
+
+def test_c2_first_step_and_completion(dev):
+    """BASELINE config 2 at full size.  The reference is chaotic there (tests/test_c2_noise.py), so the check is: the
+    first micro-step -- identical inputs on both sides -- picks the same eigenvalue to the 1e-7 its conditioning allows
+    (|M| ~ 1e8, eigenvalue ~ 1), the sweep completes, and the return types / ranks follow evp.py:168-179."""
+    from scikit_tt_b200.solvers import evp as gevp
+    from oracle import evp as oevp
+    z = load("c2_cooxidation20")
+    op, x0 = cores(z, "op"), cores(z, "x0")
+    first = {}
+    orig, oorig = gevp._local_eig, oevp._local_eig
+
+    def spy(d, M, B, k, solver, sigma):
+        lam, vec = orig(d, M, B, k, solver, sigma)
+        first.setdefault("gpu", complex(lam[0].item()))
+        return lam, vec
+
+    def ospy(M, B, k, solver, sigma, real):
+        lam, vec = oorig(M, B, k, solver, sigma, real)
+        first.setdefault("oracle", complex(lam[0]))
+        return lam, vec
+    gevp._local_eig, oevp._local_eig = spy, ospy
+    try:
+        lam, x, it = gevp.als(TT(op), TT(x0), repeats=1, conv_eps=0, solver='eig')
+        oevp.als(op, x0, repeats=1, conv_eps=0, solver='eig')
+    finally:
+        gevp._local_eig, oevp._local_eig = orig, oorig
+    assert abs(first["gpu"] - first["oracle"]) < 1e-6 * abs(first["oracle"])
+    assert isinstance(lam, float) and isinstance(x, TT) and it == 1
+    assert x.ranks[0] == x.ranks[-1] == 1 and max(x.ranks) <= 8 and np.isfinite(lam)
