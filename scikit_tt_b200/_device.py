@@ -43,6 +43,9 @@ class Device:
             raise SkttError(st, "sktt_ctx_create failed (is this an sm_100 device?)")
         self.h = h
         self._work = {}
+        import os
+        if os.environ.get("SKTT_DEBUG"):                       # diagnostics: see sktt_ctx_set_debug
+            self.lib.sktt_ctx_set_debug(self.h, int(os.environ["SKTT_DEBUG"]))
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -65,7 +68,7 @@ class Device:
         torch.cuda.synchronize(self.device)
 
     def set_debug(self, on):
-        self._check(self.lib.sktt_ctx_set_debug(self.h, int(bool(on))))
+        self._check(self.lib.sktt_ctx_set_debug(self.h, int(on)))
 
     def scratch_peek(self, byte_offset, count, ctype=C.c_uint64):
         """Diagnostics: `count` items of `ctype` from the scalar scratch area of the context (synchronises)."""

@@ -66,7 +66,7 @@ extern "C" int sktt_ctx_set_gemm_mode(sktt_ctx* ctx, int mode) {
 // diagnostics: switch kernel time stamps on/off, read a piece of the scalar scratch area (after a stream sync)
 extern "C" int sktt_ctx_set_debug(sktt_ctx* ctx, int on) {
     if (!ctx) return SKTT_ERR_ARG;
-    ctx->debug = on ? 1 : 0;
+    ctx->debug = on;      // bit 0: kernel time stamps, bit 1: Householder QR only, bit 2: no mode preconditioner
     return 0;
 }
 extern "C" int sktt_scratch_peek(sktt_ctx* ctx, int64_t byte_offset, int64_t bytes, void* out_host) {

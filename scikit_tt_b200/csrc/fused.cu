@@ -69,9 +69,10 @@ constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;   // + one producer warp
 // optional fused reductions / early exit of the Krylov step that owns the matvec (see sktt_fused_matvec_tiled_dots)
 struct MvDots {
     const double* d;       // vector (tiled layout) to reduce against, or nullptr
+    const double* d2;      // second vector: out[1] = <d2, d> (nullptr: out[1] = <d, d>)
     double* part;          // [2 * CTAs] per-CTA partials
     unsigned* counter;     // arrival counter (zero between launches)
-    double* out;           // out[0] = <y, d>, out[1] = <d, d>
+    double* out;           // out[0] = <y, d>, out[1] = <d2, d>
     const int* skip;       // if non-null and *skip != 0 the kernels return at once
 };
 
@@ -425,8 +426,9 @@ mv_stage23_kernel(const double* __restrict__ T1p, const double* __restrict__ Aim
                 *reinterpret_cast<double2*>(Y + idx) = y;
                 if (dots.d) {
                     const double2 dv = *reinterpret_cast<const double2*>(dots.d + idx);
+                    const double2 ev = dots.d2 ? *reinterpret_cast<const double2*>(dots.d2 + idx) : dv;
                     s_yd = fma(y.x, dv.x, fma(y.y, dv.y, s_yd));
-                    s_dd = fma(dv.x, dv.x, fma(dv.y, dv.y, s_dd));
+                    s_dd = fma(ev.x, dv.x, fma(ev.y, dv.y, s_dd));
                 }
             }
         }
@@ -537,11 +539,11 @@ int sktt_fused_from_tiled(sktt_ctx* ctx, long long r, long long n, const double*
 }
 
 // yt = M vt on vectors in the tiled layout; T1p: R * r * n * (r2 + 4) doubles of scratch.  With dvec the second kernel
-// also leaves <yt, dvec> and <dvec, dvec> in dots_out[0..1] (dot_part: 2 * r * m / 32 doubles, counter zeroed once);
+// also leaves <yt, dvec> and <dvec2, dvec> (dvec2 = dvec when null) in dots_out[0..1] (dot_part: 2 * r * m / 32 doubles, counter zeroed once);
 // with skip the launches are no-ops once *skip != 0.
 int sktt_fused_matvec_tiled_dots(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
-                                 const double* vt, double* yt, double* T1p, const double* dvec, double* dot_part,
-                                 unsigned* counter, double* dots_out, const int* skip) {
+                                 const double* vt, double* yt, double* T1p, const double* dvec, const double* dvec2,
+                                 double* dot_part, unsigned* counter, double* dots_out, const int* skip) {
     const int M1 = (int)(R * r), K1 = (int)r;
     const size_t smem1 = s1_smem_bytes(K1);
     static bool configured = false;
@@ -556,7 +558,7 @@ int sktt_fused_matvec_tiled_dots(sktt_ctx* ctx, long long r, long long R, long l
     mv_stage1_kernel<<<g1, THREADS, smem1, ctx->stream>>>(image + na + nr, vt, T1p, M1, K1, (int)n, skip);
     SKTT_LAUNCH_CHECK(ctx);
     dim3 g2((unsigned)r, (unsigned)(m / 32));
-    MvDots dots{dvec, dot_part, counter, dots_out, skip};
+    MvDots dots{dvec, dvec2, dot_part, counter, dots_out, skip};
     mv_stage23_kernel<3, 64, 32><<<g2, THREADS, Cfg::SMEM, ctx->stream>>>(T1p, image, image + na, yt, (int)r, (int)R,
                                                                            (int)m, (int)n, dots);
     SKTT_LAUNCH_CHECK(ctx);
@@ -565,7 +567,8 @@ int sktt_fused_matvec_tiled_dots(sktt_ctx* ctx, long long r, long long R, long l
 
 int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
                             const double* vt, double* yt, double* T1p) {
-    return sktt_fused_matvec_tiled_dots(ctx, r, R, m, n, image, vt, yt, T1p, nullptr, nullptr, nullptr, nullptr, nullptr);
+    return sktt_fused_matvec_tiled_dots(ctx, r, R, m, n, image, vt, yt, T1p, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                        nullptr);
 }
 
 // natural-layout wrapper: v [r][n][64] -> y [r][m][64]; work holds T1p followed by the two tiled vectors

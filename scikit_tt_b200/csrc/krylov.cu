@@ -15,8 +15,8 @@ int sktt_fused_from_tiled(sktt_ctx* ctx, long long r, long long n, const double*
 int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
                             const double* vt, double* yt, double* T1p);
 int sktt_fused_matvec_tiled_dots(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
-                                 const double* vt, double* yt, double* T1p, const double* dvec, double* dot_part,
-                                 unsigned* counter, double* dots_out, const int* skip);
+                                 const double* vt, double* yt, double* T1p, const double* dvec, const double* dvec2,
+                                 double* dot_part, unsigned* counter, double* dots_out, const int* skip);
 
 // The operator as the Krylov loops see it: either the generic contraction chain on natural-layout vectors, or the
 // prepared fused matvec on tiled-layout vectors (all Krylov vectors then live in that layout; padding stays zero).
@@ -53,7 +53,7 @@ static int64_t local_image_bound(const sktt_local_op* op) {
 
 // elements used by the solver proper (vectors of length Nb + small state), excluding matvec scratch
 static int64_t solver_core_work(int method, int restart, int64_t Nb) {
-    if (method == 0) return 4 * Nb + 64;                                  // r, p, Ap (+ s of the fused variant)
+    if (method == 0) return 5 * Nb + 128 * 128 + 64;                      // r, p, Ap (+ s, z, mode preconditioner of the fused variant)
     int64_t m = restart > 0 ? restart : 40;
     return (m + 2) * Nb + (m + 1) * (m + 4) + 4 * (m + 2) + 64;            // V, w, H, givens, g, y, h2
 }
@@ -219,21 +219,123 @@ static int cg_impl(sktt_ctx* ctx, int dtype, const KOp& op, const T* f, T* u, do
 }
 
 // ------------------------------------------------------------------------------------------------
-// CG on the prepared (tiled) operator in the Chronopoulos-Gear form: ONE synchronisation point per iteration.  The matvec
-// w = A r leaves delta = <w, r> and gamma = <r, r> behind (fused into the epilogue of its second kernel), and one vector
-// kernel derives alpha, beta from them and updates p, s = A p, x, r.  Three launches per iteration; a converged solve
-// raises a device flag that turns every later launch of the batch into a no-op, so the host only looks at a pinned
-// mailbox one batch behind.
+// Preconditioned CG on the prepared (tiled) operator in the Chronopoulos-Gear form: ONE synchronisation point per
+// iteration.  z = P^-1 r (mode preconditioner, below), the matvec w = A z leaves delta = <w, z> and gamma = <r, z>
+// behind (fused into the epilogue of its second kernel), and one vector kernel derives alpha, beta from them, updates
+// p, s = A p, x, r and reduces |r|^2 for the convergence test of the next iteration.  Four launches per iteration; a
+// converged solve raises a device flag that turns every later launch of the batch into a no-op, so the host only looks
+// at a pinned mailbox one batch behind.
 //   state (doubles in ctx->scratch): [8] delta, [9] gamma (matvec output) | [12 + 2 k] gamma_old, alpha_old ping-pong
+//                                    [20] |r|^2 of the current residual
 //   ints at byte 192: [0] done, [1] iterations, [2] breakdown
+//
+// Mode preconditioner: P = I (x) Abar (x) I with Abar = sum_{b,b2} tr(L_b) tr(R_b2) A[b,:,:,b2] / (r r2), the partial
+// trace of the micro operator over both rank indices (Hermitian positive definite whenever the micro operator is).  It
+// removes the conditioning of the mode factor -- all of it when the interface bases are random (first sweep), the
+// 64-point Laplacian's share of it later on.  On tiled vectors [n][a][r2 + 4] its inverse is ONE plain GEMM
+// Z[m][:] = sum_n Abar^-1[m][n] V[n][:].
 // ------------------------------------------------------------------------------------------------
-__global__ void cgear_update_kernel(long long n, double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
-                                    double* __restrict__ s, const double* __restrict__ w, const double* dots,
-                                    const double* st_cur, double* st_next, int* flags, double target2) {
+__global__ void __launch_bounds__(256)
+mode_precond_kernel(int r, int R, int n, int R2, int r2, const double* __restrict__ L, const double* __restrict__ A,
+                    const double* __restrict__ Rt, double* __restrict__ Pinv) {
+    // one CTA: traces, Abar, Gauss-Jordan inverse without pivoting (SPD), symmetrised; identity if a pivot is not positive
+    extern __shared__ double sm[];
+    double* M = sm;                 // [n][n + 1]
+    double* X = M + n * (n + 1);    // [n][n + 1]
+    double* tl = X + n * (n + 1);   // [R]
+    double* tr = tl + R;            // [R2]
+    __shared__ int bad;
+    const int tid = threadIdx.x, ld = n + 1;
+    if (tid == 0) bad = 0;
+    for (int b = tid; b < R + R2; b += blockDim.x) {
+        double t = 0.0;
+        if (b < R) for (int c = 0; c < r; ++c) t += L[((size_t)c * R + b) * r + c];
+        else for (int c = 0; c < r2; ++c) t += Rt[((size_t)c * R2 + (b - R)) * r2 + c];
+        (b < R ? tl[b] : tr[b - R]) = t;
+    }
+    __syncthreads();
+    const double scale = 1.0 / ((double)r * (double)r2);
+    for (int e = tid; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e % n;
+        double a = 0.0;
+        for (int b = 0; b < R; ++b)
+            for (int q = 0; q < R2; ++q) a = fma(tl[b] * tr[q], A[(((size_t)b * n + i) * n + j) * R2 + q], a);
+        M[i * ld + j] = a * scale;
+        X[i * ld + j] = i == j ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        const double piv = M[k * ld + k];
+        if (!(piv > 0.0) || !isfinite(piv)) {
+            if (tid == 0) bad = 1;
+            break;                                             // uniform
+        }
+        const double inv = 1.0 / piv;
+        __syncthreads();
+        for (int j = tid; j < n; j += blockDim.x) {
+            M[k * ld + j] *= inv;
+            X[k * ld + j] *= inv;
+        }
+        __syncthreads();
+        for (int e = tid; e < n * n; e += blockDim.x) {
+            const int i = e / n, j = e % n;
+            if (i == k) continue;
+            const double f = M[i * ld + k];
+            if (j != k) M[i * ld + j] = fma(-f, M[k * ld + j], M[i * ld + j]);
+            X[i * ld + j] = fma(-f, X[k * ld + j], X[i * ld + j]);
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x)
+            if (i != k) M[i * ld + k] = 0.0;
+        __syncthreads();
+    }
+    __syncthreads();
+    const int isbad = bad;
+    for (int e = tid; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e % n;
+        Pinv[e] = isbad ? (i == j ? 1.0 : 0.0) : 0.5 * (X[i * ld + j] + X[j * ld + i]);
+    }
+}
+
+// Z[m][j] = sum_n Pinv[m][n] V[n][j] for j < cols (tiled vectors: n rows of `cols` doubles); one CTA per 32 columns
+__global__ void __launch_bounds__(256)
+mode_precond_apply_kernel(int n, long long cols, const double* __restrict__ Pinv, const double* __restrict__ V,
+                          double* __restrict__ Z, const int* __restrict__ skip) {
+    extern __shared__ double sm[];
+    if (skip && *skip) return;
+    double* P = sm;                  // [n][n + 1]
+    double* Vs = P + n * (n + 1);    // [n][32]
+    const int tid = threadIdx.x, ld = n + 1;
+    const long long j0 = (long long)blockIdx.x * 32;
+    for (int e = tid; e < n * n; e += 256) P[(e / n) * ld + e % n] = Pinv[e];
+    for (int e = tid; e < n * 32; e += 256) {
+        const int k = e >> 5, j = e & 31;
+        Vs[e] = j0 + j < cols ? V[(size_t)k * cols + j0 + j] : 0.0;
+    }
+    __syncthreads();
+    const int j = tid & 31;
+    for (int i = tid >> 5; i < n; i += 8) {
+        double a0 = 0.0, a1 = 0.0;
+        int k = 0;
+        for (; k + 1 < n; k += 2) {
+            a0 = fma(P[i * ld + k], Vs[k * 32 + j], a0);
+            a1 = fma(P[i * ld + k + 1], Vs[(k + 1) * 32 + j], a1);
+        }
+        if (k < n) a0 = fma(P[i * ld + k], Vs[k * 32 + j], a0);
+        if (j0 + j < cols) Z[(size_t)i * cols + j0 + j] = a0 + a1;
+    }
+}
+
+__global__ void pcgear_update_kernel(long long n, double* __restrict__ x, double* r, double* __restrict__ p,
+                                     double* __restrict__ s, const double* __restrict__ w, const double* z,
+                                     const double* dots, const double* st_cur, double* st_next, int* flags, double* rr_slot,
+                                     double* partial, unsigned* counter, double target2) {
+    __shared__ double sh[32];
+    __shared__ bool last;
     if (flags[0]) return;
     const double delta = dots[0], gamma = dots[1];
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
-    if (gamma <= target2) {                       // x already solves the system to the requested accuracy
+    if (rr_slot[0] <= target2) {                  // x already solves the system to the requested accuracy
         if (lead) flags[0] = 1;
         return;
     }
@@ -241,7 +343,7 @@ __global__ void cgear_update_kernel(long long n, double* __restrict__ x, double*
     const bool first = gamma_old < 0.0;
     const double beta = first ? 0.0 : gamma / gamma_old;
     const double denom = first ? delta : delta - beta * gamma / alpha_old;
-    if (!(denom > 0.0)) {                         // p^H A p <= 0: not Hermitian positive definite
+    if (!(denom > 0.0) || !(gamma > 0.0)) {       // not Hermitian positive definite (operator or preconditioner)
         if (lead) {
             flags[2] = 1;
             flags[0] = 1;
@@ -249,25 +351,43 @@ __global__ void cgear_update_kernel(long long n, double* __restrict__ x, double*
         return;
     }
     const double alpha = gamma / denom;
+    double acc = 0.0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double ri = r[i];
-        const double pi = fma(beta, p[i], ri);
+        const double pi = fma(beta, p[i], z[i]);
         const double si = fma(beta, s[i], w[i]);
         p[i] = pi;
         s[i] = si;
         x[i] = fma(alpha, pi, x[i]);
-        r[i] = fma(-alpha, si, ri);
+        const double ri = fma(-alpha, si, r[i]);
+        r[i] = ri;
+        acc = fma(ri, ri, acc);
     }
-    if (lead) {
-        st_next[0] = gamma;
-        st_next[1] = alpha;
-        flags[1] += 1;
+    acc = block_sum<double>(acc, sh);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = acc;
+        __threadfence();
+        const unsigned done = atomicAdd(counter, 1u);
+        last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double t = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(partial + i);
+        t = block_sum<double>(t, sh);
+        if (threadIdx.x == 0) {
+            rr_slot[0] = t;                       // read by the next iteration's update (stream order)
+            *counter = 0;
+            st_next[0] = gamma;
+            st_next[1] = alpha;
+            flags[1] += 1;
+        }
     }
 }
 
-// Work layout of the tiled CG (doubles): matvec scratch | r | p | w | s
+// Work layout of the tiled CG (doubles): matvec scratch | r | p | w | s | z | Pinv[n][n]
 struct CgTiledBufs {
-    double *mvwork, *r, *p, *w, *s;
+    double *mvwork, *r, *p, *w, *s, *z, *pinv;
 };
 static CgTiledBufs cg_tiled_bufs(const KOp& op, double* work) {
     CgTiledBufs b;
@@ -276,27 +396,54 @@ static CgTiledBufs cg_tiled_bufs(const KOp& op, double* work) {
     b.p = b.r + op.N;
     b.w = b.p + op.N;
     b.s = b.w + op.N;
+    b.z = b.s + op.N;
+    b.pinv = b.z + op.N;
     return b;
 }
 
-// The CG loop proper: on entry b.r holds the residual of u (tiled layout); iterates until <r, r> <= target2 by the
-// recurrence, u updated in place.  iters_host accumulates.
-static int cg_tiled_core(sktt_ctx* ctx, const KOp& op, const CgTiledBufs& b, double* u, double target2, int max_iters,
-                         int* iters_host, double* rr_host) {
+#define MODE_PRECOND_MAX_N 96      // both n x n buffers of the setup kernel must fit in shared memory
+
+static int cg_tiled_precond_setup(sktt_ctx* ctx, const KOp& op, const CgTiledBufs& b) {
+    const sktt_local_op& o = op.op;
+    const int n = (int)o.n;
+    const size_t smem = ((size_t)2 * n * (n + 1) + o.R + o.R2) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(mode_precond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(mode_precond_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured = true;
+    }
+    mode_precond_kernel<<<1, 256, smem, ctx->stream>>>((int)o.r, (int)o.R, n, (int)o.R2, (int)o.r3, (const double*)o.Lst,
+                                                        (const double*)o.A1, (const double*)o.Rst, b.pinv);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// The CG loop proper: on entry b.r holds the residual of u (tiled layout) and rr its squared norm; iterates until
+// <r, r> <= target2 by the recurrence, u updated in place.  iters_host accumulates.
+static int cg_tiled_core(sktt_ctx* ctx, const KOp& op, const CgTiledBufs& b, double* u, double rr, double target2,
+                         int max_iters, bool precond, int* iters_host, double* rr_host, bool* converged) {
     const long long N = op.N;
     double* slots = (double*)ctx->scratch;
     double* dots = slots + 8;
     double* st = slots + 12;                                   // [2][2]
+    double* rr_slot = slots + 20;
     int* flags = (int*)((char*)ctx->scratch + 192);
     unsigned* counter = (unsigned*)((char*)ctx->scratch + SKTT_SCRATCH_COUNTER_OFF) + 8;
+    unsigned* counter2 = counter + 1;
     double* dpart = (double*)((char*)ctx->scratch + SKTT_SCRATCH_PARTIAL_OFF) + 2 * SKTT_DOT_MAX_BLOCKS;
+    double* upart = dpart + 2 * SKTT_DOT_MAX_BLOCKS;
     double* mbox = (double*)ctx->mailbox;
     const int nb = ew_blocks(ctx, N);
     const sktt_local_op& o = op.op;
+    const int n = (int)o.n;
+    const long long cols = N / n;
+    const size_t smem_apply = ((size_t)n * (n + 1) + (size_t)n * 32) * sizeof(double);
     SKTT_CUDA(ctx, cudaMemsetAsync(b.p, 0, (size_t)3 * N * sizeof(double), ctx->stream));      // p, w, s
-    const double init_state[4] = {-1.0, 0.0, -1.0, 0.0};
+    const double init_state[5] = {-1.0, 0.0, -1.0, 0.0, rr};
     memcpy(mbox + 32, init_state, sizeof(init_state));
-    SKTT_CUDA(ctx, cudaMemcpyAsync(st, mbox + 32, sizeof(init_state), cudaMemcpyHostToDevice, ctx->stream));
+    SKTT_CUDA(ctx, cudaMemcpyAsync(st, mbox + 32, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SKTT_CUDA(ctx, cudaMemcpyAsync(rr_slot, mbox + 36, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     SKTT_CUDA(ctx, cudaMemsetAsync(flags, 0, 4 * sizeof(int), ctx->stream));
     const int batch = 4;
     int status = 0, launched = 0, batches = 0;
@@ -305,11 +452,18 @@ static int cg_tiled_core(sktt_ctx* ctx, const KOp& op, const CgTiledBufs& b, dou
     while (!finished && launched <= max_iters) {
         const int slot = batches & 1;
         for (int q = 0; q < batch && launched <= max_iters; ++q, ++launched) {
-            status = sktt_fused_matvec_tiled_dots(ctx, o.r, o.R, o.m, o.n, (const double*)o.image, b.r, b.w, b.mvwork, b.r,
-                                                  dpart, counter, dots, flags);
+            const double* z = precond ? b.z : b.r;             // unpreconditioned: z aliases r, <r, z> = <r, r>
+            if (precond) {
+                mode_precond_apply_kernel<<<(unsigned)((cols + 31) / 32), 256, smem_apply, ctx->stream>>>(n, cols, b.pinv,
+                                                                                                          b.r, b.z, flags);
+                ctx->launches++;
+            }
+            status = sktt_fused_matvec_tiled_dots(ctx, o.r, o.R, o.m, o.n, (const double*)o.image, z, b.w, b.mvwork, z,
+                                                  precond ? b.r : nullptr, dpart, counter, dots, flags);
             if (status) break;
-            cgear_update_kernel<<<nb, 256, 0, ctx->stream>>>(N, u, b.r, b.p, b.s, b.w, dots, st + 2 * (launched & 1),
-                                                             st + 2 * ((launched + 1) & 1), flags, target2);
+            pcgear_update_kernel<<<nb, 256, 0, ctx->stream>>>(N, u, b.r, b.p, b.s, b.w, z, dots, st + 2 * (launched & 1),
+                                                              st + 2 * ((launched + 1) & 1), flags, rr_slot, upart, counter2,
+                                                              target2);
             ctx->launches++;
         }
         if (status) break;
@@ -323,13 +477,14 @@ static int cg_tiled_core(sktt_ctx* ctx, const KOp& op, const CgTiledBufs& b, dou
         ++batches;
     }
     if (status) return status;
-    SKTT_CUDA(ctx, cudaMemcpyAsync(mbox, dots, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SKTT_CUDA(ctx, cudaMemcpyAsync(mbox, rr_slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SKTT_CUDA(ctx, cudaMemcpyAsync(mflags, flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SKTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (iters_host) *iters_host += mflags[1];
-    if (rr_host) *rr_host = mbox[1];
+    if (rr_host) *rr_host = mbox[0];
     if (mflags[2]) return sktt_fail(ctx, SKTT_ERR_NOCONV, "cg: operator is not Hermitian positive definite (p^H A p <= 0)");
-    if (!mflags[0]) return sktt_fail(ctx, SKTT_ERR_NOCONV, "cg: no convergence within max_iters");
+    if (converged) *converged = mflags[0] != 0;
+    else if (!mflags[0]) return sktt_fail(ctx, SKTT_ERR_NOCONV, "cg: no convergence within max_iters");
     return 0;
 }
 
@@ -364,7 +519,7 @@ static int cg_tiled_impl(sktt_ctx* ctx, const KOp& op, const double* f, double* 
         if (relres_host) *relres_host = 0.0;
         return 0;
     }
-    int st = cg_tiled_core(ctx, op, b, u, tol * tol * fnorm2, max_iters, iters_host, &rr);
+    int st = cg_tiled_core(ctx, op, b, u, rr, tol * tol * fnorm2, max_iters, false, iters_host, &rr, nullptr);
     if (relres_host) *relres_host = sqrt(rr / fnorm2);
     return st;
 }
@@ -390,18 +545,36 @@ static int cg_tiled_refined(sktt_ctx* ctx, const KOp& op, const double* f, doubl
         SKTT_CUDA(ctx, cudaMemcpyAsync(b.r, f, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         rr = fnorm2;
     }
+    // CG runs unpreconditioned first: with the random interface bases of a first sweep the micro operator is close to a
+    // multiple of the identity and converges in a dozen iterations.  A solve that needs more than CG_PLAIN_ITERS builds
+    // the mode preconditioner and restarts preconditioned from its current iterate (and stays preconditioned).
+    const int CG_PLAIN_ITERS = 40;
+    const bool can_precond = op.op.n <= MODE_PRECOND_MAX_N && !(ctx->debug & 4);
+    bool precond = false;
     double prev = 1e300, relres = sqrt(rr / fnorm2);
     int status = 0;
     for (int cycle = 0; cycle < max_cycles; ++cycle) {
         if (relres <= tol || relres > 0.5 * prev) break;
         prev = relres;
-        double rr_rec = 0.0;
-        status = cg_tiled_core(ctx, op, b, u, 0.25 * tol * tol * fnorm2, max_iters, iters_host, &rr_rec);
+        double rr_rec = rr;
+        bool conv = false;
+        const double target2 = 0.25 * tol * tol * fnorm2;
+        if (!precond) {
+            status = cg_tiled_core(ctx, op, b, u, rr, target2, can_precond ? CG_PLAIN_ITERS : max_iters, false, iters_host,
+                                   &rr_rec, &conv);
+            if (status == 0 && !conv && can_precond) {
+                SKTT_TRY(cg_tiled_precond_setup(ctx, op, b));
+                precond = true;
+                status = cg_tiled_core(ctx, op, b, u, rr_rec, target2, max_iters, true, iters_host, &rr_rec, &conv);
+            }
+        } else {
+            status = cg_tiled_core(ctx, op, b, u, rr, target2, max_iters, true, iters_host, &rr_rec, &conv);
+        }
         if (status != 0 && status != SKTT_ERR_NOCONV) return status;
         SKTT_TRY(cg_tiled_residual(ctx, op, b, f, u, nullptr, &rr));
         relres = sqrt(rr / fnorm2);
         if (cycles_host) *cycles_host = cycle + 1;
-        if (status == SKTT_ERR_NOCONV) break;                  // breakdown / iteration limit: judged by the true residual
+        if (status == SKTT_ERR_NOCONV || !conv) break;          // breakdown / iteration limit: judged by the true residual
     }
     if (relres_host) *relres_host = relres;
     return 0;

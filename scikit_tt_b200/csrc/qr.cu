@@ -9,15 +9,17 @@
 // The loader/storer take signed strides + conjugation so that RQ is QR of the row-reversed
 // conjugate transpose without any HBM-side permutation.
 //
-// Fast path for tall matrices with few columns (the ALS unfoldings: 4096 x 64 at the bench shape): cholqr_kernel, an
-// adaptive (shifted) CholeskyQR in ONE cooperative launch -- rows stay in shared memory, per pass a Gram matrix
-// (deterministic two-level reduction, two grid barriers), its Cholesky factor and triangular inverse (computed
-// redundantly and bit-identically by every CTA), and the multiplication of the local rows.  Passes repeat until the Gram
-// matrix of the current Q is the identity to working precision; a Cholesky breakdown adds the shift of Fukaya et al.
-// (sCholQR3).  The economic Q of a full-rank matrix is unique up to the signs of its columns, so this Q equals LAPACK's
-// Householder Q up to a diagonal +-1 (an exact symmetry of every later step of the sweep).  If the passes do not
-// converge (numerically rank-deficient input) a device flag makes the Householder kernel below run instead; with the
-// flag clear that kernel exits at once, so the host never waits on the decision.
+// Fast path for tall matrices with few columns (the ALS unfoldings: 4096 x 64 at the bench shape): cholqr_kernel, a
+// randomised (sketch-preconditioned) CholeskyQR in ONE cooperative launch -- rows stay in shared memory; a CTA-local
+// CountSketch of the rows, the Householder R factor of that small sketch (the accuracy anchor), rows <- rows R_s^-1 by
+// forward substitution, then CholeskyQR passes on the now well-conditioned rows: Gram matrix (deterministic two-level
+// reduction, two grid barriers), Cholesky factor (computed redundantly and bit-identically by every CTA), substitution,
+// and a Newton-Schulz finish.  The economic Q of a full-rank matrix is unique up to the signs of its columns, so this Q
+// equals LAPACK's Householder Q up to a diagonal +-1 (an exact symmetry of every later step of the sweep); for numerically
+// rank-deficient unfoldings (the usual case for converged ALS cores) it keeps the small singular directions as
+// accurately as Householder QR does -- plain CholeskyQR does not, and the sweep is sensitive to exactly those.  If the
+// passes do not converge a device flag makes the Householder kernel below run instead; with the flag clear that kernel
+// exits at once, so the host never waits on the decision.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -354,15 +356,90 @@ __device__ __noinline__ void cq_cholesky(T* Gs, const int LD, const int NN, cons
     }
 }
 
+// R factor of the K x n matrix Y ([K][LD] in shared memory) by Householder reflections, whole CTA, LAPACK geqr2
+// conventions; R is left in the upper triangle of the first n rows.  This is the accuracy anchor of the sketched path
+// below: small (K = 4 n rows), so the serial chain of n reflectors costs tens of microseconds, not a millisecond.
+template <typename T>
+__device__ __noinline__ void cq_house_r(T* Y, const int LD, const int K, const int n, double* red, T* wv, T* wpart) {
+    // n <= 64.  Threads form a 16 x 16 grid: ty strides the rows, tx the trailing columns (at most four per thread).
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int kk = min(K, n);
+    for (int j = 0; j < kk; ++j) {
+        double part = 0.0;
+        for (int i = j + 1 + tid; i < K; i += CQ_THREADS) part += Num<T>::abs2(Y[i * LD + j]);
+        const double sigma = block_sum<double>(part, red);
+        const T alpha = Y[j * LD + j];
+        const double ar = Num<T>::real(alpha), ai = Num<T>::imag(alpha);
+        T tau = Num<T>::zero(), scl = Num<T>::zero();
+        double beta = ar;
+        if (!(sigma == 0.0 && ai == 0.0)) {
+            const double nrm = sqrt(ar * ar + ai * ai + sigma);
+            beta = ar >= 0.0 ? -nrm : nrm;
+            tau = Num<T>::from((beta - ar) / beta, -ai / beta);
+            scl = Num<T>::div(Num<T>::one(), Num<T>::from(ar - beta, ai));
+        }
+        // partial w[c] = sum over this thread's rows of conj(v_i) y_ic   (v_j = 1, v_i = y_ij * scl)
+        T acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = Num<T>::zero();
+        for (int i = j + ty; i < K; i += 16) {
+            const T cvi = i == j ? Num<T>::one() : Num<T>::conj(Num<T>::mul(Y[i * LD + j], scl));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = j + 1 + tx + 16 * q;
+                if (c < n) Num<T>::fma(acc[q], cvi, Y[i * LD + c]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = j + 1 + tx + 16 * q;
+            if (c < n) wpart[ty * 64 + c] = acc[q];
+        }
+        __syncthreads();
+        if (tid < n - j - 1) {
+            const int c = j + 1 + tid;
+            T sacc = Num<T>::zero();
+#pragma unroll
+            for (int t = 0; t < 16; ++t) sacc = Num<T>::add(sacc, wpart[t * 64 + c]);
+            wv[c] = Num<T>::mul(Num<T>::conj(tau), sacc);
+        }
+        __syncthreads();
+        for (int i = j + ty; i < K; i += 16) {
+            const T vi = i == j ? Num<T>::one() : Num<T>::mul(Y[i * LD + j], scl);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = j + 1 + tx + 16 * q;
+                if (c < n) Y[i * LD + c] = Num<T>::sub(Y[i * LD + c], Num<T>::mul(vi, wv[c]));
+            }
+        }
+        __syncthreads();
+        if (tid == 0) Y[j * LD + j] = Num<T>::from(beta, 0.0);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ unsigned cq_hash(unsigned x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+
 template <typename T, int NT>
 __global__ void __launch_bounds__(CQ_THREADS)
 cholqr_kernel(const T* __restrict__ src, QrView lv, int m, int n, int rows_per_cta, T* __restrict__ qdst, QrView qv,
-              T* __restrict__ rdst, QrView rv, T* part, T* gfull, T* rstack, int* status, unsigned long long* dbg) {
+              T* __restrict__ rdst, QrView rv, T* part, T* gfull, T* rstack, int* status, unsigned long long* dbg,
+              int sketch_k, T* ysk) {
     constexpr int NN = 16 * NT, LD = NN + 1, E = NN * NN;
     extern __shared__ unsigned char smem_raw[];
     T* tile = (T*)smem_raw;                         // [rows_per_cta][LD]
     T* Gs = tile + (size_t)rows_per_cta * LD;       // [NN][LD]  Gram matrix -> Cholesky factor R (upper)
     T* Xs = Gs + (size_t)NN * LD;                   // [NN][LD]  second buffer of the R product (only when R is wanted)
+    T* Ys = Xs + (rdst ? (size_t)NN * LD : 0);      // [sketch_k][LD]   sketch of the matrix (sketched path only)
+    __shared__ T wv[NN];
+    __shared__ T wpart[NT <= 4 ? 16 * 64 : 1];          // partial sums of the sketch Householder (sketched path: n <= 64)
     __shared__ double red[32];
     __shared__ double dinv[NN];                     // 1 / R_jj
     __shared__ double csc[NN];                      // column scaling 1 / sqrt(G_jj)
@@ -391,6 +468,121 @@ cholqr_kernel(const T* __restrict__ src, QrView lv, int m, int n, int rows_per_c
 
     int fail = 0, passes = 0;
     bool done = false;
+
+    // ---- local rows <- rows * diag(csc) * R^-1 by forward substitution (row-wise backward stable, unlike a product
+    //      with an explicit inverse): a warp owns rows warp, warp + 8, ...; lanes own columns lane + 32 q
+    auto substitute = [&](const int nrepl, const int pass) {
+        constexpr int NQ = (NN + 31) / 32, RB = 4, NW = CQ_THREADS / 32;
+        for (int r0 = warp; r0 < nrows; r0 += NW * RB) {
+            T a[RB][NQ];
+#pragma unroll
+            for (int b2 = 0; b2 < RB; ++b2)
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const int rr = r0 + NW * b2, c = lane + 32 * q;
+                    a[b2][q] = (rr < nrows && c < n) ? Num<T>::scale(tile[rr * LD + c], csc[c]) : Num<T>::zero();
+                }
+            for (int j = 0; j < n; ++j) {
+                const int owner = j & 31, qj = j >> 5;
+                const double di = dinv[j];
+                T rj[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const int c = lane + 32 * q;
+                    rj[q] = (c > j && c < n) ? Gs[j * LD + c] : Num<T>::zero();
+                }
+#pragma unroll
+                for (int b2 = 0; b2 < RB; ++b2) {
+                    T piv = a[b2][0];
+#pragma unroll
+                    for (int q = 1; q < NQ; ++q)
+                        if (qj == q) piv = a[b2][q];
+                    const T x = Num<T>::scale(lane_bcast<T>(piv, owner), di);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int c = lane + 32 * q;
+                        if (c == j) a[b2][q] = x;
+                        else a[b2][q] = Num<T>::sub(a[b2][q], Num<T>::mul(x, rj[q]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int b2 = 0; b2 < RB; ++b2)
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const int rr = r0 + NW * b2, c = lane + 32 * q;
+                    if (rr < nrows && c < n) {
+                        T v = a[b2][q];
+                        if (nrepl > 0 && repl[c]) {      // unit vector e_h, h spread over the rows and moved per pass
+                            const long long h = ((long long)c * (m / n) + 7LL * pass + 1) % m;
+                            v = (row_begin + rr == h) ? Num<T>::one() : Num<T>::zero();
+                        }
+                        tile[rr * LD + c] = v;
+                    }
+                }
+        }
+    };
+
+
+    // ---- sketched preconditioning (randomised CholeskyQR): a CountSketch of the rows that is local to each CTA (rows hashed
+    //      into the CTA's own buckets with random signs: no cross-CTA reduction), Householder R_s of the small sketch, and
+    //      rows <- rows R_s^-1.  The result has a condition number of order 10 whatever the input's, and its span and small
+    //      singular directions are as accurate as those of a Householder QR of the full matrix (the ALS sweep needs them:
+    //      plain CholeskyQR loses them in the Gram matrix and one sweep ends at 1e-6 instead of 1e-12 at the bench shape).
+    int rbase = 0;
+    if (sketch_k > 0) {
+        const int kb = sketch_k / G;
+        for (int e = tid; e < kb * NN; e += CQ_THREADS) {
+            const int q = e / NN, c = e % NN;
+            T acc = Num<T>::zero();
+            for (int rr = 0; rr < nrows; ++rr) {
+                const unsigned h = cq_hash((unsigned)(row_begin + rr) * 2654435761u + 12345u);
+                if ((int)(h % (unsigned)kb) == q) {
+                    const T t = tile[rr * LD + c];
+                    acc = (h & 0x10000u) ? Num<T>::add(acc, t) : Num<T>::sub(acc, t);
+                }
+            }
+            ysk[(size_t)(cta * kb + q) * NN + c] = acc;
+        }
+        __threadfence();
+        grid.sync();
+        for (int e = tid; e < sketch_k * NN; e += CQ_THREADS) Ys[(e / NN) * LD + e % NN] = ld_cg<T>(ysk + e);
+        __syncthreads();
+        stamp();
+        cq_house_r<T>(Ys, LD, sketch_k, n, red, wv, wpart);
+        stamp();
+        // R_s -> Gs; diagonals below 1e-15 of the largest are floored and their rows decoupled (numerically null columns)
+        double dmax = 0.0;
+        for (int j = 0; j < n; ++j) dmax = fmax(dmax, fabs(Num<T>::real(Ys[j * LD + j])));
+        for (int e = tid; e < E; e += CQ_THREADS) {
+            const int i = e / NN, c = e % NN;
+            T v = Num<T>::zero();
+            if (i < n && c < n && c >= i) {
+                const double dii = Num<T>::real(Ys[i * LD + i]);
+                const bool tiny = !(fabs(dii) > 1e-15 * dmax);
+                if (c == i) v = Num<T>::from(tiny ? fmax(1e-15 * dmax, 1e-300) : dii, 0.0);
+                else if (!tiny) v = Ys[i * LD + c];
+            } else if (i == c) v = Num<T>::one();
+            Gs[i * LD + c] = v;
+        }
+        __syncthreads();
+        if (tid < NN) {
+            dinv[tid] = 1.0 / Num<T>::real(Gs[tid * LD + tid]);
+            csc[tid] = 1.0;
+            repl[tid] = 0;
+        }
+        __syncthreads();
+        substitute(0, 0);
+        if (rdst && cta == 0)
+            for (int e = tid; e < E; e += CQ_THREADS) {
+                const int i = e / NN, c = e % NN;
+                rstack[e] = (i < n && c < n && c >= i) ? Gs[i * LD + c] : Num<T>::zero();
+            }
+        __syncthreads();
+        stamp();
+        rbase = 1;
+    }
+
     for (int pass = 0; pass < CQ_MAX_PASSES && !done; ++pass) {
         // ---- partial Gram matrix of the local rows: P[j1][j2] = sum_i conj(t[i][j1]) t[i][j2]
         {
@@ -518,65 +710,13 @@ cholqr_kernel(const T* __restrict__ src, QrView lv, int m, int n, int rows_per_c
         stamp();
         const int nrepl = __syncthreads_count(tid < n && repl[tid]);
         if (nrepl > 0) last = false;
-        // ---- local rows <- rows * diag(csc) * R^-1 by forward substitution (row-wise backward stable, unlike a product
-        //      with an explicit inverse): a warp owns rows warp, warp + 8, ...; lanes own columns lane + 32 q
-        {
-            constexpr int NQ = (NN + 31) / 32, RB = 4, NW = CQ_THREADS / 32;
-            for (int r0 = warp; r0 < nrows; r0 += NW * RB) {
-                T a[RB][NQ];
-#pragma unroll
-                for (int b2 = 0; b2 < RB; ++b2)
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const int rr = r0 + NW * b2, c = lane + 32 * q;
-                        a[b2][q] = (rr < nrows && c < n) ? Num<T>::scale(tile[rr * LD + c], csc[c]) : Num<T>::zero();
-                    }
-                for (int j = 0; j < n; ++j) {
-                    const int owner = j & 31, qj = j >> 5;
-                    const double di = dinv[j];
-                    T rj[NQ];
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const int c = lane + 32 * q;
-                        rj[q] = (c > j && c < n) ? Gs[j * LD + c] : Num<T>::zero();
-                    }
-#pragma unroll
-                    for (int b2 = 0; b2 < RB; ++b2) {
-                        T piv = a[b2][0];
-#pragma unroll
-                        for (int q = 1; q < NQ; ++q)
-                            if (qj == q) piv = a[b2][q];
-                        const T x = Num<T>::scale(lane_bcast<T>(piv, owner), di);
-#pragma unroll
-                        for (int q = 0; q < NQ; ++q) {
-                            const int c = lane + 32 * q;
-                            if (c == j) a[b2][q] = x;
-                            else a[b2][q] = Num<T>::sub(a[b2][q], Num<T>::mul(x, rj[q]));
-                        }
-                    }
-                }
-#pragma unroll
-                for (int b2 = 0; b2 < RB; ++b2)
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const int rr = r0 + NW * b2, c = lane + 32 * q;
-                        if (rr < nrows && c < n) {
-                            T v = a[b2][q];
-                            if (nrepl > 0 && repl[c]) {      // unit vector e_h, h spread over the rows and moved per pass
-                                const long long h = ((long long)c * (m / n) + 7LL * pass + 1) % m;
-                                v = (row_begin + rr == h) ? Num<T>::one() : Num<T>::zero();
-                            }
-                            tile[rr * LD + c] = v;
-                        }
-                    }
-            }
-        }
+        substitute(nrepl, pass);
         if (rdst && cta == 0)                                  // R of this pass in the unscaled columns; replaced rows drop out
             for (int e = tid; e < E; e += CQ_THREADS) {
                 const int i = e / NN, c = e % NN;
                 T v = Num<T>::zero();
                 if (i < n && c < n && c >= i && !repl[i] && csc[c] > 0.0) v = Num<T>::scale(Gs[i * LD + c], 1.0 / csc[c]);
-                rstack[(size_t)pass * E + e] = v;
+                rstack[(size_t)(pass + rbase) * E + e] = v;
             }
         __syncthreads();
         stamp();
@@ -598,7 +738,7 @@ cholqr_kernel(const T* __restrict__ src, QrView lv, int m, int n, int rows_per_c
             __syncthreads();
             for (int e = tid; e < E; e += CQ_THREADS) Gs[(e / NN) * LD + e % NN] = rstack[e];
             __syncthreads();
-            for (int p = 1; p < passes; ++p) {
+            for (int p = 1; p < passes + rbase; ++p) {
                 for (int e = tid; e < E; e += CQ_THREADS) Xs[(e / NN) * LD + e % NN] = rstack[(size_t)p * E + e];
                 __syncthreads();
                 T acc[NT][NT];
@@ -646,23 +786,31 @@ static int cholqr_launch_nt(sktt_ctx* ctx, int m, int n, const T* src, QrView lv
     if (G > ctx->sm_count) G = ctx->sm_count;
     int rows_per_cta = (m + G - 1) / G;
     G = (m + rows_per_cta - 1) / rows_per_cta;
-    const size_t smem = ((size_t)rows_per_cta * LD + (size_t)(rdst ? 2 : 1) * NN * LD) * sizeof(T);
+    // sketch: K = G * kb rows (about 2 n: as good a preconditioner as 4 n in practice, half the serial work), kb buckets per CTA
+    const bool plain = (ctx->debug & 8) != 0;                             // experiments only: CholeskyQR without the sketch
+    const int target = 2 * NN;
+    int kb = (target + G - 1) / G;
+    int sketch_k = plain ? 0 : G * kb;
+    if (!plain && (kb > rows_per_cta || sketch_k > m / 2)) return 0;      // too few rows to sketch: Householder path
+    const size_t smem = ((size_t)rows_per_cta * LD + (size_t)(rdst ? 2 : 1) * NN * LD + (size_t)sketch_k * LD) * sizeof(T);
     if (smem > budget) return 0;                                          // not for this kernel: Householder path
-    // scratch: partial Gram matrices | reduced Gram matrix | R factors of the passes; sized for the fallback as well
-    const size_t mine = ((size_t)G * E + E + (size_t)CQ_MAX_PASSES * E) * sizeof(T);
+    // scratch: partial Gram matrices | reduced Gram matrix | R factors of the passes | sketch; sized for the fallback too
+    const size_t mine = ((size_t)G * E + E + (size_t)(CQ_MAX_PASSES + 1) * E + (size_t)sketch_k * NN) * sizeof(T);
     const size_t theirs = ((size_t)2 * QR_MAX_CTAS * n + 2 * n) * sizeof(T);
     SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (mine > theirs ? mine : theirs) + 4096));
     T* part = (T*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
     T* gfull = part + (size_t)G * E;
     T* rstack = gfull + E;
+    T* ysk = rstack + (size_t)(CQ_MAX_PASSES + 1) * E;
     int* status = (int*)((char*)ctx->scratch + CQ_STATUS_OFF);
     static bool configured = false;
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(cholqr_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         configured = true;
     }
-    unsigned long long* dbg = ctx->debug ? (unsigned long long*)((char*)ctx->scratch + CQ_DEBUG_OFF) : nullptr;
-    void* args[] = {&src, &lv, &m, &n, &rows_per_cta, &qdst, &qv, &rdst, &rv, &part, &gfull, &rstack, &status, &dbg};
+    unsigned long long* dbg = (ctx->debug & 1) ? (unsigned long long*)((char*)ctx->scratch + CQ_DEBUG_OFF) : nullptr;
+    void* args[] = {&src, &lv, &m, &n, &rows_per_cta, &qdst, &qv, &rdst, &rv, &part, &gfull, &rstack, &status, &dbg,
+                    &sketch_k, &ysk};
     SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)cholqr_kernel<T, NT>, dim3(G), dim3(CQ_THREADS), args, smem,
                                                ctx->stream));
     ctx->launches++;
@@ -670,20 +818,16 @@ static int cholqr_launch_nt(sktt_ctx* ctx, int m, int n, const T* src, QrView lv
     return 0;
 }
 
-// Orthonormal factor of a tall matrix: CholeskyQR first, Householder behind its failure flag.
+// Orthonormal factor of a tall matrix: sketched CholeskyQR first, Householder behind its failure flag.
 template <typename T>
 static int qr_dispatch(sktt_ctx* ctx, int m, int n, const T* src, QrView lv, T* qdst, QrView qv, T* rdst, QrView rv,
                        bool allow_chol) {
     bool used = false;
-    if (allow_chol && m >= 2 * n && m >= 64 && ctx->gemm_mode != 1) {
+    if (allow_chol && m >= 8 * n && m >= 64 && ctx->gemm_mode != 1 && !(ctx->debug & 2)) {
         const int nt = (n + 15) / 16;
         if (nt <= 1) SKTT_TRY((cholqr_launch_nt<T, 1>(ctx, m, n, src, lv, qdst, qv, rdst, rv, &used)));
         else if (nt <= 2) SKTT_TRY((cholqr_launch_nt<T, 2>(ctx, m, n, src, lv, qdst, qv, rdst, rv, &used)));
         else if (nt <= 4) SKTT_TRY((cholqr_launch_nt<T, 4>(ctx, m, n, src, lv, qdst, qv, rdst, rv, &used)));
-        else if (nt <= 6) SKTT_TRY((cholqr_launch_nt<T, 6>(ctx, m, n, src, lv, qdst, qv, rdst, rv, &used)));
-        else if (nt <= 8 && !Num<T>::is_complex)
-            SKTT_TRY((cholqr_launch_nt<double, 8>(ctx, m, n, (const double*)src, lv, (double*)qdst, qv, (double*)rdst, rv,
-                                                  &used)));
     }
     const int* flag = used ? (const int*)((char*)ctx->scratch + CQ_STATUS_OFF) : nullptr;
     return qr_launch<T>(ctx, m, n, src, lv, qdst, qv, rdst, rv, flag);
