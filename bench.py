@@ -7,7 +7,8 @@ Workload (config.workload = "C3"): synthetic discretised-Laplacian TT operator d
 8d: SLIM layout, symmetric positive definite), right-hand side rank 1 (seed 0), initial guess with interior solution
 rank 64 (seed 1, right-orthonormalised).  One *step* = one `sle.als(op, x0, rhs, repeats=1)` = 2 half-sweeps
 (forward + backward) over the 32 cores: 64 interface-stack updates, 63 micro systems of 262 144 unknowns solved
-matrix-free (CG to 1e-13; the reference's dense micro matrix would be 512 GiB), 62 QR/RQ factorisations.
+matrix-free (CG to a TRUE relative residual of 1e-14; the reference's dense micro matrix would be 512 GiB), 62 QR/RQ
+factorisations of 4096 x 64 unfoldings.
 
 `value`  : half-sweeps/s with operator, right-hand side and initial guess resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same call through the public API with host numpy TT cores in and out (H2D + D2H inside the timed region).
@@ -35,6 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FP64_TENSOR_PEAK_TFLOPS = 37.1      # measured on this pool's B200: profiles/r01_fp64_peaks.txt (DMMA m8n8k4, sustained)
+NCU_MATVEC_DRAM_BYTES = 2345472 + 9412352   # profiles/r01_ncu_final_full.txt, one launch of each matvec kernel
 
 
 # ------------------------------------------------------------------------------------------------ workload
@@ -156,7 +158,8 @@ def run_reference(args, cfg):
 def cfg_public(cfg):
     return {"workload": "C3: sle.als on the rank-3 Laplacian-type TT operator", "d": cfg["d"], "n": cfg["n"],
             "operator_rank": 3, "solution_rank": cfg["r"], "repeats_per_step": 1, "half_sweeps_per_step": 2,
-            "micro_solver": "matrix-free CG, relative residual 1e-13 (dense micro matrix impossible at this size)",
+            "micro_solver": "matrix-free CG (Chronopoulos-Gear form, reductions fused into the matvec), true relative "
+                            "residual 1e-14 (dense micro matrix impossible at this size)",
             "l2": "256 MiB buffer written between steps (inside the timed region)",
             "parallelism": "replicas" if cfg["gpus"] > 1 else "single GPU"}
 
@@ -263,6 +266,20 @@ def run_ours(args, cfg):
     mv_ms = m0.elapsed_time(m1) / reps
     achieved = F / (mv_ms * 1e-3) / 1e12
 
+    # the interface-stack update itself (same flop count; generic strided-GEMM chain of stacks.cu)
+    xs, Ls = st.x[i - 1], st.Lop[i - 1]
+    for _ in range(5):
+        dev.stack_left_op(Ls, xs, st.A[i - 1])
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(50):
+        dev.stack_left_op(Ls, xs, st.A[i - 1])
+    s1.record()
+    torch.cuda.synchronize()
+    stack_ms = s0.elapsed_time(s1) / 50
+    F_stack = stack_flops(Ls.shape[0], st.A[i - 1].shape[0], st.A[i - 1].shape[2], xs.shape[2], st.A[i - 1].shape[3])
+
     if rank == 0:
         half_sweeps = 2 * args.steps * world
         sol = result["x"]
@@ -279,9 +296,19 @@ def run_ours(args, cfg):
                 "gpu_launches": launches,
                 "clocks": clocks,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-                             "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": None,
-                             "kernel": "mv_stage1_kernel + mv_stage23_kernel = one micro-matvec (same F as a stack update; r=64, R=3, n=64)",
+                             "frac": achieved / FP64_TENSOR_PEAK_TFLOPS,
+                             "traffic": NCU_MATVEC_DRAM_BYTES,
+                             "traffic_note": "dram__bytes_read+write per matvec (mv_stage1 2.35 MB + mv_stage23 9.41 MB) from "
+                                             "profiles/r01_ncu_final_full.txt; ncu flushes the caches per replay, inside the CG "
+                                             "loop every operand is L2-resident; algorithmic bytes 4.72 MB",
+                             "kernel": "mv_stage1_kernel + mv_stage23_kernel = one micro-matvec = the contraction chain of one "
+                                       "interface-stack update (r=64, R=3, n=64); dominant kernels of the step "
+                                       "(profiles/r01_launches_final_summary.txt: 51 % of device time)",
                              "flops_per_matvec": F, "us_per_matvec": mv_ms * 1e3,
+                             "stack_update": {"kernel": "sktt_stack_left_op (three strided DMMA GEMMs + split-K reduce)",
+                                              "flops": F_stack, "us": stack_ms * 1e3,
+                                              "achieved": F_stack / (stack_ms * 1e-3) / 1e12,
+                                              "frac": F_stack / (stack_ms * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS},
                              "peak_source": "measured fp64 DMMA pipe peak, profiles/r01_fp64_peaks.txt "
                                             "(MEASURED_PEAKS.json has no fp64 entry)"},
                 "residual": res}
