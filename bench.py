@@ -265,6 +265,10 @@ def run_ours(args, cfg):
     torch.cuda.synchronize()
     mv_ms = m0.elapsed_time(m1) / reps
     achieved = F / (mv_ms * 1e-3) / 1e12
+    Ah = opc[i]
+    nnz_blocks = int(sum(bool(np.any(Ah[b, :, :, q])) for b in range(Ah.shape[0]) for q in range(Ah.shape[3])))
+    rr_, R_, n_, r2_, R2_ = L.shape[0], A.shape[0], A.shape[2], R.shape[0], A.shape[3]
+    F_exec = 2 * rr_ * R_ * rr_ * n_ * r2_ + 2 * rr_ * r2_ * nnz_blocks * n_ * n_ + 2 * r2_ * R2_ * rr_ * n_ * r2_
 
     # the interface-stack update itself (same flop count; generic strided-GEMM chain of stacks.cu)
     xs, Ls = st.x[i - 1], st.Lop[i - 1]
@@ -305,6 +309,11 @@ def run_ours(args, cfg):
                                        "interface-stack update (r=64, R=3, n=64); dominant kernels of the step "
                                        "(profiles/r01_launches_final_summary.txt: 51 % of device time)",
                              "flops_per_matvec": F, "us_per_matvec": mv_ms * 1e3,
+                             "executed_flops_per_matvec": F_exec,
+                             "executed_note": "F is the dense formula of SURVEY.md 8d; the kernel skips the zero (b, b') "
+                                              f"blocks of the operator core ({nnz_blocks} of {A.shape[0] * A.shape[3]} non-zero "
+                                              "here), so the tensor pipe executes executed_flops_per_matvec",
+                             "achieved_executed": F_exec / (mv_ms * 1e-3) / 1e12,
                              "stack_update": {"kernel": "sktt_stack_left_op (three strided DMMA GEMMs + split-K reduce)",
                                               "flops": F_stack, "us": stack_ms * 1e3,
                                               "achieved": F_stack / (stack_ms * 1e-3) / 1e12,

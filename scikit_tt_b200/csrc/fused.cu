@@ -266,7 +266,7 @@ __global__ void from_tiled_kernel(const double* __restrict__ src, double* __rest
 template <int RB, int NA, int MB>
 __global__ void __launch_bounds__(THREADS)
 mv_stage23_kernel(const double* __restrict__ T1p, const double* __restrict__ Aimg, const double* __restrict__ Rimg,
-                  double* __restrict__ Y, int r, int R, int mtot, int ntot, MvDots dots) {
+                  double* __restrict__ Y, int r, int R, int mtot, int ntot, long long mask_off, MvDots dots) {
     using P = S23<RB, NA, MB>;
     constexpr int KC = P::KC, LDB = P::LDB, LDA = P::LDA, LDT = P::LDT, STAGES = P::STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -278,6 +278,8 @@ mv_stage23_kernel(const double* __restrict__ T1p, const double* __restrict__ Aim
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x, mblk = blockIdx.y, m0 = mblk * MB;
     const int nchunks_n = ntot / KC;
+    const unsigned long long blockmask =
+        *reinterpret_cast<const unsigned long long*>(Rimg + (size_t)(P::K3 / KC) * P::B_ELEMS + mask_off);
     const int T2n = R * nchunks_n;                         // chunks of the second contraction: (b, n-chunk)
     const int T3n = P::K3 / KC;                            // chunks of the third contraction
     const int total = T2n + T3n;
@@ -337,21 +339,23 @@ mv_stage23_kernel(const double* __restrict__ T1p, const double* __restrict__ Aim
         const double* bs = slot + wn0 + fr;
         if (t < T2n) {
             const double* as = slot + P::B_ELEMS + (size_t)(wm0 + fr) * LDA + fk;
+            const unsigned qmask = (unsigned)(blockmask >> ((t / nchunks_n) * RB)) & ((1u << RB) - 1u);   // warp-uniform
 #pragma unroll
             for (int kk = kbeg; kk < kbeg + KC / 2; kk += 4) {
-                double bf[2], af[RB][2];
+                double bf[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) bf[j] = bs[(kk + fk) * LDB + 8 * j];
 #pragma unroll
-                for (int q = 0; q < RB; ++q)
+                for (int q = 0; q < RB; ++q) {
+                    if (!((qmask >> q) & 1u)) continue;    // A[b, :, :, q] == 0
+                    double af[2];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) af[q][i] = as[((size_t)q * MB + 8 * i) * LDA + kk];
-#pragma unroll
-                for (int q = 0; q < RB; ++q)
+                    for (int i = 0; i < 2; ++i) af[i] = as[((size_t)q * MB + 8 * i) * LDA + kk];
 #pragma unroll
                     for (int i = 0; i < 2; ++i)
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) dmma(acc2[q][i][j][0], acc2[q][i][j][1], af[q][i], bf[j]);
+                        for (int j = 0; j < 2; ++j) dmma(acc2[q][i][j][0], acc2[q][i][j][1], af[i], bf[j]);
+                }
             }
         } else {
             const int k0 = (t - T2n) * KC;
@@ -485,6 +489,19 @@ mv_stage23_kernel(const double* __restrict__ T1p, const double* __restrict__ Aim
     }
 }
 
+// Operator cores of SLIM / MPO type are block-sparse in their rank indices (the bench operator has 5 non-zero blocks of
+// 9): one CTA per (b, q) block ORs a bit into the mask word, and the second contraction skips the zero blocks -- adding
+// exact zeros changes no sum.
+__global__ void mv_mask_kernel(const double* __restrict__ A, unsigned long long* __restrict__ mask, int RB, int mtot,
+                               int ntot) {
+    const int b = blockIdx.x / RB, q = blockIdx.x % RB;
+    int nz = 0;
+    for (int e = threadIdx.x; e < mtot * ntot; e += blockDim.x)
+        nz |= A[((size_t)b * mtot * ntot + e) * RB + q] != 0.0;
+    nz = __syncthreads_or(nz);
+    if (threadIdx.x == 0 && nz) atomicOr(mask, 1ull << (b * RB + q));
+}
+
 using Cfg = S23<3, 64, 32>;
 
 }  // namespace
@@ -504,8 +521,9 @@ static long long img_a_elems(long long R, long long m, long long n) { return R *
 static long long img_r_elems() { return (long long)(Cfg::K3 / Cfg::KC) * Cfg::B_ELEMS; }
 static long long img_l_elems(long long r, long long R) { return ((R * r + S1_BM - 1) / S1_BM) * r * S1_LDA; }
 
+// image = [Aimg | Rimg | Limg | mask]; mask: one 64-bit word, bit b * RB + q set iff A[b, :, :, q] has a non-zero entry
 long long sktt_fused_image_elems(long long r, long long R, long long m, long long n) {
-    return img_a_elems(R, m, n) + img_r_elems() + img_l_elems(r, R);
+    return img_a_elems(R, m, n) + img_r_elems() + img_l_elems(r, R) + 8;
 }
 // length of a vector of the micro system in the tiled layout [n][a][r2 + 4]
 long long sktt_fused_tiled_len(long long r, long long n) { return n * r * Cfg::LDB; }
@@ -523,6 +541,10 @@ int sktt_fused_prepare(sktt_ctx* ctx, long long r, long long R, long long m, lon
     mv_prepare_kernel<3, 64, 32><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(A, Rst, Lst, image, image + na,
                                                                                 image + na + nr, (int)r, (int)R, (int)m,
                                                                                 (int)n);
+    SKTT_LAUNCH_CHECK(ctx);
+    unsigned long long* mask = reinterpret_cast<unsigned long long*>(image + total - 8);
+    SKTT_CUDA(ctx, cudaMemsetAsync(mask, 0, 8 * sizeof(double), ctx->stream));
+    mv_mask_kernel<<<(unsigned)(R * 3), 256, 0, ctx->stream>>>(A, mask, 3, (int)m, (int)n);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -560,7 +582,7 @@ int sktt_fused_matvec_tiled_dots(sktt_ctx* ctx, long long r, long long R, long l
     dim3 g2((unsigned)r, (unsigned)(m / 32));
     MvDots dots{dvec, dvec2, dot_part, counter, dots_out, skip};
     mv_stage23_kernel<3, 64, 32><<<g2, THREADS, Cfg::SMEM, ctx->stream>>>(T1p, image, image + na, yt, (int)r, (int)R,
-                                                                           (int)m, (int)n, dots);
+                                                                           (int)m, (int)n, img_l_elems(r, R), dots);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
 }

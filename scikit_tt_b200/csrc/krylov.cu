@@ -48,7 +48,7 @@ static int64_t local_mv_work(const sktt_local_op* op) {
 // upper bound of the prepared-operator image (fused.cu) for one-site operators, 0 otherwise
 static int64_t local_image_bound(const sktt_local_op* op) {
     if (op->sites != 1 || op->image) return 0;
-    return op->R * ((op->m + 31) / 32) * ((op->n + 15) / 16) * 1920 + 12 * 16 * 68 + ((op->R * op->r + 95) / 96) * op->r * 100 + 64;
+    return op->R * ((op->m + 31) / 32) * ((op->n + 15) / 16) * 1920 + 12 * 16 * 68 + ((op->R * op->r + 95) / 96) * op->r * 100 + 64 + 8;
 }
 
 // elements used by the solver proper (vectors of length Nb + small state), excluding matvec scratch

@@ -117,7 +117,7 @@ def test_fused_matvec_path_matches_generic_chain_and_oracle(dev, shape):
     yref = K.micro_matvec_als(L, A, Rt, v)
     l0 = dev.launches()
     y_fused = host(dev.micro_matvec_als(dL, dA, dR, dv))
-    assert dev.launches() - l0 == 5                      # stateless: image build, to-tiled, 2 fused kernels, from-tiled
+    assert dev.launches() - l0 == 6                      # stateless: image build + block mask, to-tiled, 2 fused kernels, from-tiled
     op = dev.local_op(dL, dA, dR, prepare=True)
     assert op.image is not None
     y_prepared = host(dev.local_matvec(op, dv))
