@@ -211,6 +211,10 @@ int sktt_local_matvec(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const v
  * and call this entry point once per iteration (two kernel launches).  Exposed for benchmarking that inner step.    */
 int64_t sktt_local_op_tiled_len(sktt_ctx* ctx, int dtype, const sktt_local_op* op);
 int sktt_local_matvec_tiled(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* vt, void* yt, void* work);
+/* reps applications of the same prepared operator inside one persistent cooperative launch (timing of the contraction
+ * chain as it runs inside the persistent CG kernel; yt holds the last result)                                      */
+int sktt_local_matvec_tiled_repeat(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* vt, void* yt,
+                                   void* work, int reps);
 
 int64_t sktt_krylov_work(const sktt_local_op* op, int method, int restart);
 /* method 0: CG (Hermitian positive definite), 1: restarted GMRES(restart)                       */

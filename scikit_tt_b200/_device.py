@@ -289,6 +289,13 @@ class Device:
         self._check(self.lib.sktt_local_matvec_tiled(self.h, dtype_code(vt), C.byref(op), _ptr(vt), _ptr(yt), _ptr(w)))
         return yt
 
+    def local_matvec_tiled_repeat(self, op, vt, yt, reps):
+        """`reps` matvecs of a prepared operator inside one persistent cooperative launch (roofline timing)."""
+        w = self.work(self.lib.sktt_local_matvec_work(C.byref(op)), vt.dtype)
+        self._check(self.lib.sktt_local_matvec_tiled_repeat(self.h, dtype_code(vt), C.byref(op), _ptr(vt), _ptr(yt), _ptr(w),
+                                                            int(reps)))
+        return yt
+
     def tiled_len(self, op):
         return int(self.lib.sktt_local_op_tiled_len(self.h, dtype_code(op._keep[0]), C.byref(op)))
 

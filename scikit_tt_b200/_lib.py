@@ -63,6 +63,7 @@ SIGNATURES = {
     "sktt_local_matvec": (i32, [vp, i32, C.POINTER(LocalOp), vp, vp, vp]),
     "sktt_local_op_tiled_len": (i64, [vp, i32, C.POINTER(LocalOp)]),
     "sktt_local_matvec_tiled": (i32, [vp, i32, C.POINTER(LocalOp), vp, vp, vp]),
+    "sktt_local_matvec_tiled_repeat": (i32, [vp, i32, C.POINTER(LocalOp), vp, vp, vp, i32]),
     "sktt_krylov_work": (i64, [C.POINTER(LocalOp), i32, i32]),
     "sktt_krylov_solve": (i32, [vp, i32, C.POINTER(LocalOp), i32, i32, vp, vp, dbl, i32, vp, pint, pdbl]),
     "sktt_krylov_solve_refined": (i32, [vp, i32, C.POINTER(LocalOp), vp, vp, dbl, i32, i32, vp, pint, pdbl, pint]),

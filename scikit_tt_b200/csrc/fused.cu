@@ -16,7 +16,10 @@
 // operator core and the right stack are re-laid once per local operator into "images" that are byte-for-byte the
 // padded shared-memory tiles (mv_prepare_kernel), and stage 1 writes T1 with the padded row pitch.  Leading dimensions
 // are = 4 (mod 16) doubles so the 64-bit fragment loads of a half-warp hit 16 distinct bank pairs.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -504,6 +507,479 @@ __global__ void mv_mask_kernel(const double* __restrict__ A, unsigned long long*
 
 using Cfg = S23<3, 64, 32>;
 
+
+// ================================================================================================ persistent CG
+// One cooperative launch per micro solve: every CTA stays resident (one per SM) and walks through the phases of the
+// conjugate-gradient iteration -- stage 1 tiles, stage 2+3 tiles, vector update -- separated by grid barriers (~1 us
+// each) instead of kernel boundaries (launch ramp + prologue + tail, ~3 us each, three per iteration), with the
+// convergence test, the warm-start decision and the true-residual restarts all taken on the device from grid-wide sums
+// that every CTA forms in the same order (so every CTA takes the same branch).  The tile bodies are the two kernels
+// above, told which tile to compute; their mbarriers live in a region no phase uses for data and are re-armed per tile.
+__device__ __forceinline__ void mbar_inval(unsigned long long* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+__device__ void p_s1_tile(unsigned char* smem_raw, unsigned long long* full, const double* __restrict__ Limg,
+                          const double* __restrict__ vt, double* __restrict__ T1p, int M1, int K1, int ntot, int nn, int mt,
+                          bool first) {
+    double* As = reinterpret_cast<double*>(smem_raw);     // [K1][S1_LDA]
+    double* Bs = As + (size_t)K1 * S1_LDA;                 // [K1][S1_LDB]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = mt * S1_BM;
+    const int kg = ((K1 + 4 * S1_GROUPS - 1) / (4 * S1_GROUPS)) * 4;
+    __syncthreads();                                       // everybody is done with the previous use of this memory
+    if (tid == 0) {
+        for (int g = 0; g < S1_GROUPS; ++g) {
+            if (!first) mbar_inval(full + g);
+            mbar_init(full + g, 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == CONSUMER_WARPS) {
+        if (lane == 0) {
+            fence_proxy_async();
+            const double* asrc = Limg + (size_t)mt * K1 * S1_LDA;
+            const double* bsrc = vt + (size_t)nn * K1 * S1_LDB;
+            for (int g = 0; g < S1_GROUPS; ++g) {
+                const int k_lo = min(K1, g * kg), k_hi = min(K1, k_lo + kg);
+                const unsigned rows = (unsigned)(k_hi - k_lo);
+                mbar_expect_tx(full + g, rows * (unsigned)((S1_LDA + S1_LDB) * sizeof(double)));
+                if (rows) {
+                    bulk_g2s(As + (size_t)k_lo * S1_LDA, asrc + (size_t)k_lo * S1_LDA, rows * S1_LDA * sizeof(double), full + g);
+                    bulk_g2s(Bs + (size_t)k_lo * S1_LDB, bsrc + (size_t)k_lo * S1_LDB, rows * S1_LDB * sizeof(double), full + g);
+                }
+            }
+        }
+        return;
+    }
+    const int tile = warp & 7, khalf = warp >> 3;
+    const int wm0 = (tile & 1) * 48, wn0 = (tile >> 1) * 16;
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[6][2][2];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int g = 0; g < S1_GROUPS; ++g) {
+        const int k_lo = min(K1, g * kg), k_hi = min(K1, k_lo + kg);
+        const int steps = (k_hi - k_lo) / 4, half = (steps + 1) / 2;
+        const int s_lo = khalf == 0 ? 0 : half, s_hi = khalf == 0 ? half : steps;
+        mbar_wait(full + g, 0);
+        for (int st = s_lo; st < s_hi; ++st) {
+            const int kk = k_lo + 4 * st;
+            const double* as = As + (kk + fk) * S1_LDA + wm0 + fr;
+            const double* bs = Bs + (kk + fk) * S1_LDB + wn0 + fr;
+            double af[6], bf[2];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) af[i] = as[8 * i];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) bf[j] = bs[8 * j];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    consumer_bar_sync();
+    double* red = As + (size_t)tile * (48 * 16);
+    if (khalf == 1) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<double2*>(red + (8 * i + fr) * 16 + 8 * j + 2 * fk) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+    consumer_bar_sync();
+    if (khalf == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int m = m0 + wm0 + 8 * i + fr;
+            if (m >= M1) continue;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double2 o = *reinterpret_cast<const double2*>(red + (8 * i + fr) * 16 + 8 * j + 2 * fk);
+                double* dst = T1p + ((size_t)m * ntot + nn) * S1_LDB + wn0 + 8 * j + 2 * fk;
+                *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0] + o.x, acc[i][j][1] + o.y);
+            }
+        }
+    }
+}
+
+// returns this thread's share of <y, d> through s_yd (d: tiled vector or nullptr)
+template <int RB, int NA, int MB>
+__device__ void p_s23_tile(unsigned char* smem_raw, unsigned long long* full, const double* __restrict__ T1p,
+                           const double* __restrict__ Aimg, const double* __restrict__ Rimg, double* __restrict__ Y, int r,
+                           int R, int mtot, int ntot, unsigned long long blockmask, int c, int mblk,
+                           const double* __restrict__ dvec, double& s_yd, bool first) {
+    using P = S23<RB, NA, MB>;
+    constexpr int KC = P::KC, LDB = P::LDB, LDA = P::LDA, LDT = P::LDT, STAGES = P::STAGES;
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    double* T2s = ring + (size_t)STAGES * P::SLOT;
+    unsigned long long* empty = full + STAGES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = mblk * MB;
+    const int nchunks_n = ntot / KC;
+    const int T2n = R * nchunks_n, T3n = P::K3 / KC, total = T2n + T3n;
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            if (!first) {
+                mbar_inval(full + s);
+                mbar_inval(empty + s);
+            }
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == CONSUMER_WARPS) {
+        if (lane == 0) {
+            fence_proxy_async();
+            for (int t = 0; t < total; ++t) {
+                const int s = t % STAGES;
+                if (t >= STAGES) mbar_wait(empty + s, ((t / STAGES) & 1) ^ 1);
+                double* slot = ring + (size_t)s * P::SLOT;
+                if (t < T2n) {
+                    const int b = t / nchunks_n, nc = t % nchunks_n;
+                    mbar_expect_tx(full + s, (unsigned)(P::SLOT * sizeof(double)));
+                    bulk_g2s(slot, T1p + (((size_t)b * r + c) * ntot + (size_t)nc * KC) * LDB, P::B_ELEMS * sizeof(double),
+                             full + s);
+                    bulk_g2s(slot + P::B_ELEMS, Aimg + (((size_t)b * (mtot / MB) + mblk) * nchunks_n + nc) * P::A_ELEMS,
+                             P::A_ELEMS * sizeof(double), full + s);
+                } else {
+                    mbar_expect_tx(full + s, (unsigned)(P::B_ELEMS * sizeof(double)));
+                    bulk_g2s(slot, Rimg + (size_t)(t - T2n) * P::B_ELEMS, P::B_ELEMS * sizeof(double), full + s);
+                }
+            }
+        }
+        return;
+    }
+    const int tile = warp & 7, khalf = warp >> 3;
+    const int wm0 = (tile & 1) * 16, wn0 = (tile >> 1) * 16;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int kbeg = khalf * (KC / 2);
+    double acc2[RB][2][2][2];
+    double acc3[2][2][2];
+#pragma unroll
+    for (int q = 0; q < RB; ++q)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc2[q][i][j][0] = acc2[q][i][j][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc3[i][j][0] = acc3[i][j][1] = 0.0;
+    for (int t = 0; t < total; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(full + s, (t / STAGES) & 1);
+        const double* slot = ring + (size_t)s * P::SLOT;
+        const double* bs = slot + wn0 + fr;
+        if (t < T2n) {
+            const double* as = slot + P::B_ELEMS + (size_t)(wm0 + fr) * LDA + fk;
+            const unsigned qmask = (unsigned)(blockmask >> ((t / nchunks_n) * RB)) & ((1u << RB) - 1u);
+#pragma unroll
+            for (int kk = kbeg; kk < kbeg + KC / 2; kk += 4) {
+                double bf[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) bf[j] = bs[(kk + fk) * LDB + 8 * j];
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    if (!((qmask >> q) & 1u)) continue;
+                    double af[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) af[i] = as[((size_t)q * MB + 8 * i) * LDA + kk];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) dmma(acc2[q][i][j][0], acc2[q][i][j][1], af[i], bf[j]);
+                }
+            }
+        } else {
+            const int k0 = (t - T2n) * KC;
+            const double* ts = T2s + (size_t)(wm0 + fr) * LDT + k0 + fk;
+#pragma unroll
+            for (int kk = kbeg; kk < kbeg + KC / 2; kk += 4) {
+                double bf[2], af[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) bf[j] = bs[(kk + fk) * LDB + 8 * j];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) af[i] = ts[(size_t)(8 * i) * LDT + kk];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) dmma(acc3[i][j][0], acc3[i][j][1], af[i], bf[j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+        if (t == T2n - 1) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (khalf == h) {
+#pragma unroll
+                    for (int q = 0; q < RB; ++q)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const int mm = wm0 + 8 * i + fr, a2 = wn0 + 8 * j + 2 * fk;
+                                double* d0 = T2s + (size_t)mm * LDT + (size_t)a2 * RB + q;
+                                double* d1 = d0 + RB;
+                                if (h == 0) {
+                                    *d0 = acc2[q][i][j][0];
+                                    *d1 = acc2[q][i][j][1];
+                                } else {
+                                    *d0 += acc2[q][i][j][0];
+                                    *d1 += acc2[q][i][j][1];
+                                }
+                            }
+                }
+                consumer_bar_sync();
+            }
+        }
+    }
+    consumer_bar_sync();
+    double* red = ring;
+    if (khalf == 1) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                double* d = red + (size_t)tile * 256 + (size_t)(8 * i + fr) * 16 + 8 * j + 2 * fk;
+                *reinterpret_cast<double2*>(d) = make_double2(acc3[i][j][0], acc3[i][j][1]);
+            }
+    }
+    consumer_bar_sync();
+    if (khalf == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int m = m0 + wm0 + 8 * i + fr;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c2 = wn0 + 8 * j + 2 * fk;
+                const double2 o = *reinterpret_cast<const double2*>(red + (size_t)tile * 256 + (size_t)(8 * i + fr) * 16 +
+                                                                    8 * j + 2 * fk);
+                const double2 y = make_double2(acc3[i][j][0] + o.x, acc3[i][j][1] + o.y);
+                const size_t idx = ((size_t)m * r + c) * LDB + c2;
+                *reinterpret_cast<double2*>(Y + idx) = y;
+                if (dvec) {
+                    const double2 dv = *reinterpret_cast<const double2*>(dvec + idx);
+                    s_yd = fma(y.x, dv.x, fma(y.y, dv.y, s_yd));
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+struct PcgParams {
+    const double* image;      // [Aimg | Rimg | Limg | mask]
+    long long na, nr, nl;
+    int r, R, mtot, ntot;
+    long long N;              // tiled vector length
+    const double* f;
+    double *u, *rv, *p, *s, *w, *T1p;
+    double tol;
+    int max_iters, max_cycles, mode, reps;   // mode 0: solve; 1: `reps` matvecs w = M f (timing)
+    double* part;             // [2][gridDim.x][2] partial sums (double-buffered)
+    double* out;              // [0] iterations, [1] true relres, [2] cycles, [3] status (0 ok, 1 iteration limit, 2 breakdown)
+};
+
+namespace {
+
+__global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double red_s[2][32];
+    cg::grid_group grid = cg::this_grid();
+    const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARPS = THREADS / 32;
+    const long long gtid = (long long)cta * THREADS + tid, gstride = (long long)G * THREADS;
+    const double* Aimg = a.image;
+    const double* Rimg = a.image + a.na;
+    const double* Limg = a.image + a.na + a.nr;
+    const unsigned long long blockmask = *reinterpret_cast<const unsigned long long*>(a.image + a.na + a.nr + a.nl);
+    const int M1 = a.R * a.r, K1 = a.r;
+    const int tiles1 = a.ntot * ((M1 + S1_BM - 1) / S1_BM), tiles2 = a.r * (a.mtot / 32);
+    // barrier objects beyond every phase's data
+    const size_t data_bytes = s1_smem_bytes(K1) > Cfg::SMEM ? s1_smem_bytes(K1) : Cfg::SMEM;
+    unsigned long long* bars1 = reinterpret_cast<unsigned long long*>(smem_raw + data_bytes);
+    unsigned long long* bars2 = bars1 + S1_GROUPS;
+    bool first1 = true, first2 = true;
+    int parity = 0;
+
+    auto gsync = [&]() {
+        fence_proxy_async();
+        __threadfence();
+        grid.sync();
+    };
+    // grid-wide sums of two per-thread values; every thread of every CTA gets the same bits
+    auto grid_sum2 = [&](double v0, double v1, double& o0, double& o1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        }
+        __syncthreads();
+        if (lane == 0) {
+            red_s[0][warp] = v0;
+            red_s[1][warp] = v1;
+        }
+        __syncthreads();
+        double* part = a.part + (size_t)parity * G * 2;
+        if (tid == 0) {
+            double t0 = 0.0, t1 = 0.0;
+            for (int wv = 0; wv < NWARPS; ++wv) {
+                t0 += red_s[0][wv];
+                t1 += red_s[1][wv];
+            }
+            part[2 * cta] = t0;
+            part[2 * cta + 1] = t1;
+        }
+        gsync();
+        if (warp == 0) {
+            double t0 = 0.0, t1 = 0.0;
+            for (int g = lane; g < G; g += 32) {
+                t0 += __ldcg(part + 2 * g);
+                t1 += __ldcg(part + 2 * g + 1);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+                t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+            }
+            if (lane == 0) {
+                red_s[0][0] = t0;
+                red_s[1][0] = t1;
+            }
+        }
+        __syncthreads();
+        o0 = red_s[0][0];
+        o1 = red_s[1][0];
+        parity ^= 1;
+    };
+    // dst = M src (tiled vectors); yd = <dst, dvec> when dvec is given (one grid barrier more inside grid_sum2)
+    auto matvec = [&](const double* src, double* dst, const double* dvec, double& yd) {
+        for (int t = cta; t < tiles1; t += G) {
+            p_s1_tile(smem_raw, bars1, Limg, src, a.T1p, M1, K1, a.ntot, t % a.ntot, t / a.ntot, first1);
+            first1 = false;
+        }
+        gsync();
+        double s_yd = 0.0;
+        for (int t = cta; t < tiles2; t += G) {
+            p_s23_tile<3, 64, 32>(smem_raw, bars2, a.T1p, Aimg, Rimg, dst, a.r, a.R, a.mtot, a.ntot, blockmask, t % a.r, t / a.r,
+                                  dvec, s_yd, first2);
+            first2 = false;
+        }
+        if (dvec) {
+            double dummy;
+            grid_sum2(s_yd, 0.0, yd, dummy);
+        } else {
+            gsync();
+        }
+    };
+
+    if (a.mode == 1) {
+        double dummy = 0.0;
+        for (int rep = 0; rep < a.reps; ++rep) matvec(a.f, a.w, nullptr, dummy);
+        return;
+    }
+
+    // |f|^2
+    double fn2, rr, tmp;
+    {
+        double acc = 0.0;
+        for (long long i = gtid; i < a.N; i += gstride) acc = fma(a.f[i], a.f[i], acc);
+        grid_sum2(acc, 0.0, fn2, tmp);
+    }
+    if (fn2 == 0.0) {
+        for (long long i = gtid; i < a.N; i += gstride) a.u[i] = 0.0;
+        if (gtid == 0) a.out[0] = a.out[1] = a.out[2] = a.out[3] = 0.0;
+        return;
+    }
+    // r = f - M u
+    auto true_residual = [&]() {
+        double dummy = 0.0;
+        matvec(a.u, a.w, nullptr, dummy);
+        double acc = 0.0;
+        for (long long i = gtid; i < a.N; i += gstride) {
+            const double ri = a.f[i] - a.w[i];
+            a.rv[i] = ri;
+            acc = fma(ri, ri, acc);
+        }
+        grid_sum2(acc, 0.0, rr, tmp);
+    };
+    true_residual();
+    if (!(rr < fn2)) {                                     // the warm start is no better than zero: drop it
+        for (long long i = gtid; i < a.N; i += gstride) {
+            a.u[i] = 0.0;
+            a.rv[i] = a.f[i];
+        }
+        rr = fn2;
+        gsync();
+    }
+    const double target2 = 0.25 * a.tol * a.tol * fn2;
+    double prev = 1e300, relres = sqrt(rr / fn2);
+    int iters = 0, cycles = 0, status = 0;
+    for (int cycle = 0; cycle < a.max_cycles; ++cycle) {
+        if (relres <= a.tol || relres > 0.5 * prev) break;
+        prev = relres;
+        double gamma_old = -1.0, alpha_old = 0.0, rr_rec = rr;
+        bool conv = false;
+        for (int it = 0; it < a.max_iters; ++it) {
+            if (rr_rec <= target2) {
+                conv = true;
+                break;
+            }
+            double delta = 0.0;
+            matvec(a.rv, a.w, a.rv, delta);                // w = M r, delta = <w, r>; gamma = <r, r> = rr_rec
+            const double gamma = rr_rec;
+            const bool firstit = gamma_old < 0.0;
+            const double beta = firstit ? 0.0 : gamma / gamma_old;
+            const double denom = firstit ? delta : delta - beta * gamma / alpha_old;
+            if (!(denom > 0.0)) {
+                status = 2;
+                break;
+            }
+            const double alpha = gamma / denom;
+            double acc = 0.0;
+            for (long long i = gtid; i < a.N; i += gstride) {
+                const double ri = a.rv[i];
+                const double pi = firstit ? ri : fma(beta, a.p[i], ri);
+                const double si = firstit ? a.w[i] : fma(beta, a.s[i], a.w[i]);
+                a.p[i] = pi;
+                a.s[i] = si;
+                a.u[i] = fma(alpha, pi, a.u[i]);
+                const double rn = fma(-alpha, si, ri);
+                a.rv[i] = rn;
+                acc = fma(rn, rn, acc);
+            }
+            grid_sum2(acc, 0.0, rr_rec, tmp);
+            gamma_old = gamma;
+            alpha_old = alpha;
+            ++iters;
+        }
+        true_residual();
+        relres = sqrt(rr / fn2);
+        cycles = cycle + 1;
+        if (status == 2) break;
+        if (!conv) {
+            status = 1;
+            break;
+        }
+    }
+    if (gtid == 0) {
+        a.out[0] = (double)iters;
+        a.out[1] = relres;
+        a.out[2] = (double)cycles;
+        a.out[3] = (double)status;
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -602,4 +1078,51 @@ int sktt_fused_matvec(sktt_ctx* ctx, long long r, long long R, long long m, long
     SKTT_TRY(sktt_fused_to_tiled(ctx, r, n, v, vt));
     SKTT_TRY(sktt_fused_matvec_tiled(ctx, r, R, m, n, image, vt, yt, T1p));
     return sktt_fused_from_tiled(ctx, r, m, yt, y);
+}
+
+// ------------------------------------------------------------------------------------------------ persistent CG, host side
+// Vectors in the tiled layout.  mode 0: solve M u = f (u: warm start in, solution out); results land in out_dev[0..3]
+// (iterations, true relative residual, cycles, status 0 ok / 1 iteration limit of a CG run / 2 breakdown).
+// mode 1: `reps` matvecs w = M f inside one launch (timing of the contraction chain without launch overheads).
+// Scratch: rv, p, s, w of tiled length each, T1p as for sktt_fused_matvec_tiled, part of 4 * SMs doubles.
+int sktt_fused_pcg_persistent(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                              const double* f, double* u, double* rv, double* p, double* s, double* w, double* T1p,
+                              double tol, int max_iters, int max_cycles, int mode, int reps, double* part,
+                              double* out_dev) {
+    PcgParams a;
+    a.image = image;
+    a.na = img_a_elems(R, m, n);
+    a.nr = img_r_elems();
+    a.nl = img_l_elems(r, R);
+    a.r = (int)r;
+    a.R = (int)R;
+    a.mtot = (int)m;
+    a.ntot = (int)n;
+    a.N = sktt_fused_tiled_len(r, n);
+    a.f = f;
+    a.u = u;
+    a.rv = rv;
+    a.p = p;
+    a.s = s;
+    a.w = w;
+    a.T1p = T1p;
+    a.tol = tol;
+    a.max_iters = max_iters;
+    a.max_cycles = max_cycles;
+    a.mode = mode;
+    a.reps = reps;
+    a.part = part;
+    a.out = out_dev;
+    const size_t data_bytes = s1_smem_bytes((int)r) > Cfg::SMEM ? s1_smem_bytes((int)r) : Cfg::SMEM;
+    const size_t smem = data_bytes + 128;
+    static bool configured = false;
+    if (!configured) {
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(pcg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
+        configured = true;
+    }
+    void* args[] = {&a};
+    SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)pcg_persistent_kernel, dim3(ctx->sm_count), dim3(THREADS), args, smem,
+                                               ctx->stream));
+    ctx->launches++;
+    return 0;
 }

@@ -18,6 +18,11 @@ int sktt_fused_matvec_tiled_dots(sktt_ctx* ctx, long long r, long long R, long l
                                  const double* vt, double* yt, double* T1p, const double* dvec, const double* dvec2,
                                  double* dot_part, unsigned* counter, double* dots_out, const int* skip);
 
+int sktt_fused_pcg_persistent(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                              const double* f, double* u, double* rv, double* p, double* s, double* w, double* T1p,
+                              double tol, int max_iters, int max_cycles, int mode, int reps, double* part,
+                              double* out_dev);
+
 // The operator as the Krylov loops see it: either the generic contraction chain on natural-layout vectors, or the
 // prepared fused matvec on tiled-layout vectors (all Krylov vectors then live in that layout; padding stays zero).
 struct KOp {
@@ -527,8 +532,8 @@ static int cg_tiled_impl(sktt_ctx* ctx, const KOp& op, const double* f, double* 
 // Whole micro solve on the prepared operator: warm start (dropped when it is worse than the zero vector), CG, then the
 // TRUE residual f - A u is recomputed and CG restarted from it until that residual is below tol * |f| or stops improving
 // (the eps * cond floor any backward-stable solver, LU included, ends at).  A handful of host synchronisations per solve.
-static int cg_tiled_refined(sktt_ctx* ctx, const KOp& op, const double* f, double* u, double tol, int max_iters,
-                            int max_cycles, double* work, int* iters_host, double* relres_host, int* cycles_host) {
+static int cg_tiled_refined_host(sktt_ctx* ctx, const KOp& op, const double* f, double* u, double tol, int max_iters,
+                                 int max_cycles, double* work, int* iters_host, double* relres_host, int* cycles_host) {
     const CgTiledBufs b = cg_tiled_bufs(op, work);
     const long long N = op.N;
     double fnorm2 = 0.0, rr = 0.0;
@@ -578,6 +583,49 @@ static int cg_tiled_refined(sktt_ctx* ctx, const KOp& op, const double* f, doubl
     }
     if (relres_host) *relres_host = relres;
     return 0;
+}
+
+// The persistent-kernel form of the same solve (fused.cu): one cooperative launch, one host synchronisation.  Returns 0
+// with *finished = false when a CG run hit PERSISTENT_CG_ITERS without converging -- the caller then continues with
+// the host-driven, preconditioned loop from the iterate left in u.
+#define PERSISTENT_CG_ITERS 48
+static int cg_tiled_persistent(sktt_ctx* ctx, const KOp& op, const double* f, double* u, double tol, int max_cycles,
+                               double* work, int* iters_host, double* relres_host, int* cycles_host, bool* finished) {
+    const CgTiledBufs b = cg_tiled_bufs(op, work);
+    const sktt_local_op& o = op.op;
+    double* part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
+    double* outd = part + 4 * 256;
+    double* mbox = (double*)ctx->mailbox;
+    SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (4 * 256 + 16) * sizeof(double)));
+    part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
+    outd = part + 4 * 256;
+    SKTT_TRY(sktt_fused_pcg_persistent(ctx, o.r, o.R, o.m, o.n, (const double*)o.image, f, u, b.r, b.p, b.s, b.w, b.mvwork,
+                                       tol, PERSISTENT_CG_ITERS, max_cycles, 0, 0, part, outd));
+    SKTT_CUDA(ctx, cudaMemcpyAsync(mbox + 40, outd, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SKTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (iters_host) *iters_host = (int)mbox[40];
+    if (relres_host) *relres_host = mbox[41];
+    if (cycles_host) *cycles_host = (int)mbox[42];
+    *finished = mbox[43] == 0.0;
+    return 0;
+}
+
+static int cg_tiled_refined(sktt_ctx* ctx, const KOp& op, const double* f, double* u, double tol, int max_iters,
+                            int max_cycles, double* work, int* iters_host, double* relres_host, int* cycles_host) {
+    if (!(ctx->debug & 16) && ctx->sm_count <= 256) {
+        bool finished = false;
+        int it0 = 0;
+        SKTT_TRY(cg_tiled_persistent(ctx, op, f, u, tol, max_cycles, work, &it0, relres_host, cycles_host, &finished));
+        if (finished) {
+            if (iters_host) *iters_host = it0;
+            return 0;
+        }
+        int it1 = 0;
+        int st = cg_tiled_refined_host(ctx, op, f, u, tol, max_iters, max_cycles, work, &it1, relres_host, cycles_host);
+        if (iters_host) *iters_host = it0 + it1;
+        return st;
+    }
+    return cg_tiled_refined_host(ctx, op, f, u, tol, max_iters, max_cycles, work, iters_host, relres_host, cycles_host);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -383,3 +383,22 @@ extern "C" int sktt_local_matvec_tiled(sktt_ctx* ctx, int dtype, const sktt_loca
     return sktt_fused_matvec_tiled(ctx, op->r, op->R, op->m, op->n, (const double*)op->image, (const double*)vt,
                                    (double*)yt, (double*)work);
 }
+
+int sktt_fused_pcg_persistent(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                              const double* f, double* u, double* rv, double* p, double* s, double* w, double* T1p,
+                              double tol, int max_iters, int max_cycles, int mode, int reps, double* part,
+                              double* out_dev);
+
+// `reps` applications yt = M vt of a prepared operator inside ONE persistent cooperative launch (the form the matvec
+// takes inside the persistent CG kernel): the contraction chain without per-launch overheads, for the roofline line.
+extern "C" int sktt_local_matvec_tiled_repeat(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* vt, void* yt,
+                                              void* work, int reps) {
+    if (!ctx || !op || !vt || !yt || !work || reps < 1) return SKTT_ERR_ARG;
+    if (sktt_local_op_tiled_len(ctx, dtype, op) <= 0)
+        return sktt_fail(ctx, SKTT_ERR_ARG, "local_matvec_tiled_repeat: operator is not prepared for the tiled path");
+    SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (4 * 256 + 16) * sizeof(double)));
+    double* part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
+    return sktt_fused_pcg_persistent(ctx, op->r, op->R, op->m, op->n, (const double*)op->image, (const double*)vt, nullptr,
+                                     nullptr, nullptr, nullptr, (double*)yt, (double*)work, 0.0, 0, 0, 1, reps, part,
+                                     part + 4 * 256);
+}
