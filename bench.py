@@ -247,23 +247,32 @@ def run_ours(args, cfg):
     F = stack_flops(L.shape[0], A.shape[0], A.shape[2], R.shape[0], A.shape[3])
     lop = dev.local_op(L, A, R, prepare=True)                # prepared exactly as the Krylov solvers prepare it
     nt = dev.tiled_len(lop)
-    if nt > 0:                                               # the CG inner step: tiled-layout vectors, two launches
+    reps = 200
+    if nt > 0:
+        # the form the matvec takes inside the persistent CG kernel (the dominant kernel of the step): `reps` matvecs in
+        # ONE cooperative launch of pcg_persistent_kernel, stage-1 tiles | grid barrier | stage-2+3 tiles | grid barrier
         vt = torch.randn(nt, dtype=torch.float64, device="cuda")
+        vt.view(-1, 68)[:, 64:] = 0.0
         yt = torch.zeros(nt, dtype=torch.float64, device="cuda")
-        mv = lambda: dev.local_matvec_tiled(lop, vt, yt)
+        mv = lambda: dev.local_matvec_tiled_repeat(lop, vt, yt, reps)
+        per_call = reps
+        kernel_name = ("pcg_persistent_kernel, matvec phases (stage-1 tiles | grid barrier | stage-2+3 tiles | grid barrier) = the "
+                       "contraction chain of one interface-stack update (r=64, R=3, n=64); the kernel is 1 launch per micro solve")
     else:
         mv = lambda: dev.local_matvec(lop, v)
-    for _ in range(10):
+        per_call = 1
+        kernel_name = "generic three-GEMM contraction chain"
+    for _ in range(3):
         mv()
     torch.cuda.synchronize()
     m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 200
+    calls = 5 if per_call > 1 else 200
     m0.record()
-    for _ in range(reps):
+    for _ in range(calls):
         mv()
     m1.record()
     torch.cuda.synchronize()
-    mv_ms = m0.elapsed_time(m1) / reps
+    mv_ms = m0.elapsed_time(m1) / (calls * per_call)
     achieved = F / (mv_ms * 1e-3) / 1e12
     Ah = opc[i]
     nnz_blocks = int(sum(bool(np.any(Ah[b, :, :, q])) for b in range(Ah.shape[0]) for q in range(Ah.shape[3])))
@@ -302,12 +311,11 @@ def run_ours(args, cfg):
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
                              "frac": achieved / FP64_TENSOR_PEAK_TFLOPS,
                              "traffic": NCU_MATVEC_DRAM_BYTES,
-                             "traffic_note": "dram__bytes_read+write per matvec (mv_stage1 2.35 MB + mv_stage23 9.41 MB) from "
-                                             "profiles/r01_ncu_final_full.txt; ncu flushes the caches per replay, inside the CG "
-                                             "loop every operand is L2-resident; algorithmic bytes 4.72 MB",
-                             "kernel": "mv_stage1_kernel + mv_stage23_kernel = one micro-matvec = the contraction chain of one "
-                                       "interface-stack update (r=64, R=3, n=64); dominant kernels of the step "
-                                       "(profiles/r01_launches_final_summary.txt: 51 % of device time)",
+                             "traffic_note": "dram bytes per matvec of the two-kernel form (mv_stage1 2.35 MB + mv_stage23 9.41 MB, "
+                                             "profiles/r01_ncu_final_full.txt, ncu flushes the caches per replay); inside the "
+                                             "persistent kernel every operand is L2-resident: 3.1 MB of DRAM reads for 20 matvecs "
+                                             "(profiles/r01_ncu_persistent.txt); algorithmic bytes 4.72 MB",
+                             "kernel": kernel_name,
                              "flops_per_matvec": F, "us_per_matvec": mv_ms * 1e3,
                              "executed_flops_per_matvec": F_exec,
                              "executed_note": "F is the dense formula of SURVEY.md 8d; the kernel skips the zero (b, b') "

@@ -607,21 +607,51 @@ __device__ void p_s1_tile(unsigned char* smem_raw, unsigned long long* full, con
     }
 }
 
-// returns this thread's share of <y, d> through s_yd (d: tiled vector or nullptr)
+// One operator chunk of the second contraction for a COMPILE-TIME block mask QM (bit q set: A[b, :, :, q] is non-zero):
+// the caller switches on the run-time mask, so zero blocks cost no issue slots (a predicated-off DMMA still does).
+template <int RB, int MB, int LDA, int LDB, int KC, unsigned QM>
+__device__ __forceinline__ void s2_chunk(double (&acc2)[RB][2][2][2], const double* __restrict__ as,
+                                         const double* __restrict__ bs, int kbeg, int fk) {
+#pragma unroll
+    for (int kk = kbeg; kk < kbeg + KC / 2; kk += 4) {
+        double bf[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) bf[j] = bs[(kk + fk) * LDB + 8 * j];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+            if ((QM >> q) & 1u) {
+                double af[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) af[i] = as[((size_t)q * MB + 8 * i) * LDA + kk];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) dmma(acc2[q][i][j][0], acc2[q][i][j][1], af[i], bf[j]);
+            }
+        }
+    }
+}
+
+// returns this thread's share of <y, d> through s_yd (d: tiled vector or nullptr).
+// Differences from mv_stage23_kernel: the right-stack image is RESIDENT in shared memory (Rres, loaded once per solve),
+// so the last contraction needs no staging at all; the ring has three slots; and the producer only copies the
+// (b, q) blocks of the operator image whose mask bit is set.
+constexpr int PSTAGES = 3;
 template <int RB, int NA, int MB>
-__device__ void p_s23_tile(unsigned char* smem_raw, unsigned long long* full, const double* __restrict__ T1p,
-                           const double* __restrict__ Aimg, const double* __restrict__ Rimg, double* __restrict__ Y, int r,
+__device__ void p_s23_tile(unsigned char* smem_raw, unsigned long long* full, const double* __restrict__ Rres,
+                           const double* __restrict__ T1p, const double* __restrict__ Aimg, double* __restrict__ Y, int r,
                            int R, int mtot, int ntot, unsigned long long blockmask, int c, int mblk,
                            const double* __restrict__ dvec, double& s_yd, bool first) {
     using P = S23<RB, NA, MB>;
-    constexpr int KC = P::KC, LDB = P::LDB, LDA = P::LDA, LDT = P::LDT, STAGES = P::STAGES;
+    constexpr int KC = P::KC, LDB = P::LDB, LDA = P::LDA, LDT = P::LDT, STAGES = PSTAGES;
+    constexpr int QBLK = MB * LDA;                         // one (b, q) block of an operator chunk
     double* ring = reinterpret_cast<double*>(smem_raw);
     double* T2s = ring + (size_t)STAGES * P::SLOT;
     unsigned long long* empty = full + STAGES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = mblk * MB;
     const int nchunks_n = ntot / KC;
-    const int T2n = R * nchunks_n, T3n = P::K3 / KC, total = T2n + T3n;
+    const int T2n = R * nchunks_n, T3n = P::K3 / KC;
     __syncthreads();
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -638,21 +668,20 @@ __device__ void p_s23_tile(unsigned char* smem_raw, unsigned long long* full, co
     if (warp == CONSUMER_WARPS) {
         if (lane == 0) {
             fence_proxy_async();
-            for (int t = 0; t < total; ++t) {
+            for (int t = 0; t < T2n; ++t) {
                 const int s = t % STAGES;
                 if (t >= STAGES) mbar_wait(empty + s, ((t / STAGES) & 1) ^ 1);
                 double* slot = ring + (size_t)s * P::SLOT;
-                if (t < T2n) {
-                    const int b = t / nchunks_n, nc = t % nchunks_n;
-                    mbar_expect_tx(full + s, (unsigned)(P::SLOT * sizeof(double)));
-                    bulk_g2s(slot, T1p + (((size_t)b * r + c) * ntot + (size_t)nc * KC) * LDB, P::B_ELEMS * sizeof(double),
-                             full + s);
-                    bulk_g2s(slot + P::B_ELEMS, Aimg + (((size_t)b * (mtot / MB) + mblk) * nchunks_n + nc) * P::A_ELEMS,
-                             P::A_ELEMS * sizeof(double), full + s);
-                } else {
-                    mbar_expect_tx(full + s, (unsigned)(P::B_ELEMS * sizeof(double)));
-                    bulk_g2s(slot, Rimg + (size_t)(t - T2n) * P::B_ELEMS, P::B_ELEMS * sizeof(double), full + s);
-                }
+                const int b = t / nchunks_n, nc = t % nchunks_n;
+                const unsigned qmask = (unsigned)(blockmask >> (b * RB)) & ((1u << RB) - 1u);
+                mbar_expect_tx(full + s, (unsigned)((P::B_ELEMS + __popc(qmask) * QBLK) * sizeof(double)));
+                bulk_g2s(slot, T1p + (((size_t)b * r + c) * ntot + (size_t)nc * KC) * LDB, P::B_ELEMS * sizeof(double),
+                         full + s);
+                const double* asrc = Aimg + (((size_t)b * (mtot / MB) + mblk) * nchunks_n + nc) * P::A_ELEMS;
+#pragma unroll
+                for (int q = 0; q < RB; ++q)
+                    if ((qmask >> q) & 1u)
+                        bulk_g2s(slot + P::B_ELEMS + (size_t)q * QBLK, asrc + (size_t)q * QBLK, QBLK * sizeof(double), full + s);
             }
         }
         return;
@@ -673,72 +702,67 @@ __device__ void p_s23_tile(unsigned char* smem_raw, unsigned long long* full, co
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) acc3[i][j][0] = acc3[i][j][1] = 0.0;
-    for (int t = 0; t < total; ++t) {
+    for (int t = 0; t < T2n; ++t) {
         const int s = t % STAGES;
         mbar_wait(full + s, (t / STAGES) & 1);
         const double* slot = ring + (size_t)s * P::SLOT;
         const double* bs = slot + wn0 + fr;
-        if (t < T2n) {
-            const double* as = slot + P::B_ELEMS + (size_t)(wm0 + fr) * LDA + fk;
-            const unsigned qmask = (unsigned)(blockmask >> ((t / nchunks_n) * RB)) & ((1u << RB) - 1u);
+        const double* as = slot + P::B_ELEMS + (size_t)(wm0 + fr) * LDA + fk;
+        const unsigned qmask = (unsigned)(blockmask >> ((t / nchunks_n) * RB)) & ((1u << RB) - 1u);
+        static_assert(RB == 3, "mask dispatch below is written for three operator-rank blocks");
+        switch (qmask) {                                   // warp-uniform
+            case 1: s2_chunk<RB, MB, LDA, LDB, KC, 1>(acc2, as, bs, kbeg, fk); break;
+            case 2: s2_chunk<RB, MB, LDA, LDB, KC, 2>(acc2, as, bs, kbeg, fk); break;
+            case 3: s2_chunk<RB, MB, LDA, LDB, KC, 3>(acc2, as, bs, kbeg, fk); break;
+            case 4: s2_chunk<RB, MB, LDA, LDB, KC, 4>(acc2, as, bs, kbeg, fk); break;
+            case 5: s2_chunk<RB, MB, LDA, LDB, KC, 5>(acc2, as, bs, kbeg, fk); break;
+            case 6: s2_chunk<RB, MB, LDA, LDB, KC, 6>(acc2, as, bs, kbeg, fk); break;
+            case 7: s2_chunk<RB, MB, LDA, LDB, KC, 7>(acc2, as, bs, kbeg, fk); break;
+            default: break;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+    // T2[m, a2, b2] = sum of the two K-halves -> T2s[m][a2 * RB + b2]
 #pragma unroll
-            for (int kk = kbeg; kk < kbeg + KC / 2; kk += 4) {
-                double bf[2];
+    for (int h = 0; h < 2; ++h) {
+        if (khalf == h) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) bf[j] = bs[(kk + fk) * LDB + 8 * j];
+            for (int q = 0; q < RB; ++q)
 #pragma unroll
-                for (int q = 0; q < RB; ++q) {
-                    if (!((qmask >> q) & 1u)) continue;
-                    double af[2];
+                for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) af[i] = as[((size_t)q * MB + 8 * i) * LDA + kk];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) dmma(acc2[q][i][j][0], acc2[q][i][j][1], af[i], bf[j]);
-                }
-            }
-        } else {
-            const int k0 = (t - T2n) * KC;
-            const double* ts = T2s + (size_t)(wm0 + fr) * LDT + k0 + fk;
+                    for (int j = 0; j < 2; ++j) {
+                        const int mm = wm0 + 8 * i + fr, a2 = wn0 + 8 * j + 2 * fk;
+                        double* d0 = T2s + (size_t)mm * LDT + (size_t)a2 * RB + q;
+                        double* d1 = d0 + RB;
+                        if (h == 0) {
+                            *d0 = acc2[q][i][j][0];
+                            *d1 = acc2[q][i][j][1];
+                        } else {
+                            *d0 += acc2[q][i][j][0];
+                            *d1 += acc2[q][i][j][1];
+                        }
+                    }
+        }
+        consumer_bar_sync();
+    }
+    // last contraction straight from the resident right-stack image: no staging, no barriers
+    {
+        const double* bs = Rres + wn0 + fr;
+        const double* ts = T2s + (size_t)(wm0 + fr) * LDT + fk;
+        for (int t3 = 0; t3 < T3n; ++t3) {
 #pragma unroll
             for (int kk = kbeg; kk < kbeg + KC / 2; kk += 4) {
                 double bf[2], af[2];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) bf[j] = bs[(kk + fk) * LDB + 8 * j];
+                for (int j = 0; j < 2; ++j) bf[j] = bs[((size_t)t3 * KC + kk + fk) * LDB + 8 * j];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) af[i] = ts[(size_t)(8 * i) * LDT + kk];
+                for (int i = 0; i < 2; ++i) af[i] = ts[(size_t)(8 * i) * LDT + t3 * KC + kk];
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) dmma(acc3[i][j][0], acc3[i][j][1], af[i], bf[j]);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + s);
-        if (t == T2n - 1) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (khalf == h) {
-#pragma unroll
-                    for (int q = 0; q < RB; ++q)
-#pragma unroll
-                        for (int i = 0; i < 2; ++i)
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const int mm = wm0 + 8 * i + fr, a2 = wn0 + 8 * j + 2 * fk;
-                                double* d0 = T2s + (size_t)mm * LDT + (size_t)a2 * RB + q;
-                                double* d1 = d0 + RB;
-                                if (h == 0) {
-                                    *d0 = acc2[q][i][j][0];
-                                    *d1 = acc2[q][i][j][1];
-                                } else {
-                                    *d0 += acc2[q][i][j][0];
-                                    *d1 += acc2[q][i][j][1];
-                                }
-                            }
-                }
-                consumer_bar_sync();
             }
         }
     }
@@ -775,6 +799,14 @@ __device__ void p_s23_tile(unsigned char* smem_raw, unsigned long long* full, co
     }
 }
 
+// shared-memory plan of the persistent kernel (bytes): phase data | resident right-stack image | barriers
+__host__ __device__ inline size_t pcg_phase_bytes(int K1) {
+    const size_t s23 = ((size_t)PSTAGES * Cfg::SLOT + (size_t)32 * Cfg::LDT) * sizeof(double);
+    const size_t s1 = s1_smem_bytes(K1);
+    return (s1 > s23 ? s1 : s23);
+}
+__host__ __device__ inline size_t pcg_rres_bytes() { return (size_t)(Cfg::K3 / Cfg::KC) * Cfg::B_ELEMS * sizeof(double); }
+
 }  // namespace
 
 struct PcgParams {
@@ -805,16 +837,22 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
     const unsigned long long blockmask = *reinterpret_cast<const unsigned long long*>(a.image + a.na + a.nr + a.nl);
     const int M1 = a.R * a.r, K1 = a.r;
     const int tiles1 = a.ntot * ((M1 + S1_BM - 1) / S1_BM), tiles2 = a.r * (a.mtot / 32);
-    // barrier objects beyond every phase's data
-    const size_t data_bytes = s1_smem_bytes(K1) > Cfg::SMEM ? s1_smem_bytes(K1) : Cfg::SMEM;
-    unsigned long long* bars1 = reinterpret_cast<unsigned long long*>(smem_raw + data_bytes);
+    // phase data | resident right-stack image | barrier objects (beyond every phase's data)
+    const size_t data_bytes = pcg_phase_bytes(K1);
+    double* Rres = reinterpret_cast<double*>(smem_raw + data_bytes);
+    unsigned long long* bars1 = reinterpret_cast<unsigned long long*>(smem_raw + data_bytes + pcg_rres_bytes());
     unsigned long long* bars2 = bars1 + S1_GROUPS;
+    for (int e = tid; e < (int)(pcg_rres_bytes() / sizeof(double)); e += THREADS) Rres[e] = Rimg[e];
+    __syncthreads();
     bool first1 = true, first2 = true;
     int parity = 0;
 
-    auto gsync = [&]() {
-        fence_proxy_async();
-        __threadfence();
+    auto gsync = [&]() {                                   // CTA barrier, then one thread publishes the CTA's writes
+        __syncthreads();
+        if (tid == 0) {
+            fence_proxy_async();
+            __threadfence();
+        }
         grid.sync();
     };
     // grid-wide sums of two per-thread values; every thread of every CTA gets the same bits
@@ -863,18 +901,31 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
         parity ^= 1;
     };
     // dst = M src (tiled vectors); yd = <dst, dvec> when dvec is given (one grid barrier more inside grid_sum2)
+    unsigned long long* stamps = a.mode == 1 ? reinterpret_cast<unsigned long long*>(a.out + 8) : nullptr;
+    int nstamp = 0;
+    auto stamp = [&]() {
+        if (stamps && cta == 0 && tid == 0 && nstamp < 60) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            stamps[1 + nstamp++] = t;
+        }
+    };
     auto matvec = [&](const double* src, double* dst, const double* dvec, double& yd) {
+        stamp();
         for (int t = cta; t < tiles1; t += G) {
             p_s1_tile(smem_raw, bars1, Limg, src, a.T1p, M1, K1, a.ntot, t % a.ntot, t / a.ntot, first1);
             first1 = false;
         }
+        stamp();
         gsync();
+        stamp();
         double s_yd = 0.0;
         for (int t = cta; t < tiles2; t += G) {
-            p_s23_tile<3, 64, 32>(smem_raw, bars2, a.T1p, Aimg, Rimg, dst, a.r, a.R, a.mtot, a.ntot, blockmask, t % a.r, t / a.r,
+            p_s23_tile<3, 64, 32>(smem_raw, bars2, Rres, a.T1p, Aimg, dst, a.r, a.R, a.mtot, a.ntot, blockmask, t % a.r, t / a.r,
                                   dvec, s_yd, first2);
             first2 = false;
         }
+        stamp();
         if (dvec) {
             double dummy;
             grid_sum2(s_yd, 0.0, yd, dummy);
@@ -886,6 +937,8 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
     if (a.mode == 1) {
         double dummy = 0.0;
         for (int rep = 0; rep < a.reps; ++rep) matvec(a.f, a.w, nullptr, dummy);
+        stamp();
+        if (stamps && cta == 0 && tid == 0) stamps[0] = (unsigned long long)nstamp;
         return;
     }
 
@@ -1113,11 +1166,10 @@ int sktt_fused_pcg_persistent(sktt_ctx* ctx, long long r, long long R, long long
     a.reps = reps;
     a.part = part;
     a.out = out_dev;
-    const size_t data_bytes = s1_smem_bytes((int)r) > Cfg::SMEM ? s1_smem_bytes((int)r) : Cfg::SMEM;
-    const size_t smem = data_bytes + 128;
+    const size_t smem = pcg_phase_bytes((int)r) + pcg_rres_bytes() + 128;
     static bool configured = false;
     if (!configured) {
-        SKTT_CUDA(ctx, cudaFuncSetAttribute(pcg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(pcg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         configured = true;
     }
     void* args[] = {&a};

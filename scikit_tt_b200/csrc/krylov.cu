@@ -596,7 +596,7 @@ static int cg_tiled_persistent(sktt_ctx* ctx, const KOp& op, const double* f, do
     double* part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
     double* outd = part + 4 * 256;
     double* mbox = (double*)ctx->mailbox;
-    SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (4 * 256 + 16) * sizeof(double)));
+    SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (4 * 256 + 128) * sizeof(double)));
     part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
     outd = part + 4 * 256;
     SKTT_TRY(sktt_fused_pcg_persistent(ctx, o.r, o.R, o.m, o.n, (const double*)o.image, f, u, b.r, b.p, b.s, b.w, b.mvwork,

@@ -396,7 +396,7 @@ extern "C" int sktt_local_matvec_tiled_repeat(sktt_ctx* ctx, int dtype, const sk
     if (!ctx || !op || !vt || !yt || !work || reps < 1) return SKTT_ERR_ARG;
     if (sktt_local_op_tiled_len(ctx, dtype, op) <= 0)
         return sktt_fail(ctx, SKTT_ERR_ARG, "local_matvec_tiled_repeat: operator is not prepared for the tiled path");
-    SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (4 * 256 + 16) * sizeof(double)));
+    SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (4 * 256 + 128) * sizeof(double)));
     double* part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
     return sktt_fused_pcg_persistent(ctx, op->r, op->R, op->m, op->n, (const double*)op->image, (const double*)vt, nullptr,
                                      nullptr, nullptr, nullptr, (double*)yt, (double*)work, 0.0, 0, 0, 1, reps, part,

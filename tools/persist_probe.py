@@ -29,6 +29,10 @@ for reps in (1, 10, 100):
     dev.local_matvec_tiled_repeat(op, vt, y2, reps); torch.cuda.synchronize()
     e0.record(); dev.local_matvec_tiled_repeat(op, vt, y2, reps); e1.record(); torch.cuda.synchronize()
     print("reps", reps, "us per matvec", e0.elapsed_time(e1) * 1e3 / reps)
+dev.local_matvec_tiled_repeat(op, vt, y2, 3)
+st_ = dev.scratch_peek(65536 + (4 * 256 + 8) * 8, 40)
+k = int(st_[0]); tt = np.array(st_[1:1 + k], dtype=np.float64)
+print("phase stamps (us) [start, S1 done, barrier, S23 done | ...]:", [round(float(x), 1) for x in np.diff(tt) / 1e3])
 for dbg in (16, 0):
     dev.set_debug(dbg)
     u = torch.zeros(f.size, dtype=torch.float64, device="cuda")
