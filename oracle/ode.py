@@ -21,3 +21,18 @@ def implicit_euler(op, x_init, guess, step_sizes, repeats=1, tt_solver='als', th
             cur = tt.scale(cur, 1.0 / tt.norm(cur, p=normalize))
         sol.append(tt.copy_cores(cur))
     return sol
+
+
+def trapezoidal_rule(op, x_init, guess, step_sizes, repeats=1, normalize=1):
+    """ode.py:366-450 on core lists (ALS variant)."""
+    sol = [x_init]
+    cur = guess
+    dims = [c.shape[1] for c in op]
+    for i, h in enumerate(step_sizes):
+        lhs = tt.sub(tt.eye(dims), tt.scale(op, 0.5 * h))
+        rhs = tt.matmul(tt.add(tt.eye(dims), tt.scale(op, 0.5 * h)), sol[i])              # ode.py:431-437
+        cur = sle.als(lhs, cur, rhs, repeats=repeats)
+        if normalize > 0:
+            cur = tt.scale(cur, 1.0 / tt.norm(cur, p=normalize))
+        sol.append(tt.copy_cores(cur))
+    return sol

@@ -466,3 +466,18 @@ def test_refined_cg_ill_conditioned_uses_the_mode_preconditioner(dev):
         dev.set_debug(0)
     assert st2 == 0 and relres2 <= 1e-12 and iters2 > iters, (iters, iters2)
     assert np.linalg.norm(u2.cpu().numpy() - u.cpu().numpy()) <= 1e-9 * np.linalg.norm(uh)
+
+
+# ------------------------------------------------------------------------------------------------ full BASELINE sizes
+@pytest.mark.parametrize("r", [128, 256])
+def test_c4_full_size_contractions(dev, r):
+    """BASELINE config 4 at full size (d=10 interior core: n=16, R=8, r=128 / 256): stack updates and the micro-matvec
+    against the einsum restatement (SURVEY.md 8c parity plan, item 1).  The reference cannot run this size at all."""
+    R, n = 8, 16
+    rng = np.random.default_rng(r)
+    L, Rt = rnd(rng, (r, R, r), False), rnd(rng, (r, R, r), False)
+    x, A = rnd(rng, (r, n, r), False), rnd(rng, (R, n, n, R), False)
+    dL, dR, dx, dA = (dev.to_device(a) for a in (L, Rt, x, A))
+    assert relerr(host(dev.stack_left_op(dL, dx, dA)), K.stack_left_op(L, x, A)) < 1e-12
+    assert relerr(host(dev.stack_right_op(dR, dx, dA)), K.stack_right_op(Rt, x, A)) < 1e-12
+    assert relerr(host(dev.micro_matvec_als(dL, dA, dR, dx)), K.micro_matvec_als(L, A, Rt, x)) < 1e-12

@@ -246,3 +246,61 @@ def test_c2_first_step_and_completion(dev):
     assert abs(first["gpu"] - first["oracle"]) < 1e-6 * abs(first["oracle"])
     assert isinstance(lam, float) and isinstance(x, TT) and it == 1
     assert x.ranks[0] == x.ranks[-1] == 1 and max(x.ranks) <= 8 and np.isfinite(lam)
+
+
+def test_c3_full_size_properties(dev):
+    """BASELINE config 3 at full size (d=32, n=64, R=3, r=64; 262 144 unknowns per micro system) -- no reference result can
+    exist (512 GiB micro matrices), so the checks are the size-independent ones: the global residual ||A x - b|| / ||b||
+    falls from one sweep to two and ends below 1e-11, ranks and shapes are those of the guess, and two runs on the same
+    inputs return bit-identical cores (every reduction of the path is ordered)."""
+    import bench
+    opc, rhsc, x0c = bench.workload_cores(32, 64, 64)
+    op, rhs = TT(opc), TT(rhsc)
+    x0 = TT(ott.ortho_right(x0c))
+    one = sle.als(op, x0, rhs, repeats=1)
+    two = sle.als(op, x0, rhs, repeats=2)
+    bnorm = np.prod([np.linalg.norm(c) for c in rhsc])
+    r1, r2 = tt.residual_error(op, one, rhs) / bnorm, tt.residual_error(op, two, rhs) / bnorm
+    assert r2 < r1 < 1e-9 and r2 < 1e-11, (r1, r2)
+    assert two.ranks == x0.ranks and two.row_dims == x0.row_dims and two.col_dims == [1] * 32
+    again = sle.als(op, x0, rhs, repeats=1)
+    assert all(np.array_equal(a, b) for a, b in zip(one.cores, again.cores))
+
+
+def test_mals_matrix_free_two_site(dev):
+    """MALS where the two-site micro matrix cannot be formed (n = 64: r n n r'' = 65 536 unknowns, a 32 GiB matrix): the
+    matrix-free two-site path must reduce the residual sweep over sweep and respect max_rank (sle.py:603-650)."""
+    rng = np.random.default_rng(7)
+    d, n, r = 4, 64, 4
+    S = 2 * np.eye(n) - np.eye(n, k=1) - np.eye(n, k=-1)
+    D = 0.5 * (np.eye(n, k=1) - np.eye(n, k=-1)) * np.sqrt(1e-3)
+    first = tt.build_core([[S, D, 1]])
+    mid = tt.build_core([[1, 0, 0], [D, 0, 0], [S, D, 1]])
+    last = tt.build_core([[1], [D], [S]])
+    op = TT([first] + [mid.copy() for _ in range(d - 2)] + [last])
+    rhs = TT([rng.standard_normal((1, n, 1, 1)) for _ in range(d)])
+    x0 = TT(ott.ortho_right([rng.standard_normal((1 if i == 0 else r, n, 1, 1 if i == d - 1 else r)) for i in range(d)]))
+    sols = [sle.mals(op, x0, rhs, repeats=k, threshold=1e-12, max_rank=6) for k in (1, 2)]
+    res = [osle.residual(op.cores, s.cores, rhs.cores) for s in sols]
+    assert res[1] <= res[0] * (1 + 1e-9) and res[1] < 1e-2
+    assert max(sols[1].ranks) <= 6 and sols[1].ranks[0] == sols[1].ranks[-1] == 1
+
+
+def test_trapezoidal_rule_and_adaptive_step_size(dev):
+    """The steppers next to implicit_euler (ode.py:366-450, :487-636) against the live reference's
+    states on the signaling cascade.  Chained steps amplify rounding differences, hence the per-step
+    tolerance schedule; the accepted time grid of the step-size control must be the reference's."""
+    z, zc = load("ode_steppers"), load("euler_cascade")
+    op = TT(cascade_operator(zc))
+    iv, guess = T(zc, "iv"), T(zc, "guess")
+    sol = ode.trapezoidal_rule(op, iv, guess, [0.5, 1.0, 0.5], repeats=2, progress=False)
+    assert sol[0] is iv and len(sol) == 4
+    for k in range(1, 4):
+        assert rel_diff(sol[k].cores, cores(z, f"trap/step{k}")) < 10 ** (k - 1) * SOL_TOL, k
+    for method in ("two_step_Euler", "trapezoidal_rule"):
+        ref_times = z[f"adapt/{method}/times"]
+        sol, times = ode.adaptive_step_size(op, iv, guess, 2.0, step_size_first=0.1, repeats=2, second_method=method,
+                                            progress=False)
+        assert len(times) == len(ref_times) and np.allclose(times, ref_times, rtol=1e-6, atol=0)
+        assert rel_diff(sol[1].cores, cores(z, f"adapt/{method}/step1")) < SOL_TOL
+        assert rel_diff(sol[-1].cores, cores(z, f"adapt/{method}/step{len(ref_times) - 1}")) < 1e-5

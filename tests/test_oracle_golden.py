@@ -149,3 +149,13 @@ def test_ortho():
     tc = cores(z, "tc")
     assert rel_diff(ott.ortho_left(ott.copy_cores(tc)), cores(z, "tc_left")) < 1e-12
     assert rel_diff(ott.ortho_right(ott.copy_cores(tc)), cores(z, "tc_right")) < 1e-12
+
+
+def test_trapezoidal_rule_oracle_matches_reference():
+    """ode.trapezoidal_rule (ode.py:366-450) on the signaling cascade: the oracle against the live reference's steps."""
+    from oracle import ode as oode
+    z, zc = load("ode_steppers"), load("euler_cascade")
+    op = cascade_operator(zc)
+    sol = oode.trapezoidal_rule(op, cores(zc, "iv"), cores(zc, "guess"), [0.5, 1.0, 0.5], repeats=2)
+    for k in range(1, 4):
+        assert rel_diff(sol[k], cores(z, f"trap/step{k}")) < 1e-9, k
