@@ -322,7 +322,7 @@ def run_ours(args, cfg):
                                               f"blocks of the operator core ({nnz_blocks} of {A.shape[0] * A.shape[3]} non-zero "
                                               "here), so the tensor pipe executes executed_flops_per_matvec",
                              "achieved_executed": F_exec / (mv_ms * 1e-3) / 1e12,
-                             "stack_update": {"kernel": "sktt_stack_left_op (three strided DMMA GEMMs + split-K reduce)",
+                             "stack_update": {"kernel": "sktt_stack_left_op = image build + tiling + stack_persistent_kernel (stage-1 tiles | stage-2 tiles with the third contraction per tile | ordered reduction of the tile partials)",
                                               "flops": F_stack, "us": stack_ms * 1e3,
                                               "achieved": F_stack / (stack_ms * 1e-3) / 1e12,
                                               "frac": F_stack / (stack_ms * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS},

@@ -204,7 +204,9 @@ struct S23 {
 template <int RB, int NA, int MB>
 __global__ void mv_prepare_kernel(const double* __restrict__ A, const double* __restrict__ Rt, const double* __restrict__ L,
                                   double* __restrict__ Aimg, double* __restrict__ Rimg, double* __restrict__ Limg, int r,
-                                  int R, int mtot, int ntot) {
+                                  int R, int mtot, int ntot, int swap) {
+    // swap: the operator core is read with its two rank indices exchanged, image A~[b', m, n, b] = A[b, m, n, b'] stored
+    // as [RB][m][n][R] in memory (the right-stack update is the left-stack update of the mirrored core)
     using P = S23<RB, NA, MB>;
     const long long na = (long long)R * (mtot / MB) * (ntot / P::KC) * P::A_ELEMS;
     const long long nr = (long long)(P::K3 / P::KC) * P::B_ELEMS;
@@ -231,27 +233,32 @@ __global__ void mv_prepare_kernel(const double* __restrict__ A, const double* __
             int mblk = (int)(t % (mtot / MB));
             int b = (int)(t / (mtot / MB));
             double v = 0.0;
-            if (kk < P::KC) v = A[(((size_t)b * mtot + mblk * MB + mm) * ntot + nc * P::KC + kk) * RB + q];
+            if (kk < P::KC)
+                v = swap ? A[(((size_t)q * mtot + mblk * MB + mm) * ntot + nc * P::KC + kk) * R + b]
+                         : A[(((size_t)b * mtot + mblk * MB + mm) * ntot + nc * P::KC + kk) * RB + q];
             Aimg[e] = v;
         } else {
             long long f = e - na;
             int col = (int)(f % P::LDB);
             long long row = f / P::LDB;
-            Rimg[f] = col < NA ? Rt[(size_t)row * NA + col] : 0.0;
+            Rimg[f] = (Rt && col < NA) ? Rt[(size_t)row * NA + col] : 0.0;
         }
     }
 }
 
 // natural [a][n][NA]  <->  tiled [n][a][NA + 4] (padding columns zero)
 template <int NA>
-__global__ void to_tiled_kernel(const double* __restrict__ src, double* __restrict__ dst, int r, int ntot) {
+__global__ void to_tiled_kernel(const double* __restrict__ src, double* __restrict__ dst, int r, int ntot, int swap) {
+    // swap: src is [NA][n][r] and the tiled vector holds its mirror x~[a][n][col] = src[col][n][a]
     const long long total = (long long)ntot * r * (NA + 4);
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
         int col = (int)(e % (NA + 4));
         long long t = e / (NA + 4);
         int a = (int)(t % r), nn = (int)(t / r);
-        dst[e] = col < NA ? src[((size_t)a * ntot + nn) * NA + col] : 0.0;
+        double v = 0.0;
+        if (col < NA) v = swap ? src[((size_t)col * ntot + nn) * r + a] : src[((size_t)a * ntot + nn) * NA + col];
+        dst[e] = v;
     }
 }
 template <int NA>
@@ -496,11 +503,12 @@ mv_stage23_kernel(const double* __restrict__ T1p, const double* __restrict__ Aim
 // 9): one CTA per (b, q) block ORs a bit into the mask word, and the second contraction skips the zero blocks -- adding
 // exact zeros changes no sum.
 __global__ void mv_mask_kernel(const double* __restrict__ A, unsigned long long* __restrict__ mask, int RB, int mtot,
-                               int ntot) {
+                               int ntot, int swap) {
+    const int R = gridDim.x / RB;
     const int b = blockIdx.x / RB, q = blockIdx.x % RB;
     int nz = 0;
     for (int e = threadIdx.x; e < mtot * ntot; e += blockDim.x)
-        nz |= A[((size_t)b * mtot * ntot + e) * RB + q] != 0.0;
+        nz |= (swap ? A[((size_t)q * mtot * ntot + e) * R + b] : A[((size_t)b * mtot * ntot + e) * RB + q]) != 0.0;
     nz = __syncthreads_or(nz);
     if (threadIdx.x == 0 && nz) atomicOr(mask, 1ull << (b * RB + q));
 }
@@ -807,6 +815,146 @@ __host__ __device__ inline size_t pcg_phase_bytes(int K1) {
 }
 __host__ __device__ inline size_t pcg_rres_bytes() { return (size_t)(Cfg::K3 / Cfg::KC) * Cfg::B_ELEMS * sizeof(double); }
 
+// Interface-stack update (sle.py:217-219 / :274-276 through the mirrored core): stages 1 and 2 are those of the matvec with
+// the solution core x in the place of the Krylov vector; the third contraction sums over (c, m) -- across tiles -- so
+// every tile leaves the partial   P_tile[(a2, b2), c2] = sum_{m in tile} T2[m, (a2, b2)] x[c, m, c2]   (192 x 64, K = 32)
+// and a last phase adds the partials in a fixed order.
+template <int RB, int NA, int MB>
+__device__ void p_s2x_tile(unsigned char* smem_raw, unsigned long long* full, const double* __restrict__ T1p,
+                           const double* __restrict__ Aimg, const double* __restrict__ xt, double* __restrict__ part, int r,
+                           int R, int mtot, int ntot, unsigned long long blockmask, int c, int mblk, bool first) {
+    using P = S23<RB, NA, MB>;
+    constexpr int KC = P::KC, LDB = P::LDB, LDA = P::LDA, LDT = P::LDT, STAGES = PSTAGES;
+    constexpr int QBLK = MB * LDA;
+    static_assert(RB == 3 && NA == 64 && MB == 32, "warp layout of the last contraction: 8 x 2 warps of 24 x 32");
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    double* T2s = ring + (size_t)STAGES * P::SLOT;
+    unsigned long long* empty = full + STAGES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = mblk * MB;
+    const int nchunks_n = ntot / KC;
+    const int T2n = R * nchunks_n;
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            if (!first) {
+                mbar_inval(full + s);
+                mbar_inval(empty + s);
+            }
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == CONSUMER_WARPS) {
+        if (lane == 0) {
+            fence_proxy_async();
+            for (int t = 0; t < T2n; ++t) {
+                const int s = t % STAGES;
+                if (t >= STAGES) mbar_wait(empty + s, ((t / STAGES) & 1) ^ 1);
+                double* slot = ring + (size_t)s * P::SLOT;
+                const int b = t / nchunks_n, nc = t % nchunks_n;
+                const unsigned qmask = (unsigned)(blockmask >> (b * RB)) & ((1u << RB) - 1u);
+                mbar_expect_tx(full + s, (unsigned)((P::B_ELEMS + __popc(qmask) * QBLK) * sizeof(double)));
+                bulk_g2s(slot, T1p + (((size_t)b * r + c) * ntot + (size_t)nc * KC) * LDB, P::B_ELEMS * sizeof(double),
+                         full + s);
+                const double* asrc = Aimg + (((size_t)b * (mtot / MB) + mblk) * nchunks_n + nc) * P::A_ELEMS;
+#pragma unroll
+                for (int q = 0; q < RB; ++q)
+                    if ((qmask >> q) & 1u)
+                        bulk_g2s(slot + P::B_ELEMS + (size_t)q * QBLK, asrc + (size_t)q * QBLK, QBLK * sizeof(double), full + s);
+            }
+        }
+        return;
+    }
+    const int tile = warp & 7, khalf = warp >> 3;
+    const int wm0 = (tile & 1) * 16, wn0 = (tile >> 1) * 16;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int kbeg = khalf * (KC / 2);
+    double acc2[RB][2][2][2];
+#pragma unroll
+    for (int q = 0; q < RB; ++q)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc2[q][i][j][0] = acc2[q][i][j][1] = 0.0;
+    for (int t = 0; t < T2n; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(full + s, (t / STAGES) & 1);
+        const double* slot = ring + (size_t)s * P::SLOT;
+        const double* bs = slot + wn0 + fr;
+        const double* as = slot + P::B_ELEMS + (size_t)(wm0 + fr) * LDA + fk;
+        const unsigned qmask = (unsigned)(blockmask >> ((t / nchunks_n) * RB)) & ((1u << RB) - 1u);
+        switch (qmask) {
+            case 1: s2_chunk<RB, MB, LDA, LDB, KC, 1>(acc2, as, bs, kbeg, fk); break;
+            case 2: s2_chunk<RB, MB, LDA, LDB, KC, 2>(acc2, as, bs, kbeg, fk); break;
+            case 3: s2_chunk<RB, MB, LDA, LDB, KC, 3>(acc2, as, bs, kbeg, fk); break;
+            case 4: s2_chunk<RB, MB, LDA, LDB, KC, 4>(acc2, as, bs, kbeg, fk); break;
+            case 5: s2_chunk<RB, MB, LDA, LDB, KC, 5>(acc2, as, bs, kbeg, fk); break;
+            case 6: s2_chunk<RB, MB, LDA, LDB, KC, 6>(acc2, as, bs, kbeg, fk); break;
+            case 7: s2_chunk<RB, MB, LDA, LDB, KC, 7>(acc2, as, bs, kbeg, fk); break;
+            default: break;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+    // x tile of this (c, m block): rows of the tiled vector, straight into the ring once every warp is done with it
+    consumer_bar_sync();
+    double* Xs = ring;                                     // [MB][LDB]
+    for (int e = tid; e < MB * LDB; e += CONSUMER_WARPS * 32)
+        Xs[e] = xt[((size_t)(m0 + e / LDB) * r + c) * LDB + e % LDB];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (khalf == h) {
+#pragma unroll
+            for (int q = 0; q < RB; ++q)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int mm = wm0 + 8 * i + fr, a2 = wn0 + 8 * j + 2 * fk;
+                        double* d0 = T2s + (size_t)mm * LDT + (size_t)a2 * RB + q;
+                        double* d1 = d0 + RB;
+                        if (h == 0) {
+                            *d0 = acc2[q][i][j][0];
+                            *d1 = acc2[q][i][j][1];
+                        } else {
+                            *d0 += acc2[q][i][j][0];
+                            *d1 += acc2[q][i][j][1];
+                        }
+                    }
+        }
+        consumer_bar_sync();
+    }
+    // P[(a2,b2), c2] = sum_m T2s[m][(a2,b2)] Xs[m][c2]: warp (wr, wc) owns rows 24 wr .. +24, columns 32 wc .. +32
+    const int wr = warp >> 1, wc = warp & 1;
+    double acc[3][4][2];
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < MB; k0 += 4) {
+        double af[3], bf[4];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) af[t] = T2s[(size_t)(k0 + fk) * LDT + 24 * wr + 8 * t + fr];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bf[u] = Xs[(k0 + fk) * LDB + 32 * wc + 8 * u + fr];
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dmma(acc[t][u][0], acc[t][u][1], af[t], bf[u]);
+    }
+    double* dst = part + (size_t)(mblk * r + c) * (NA * RB) * NA;
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<double2*>(dst + (size_t)(24 * wr + 8 * t + fr) * NA + 32 * wc + 8 * u + 2 * fk) =
+                make_double2(acc[t][u][0], acc[t][u][1]);
+}
+
 }  // namespace
 
 struct PcgParams {
@@ -1063,25 +1211,32 @@ static inline int ew_grid(const sktt_ctx* ctx, long long total) {
 }
 
 // image = [Aimg | Rimg | Limg]
-int sktt_fused_prepare(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* Lst,
-                       const double* A, const double* Rst, double* image) {
+int sktt_fused_prepare_ex(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* Lst,
+                          const double* A, const double* Rst, double* image, int swap) {
     const long long na = img_a_elems(R, m, n), nr = img_r_elems();
     const long long total = sktt_fused_image_elems(r, R, m, n);
     mv_prepare_kernel<3, 64, 32><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(A, Rst, Lst, image, image + na,
                                                                                 image + na + nr, (int)r, (int)R, (int)m,
-                                                                                (int)n);
+                                                                                (int)n, swap);
     SKTT_LAUNCH_CHECK(ctx);
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(image + total - 8);
     SKTT_CUDA(ctx, cudaMemsetAsync(mask, 0, 8 * sizeof(double), ctx->stream));
-    mv_mask_kernel<<<(unsigned)(R * 3), 256, 0, ctx->stream>>>(A, mask, 3, (int)m, (int)n);
+    mv_mask_kernel<<<(unsigned)(R * 3), 256, 0, ctx->stream>>>(A, mask, 3, (int)m, (int)n, swap);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
 }
+int sktt_fused_prepare(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* Lst,
+                       const double* A, const double* Rst, double* image) {
+    return sktt_fused_prepare_ex(ctx, r, R, m, n, Lst, A, Rst, image, 0);
+}
 
-int sktt_fused_to_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst) {
-    to_tiled_kernel<64><<<ew_grid(ctx, sktt_fused_tiled_len(r, n)), 256, 0, ctx->stream>>>(src, dst, (int)r, (int)n);
+int sktt_fused_to_tiled_ex(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst, int swap) {
+    to_tiled_kernel<64><<<ew_grid(ctx, sktt_fused_tiled_len(r, n)), 256, 0, ctx->stream>>>(src, dst, (int)r, (int)n, swap);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
+}
+int sktt_fused_to_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst) {
+    return sktt_fused_to_tiled_ex(ctx, r, n, src, dst, 0);
 }
 int sktt_fused_from_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst) {
     from_tiled_kernel<64><<<ew_grid(ctx, r * n * 64), 256, 0, ctx->stream>>>(src, dst, (int)r, (int)n);
@@ -1174,6 +1329,95 @@ int sktt_fused_pcg_persistent(sktt_ctx* ctx, long long r, long long R, long long
     }
     void* args[] = {&a};
     SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)pcg_persistent_kernel, dim3(ctx->sm_count), dim3(THREADS), args, smem,
+                                               ctx->stream));
+    ctx->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ persistent stack update
+namespace {
+struct StackParams {
+    const double* image;      // [Aimg | Rimg (unused) | Limg | mask] of (stack, operator core)
+    long long na, nr, nl;
+    int r, R, mtot, ntot;
+    const double* xt;         // solution core, tiled layout
+    double* T1p;
+    double* part;             // [tiles][192][64]
+    double* out;              // [64][3][64] new stack
+};
+
+__global__ void __launch_bounds__(THREADS) stack_persistent_kernel(StackParams a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x;
+    const double* Aimg = a.image;
+    const double* Limg = a.image + a.na + a.nr;
+    const unsigned long long blockmask = *reinterpret_cast<const unsigned long long*>(a.image + a.na + a.nr + a.nl);
+    const int M1 = a.R * a.r, K1 = a.r;
+    const int tiles1 = a.ntot * ((M1 + S1_BM - 1) / S1_BM), tiles2 = a.r * (a.mtot / 32);
+    const size_t data_bytes = pcg_phase_bytes(K1);
+    unsigned long long* bars1 = reinterpret_cast<unsigned long long*>(smem_raw + data_bytes);
+    unsigned long long* bars2 = bars1 + S1_GROUPS;
+    bool first1 = true, first2 = true;
+    auto gsync = [&]() {
+        __syncthreads();
+        if (tid == 0) {
+            fence_proxy_async();
+            __threadfence();
+        }
+        grid.sync();
+    };
+    for (int t = cta; t < tiles1; t += G) {
+        p_s1_tile(smem_raw, bars1, Limg, a.xt, a.T1p, M1, K1, a.ntot, t % a.ntot, t / a.ntot, first1);
+        first1 = false;
+    }
+    gsync();
+    for (int t = cta; t < tiles2; t += G) {
+        p_s2x_tile<3, 64, 32>(smem_raw, bars2, a.T1p, Aimg, a.xt, a.part, a.r, a.R, a.mtot, a.ntot, blockmask, t % a.r, t / a.r,
+                              first2);
+        first2 = false;
+    }
+    gsync();
+    // out[e] = sum over tiles, in tile order; eight lanes share an entry (16 tiles each for 128 tiles), fixed shuffle tree
+    const int E = 64 * 3 * 64;
+    const long long gtid = (long long)cta * THREADS + tid, gthreads = (long long)G * THREADS;
+    const int sub = (int)(gtid & 7);
+    for (long long e = gtid >> 3; e < E + 3; e += gthreads >> 3) {         // + 3: keeps whole warps in the shuffles
+        double sacc = 0.0;
+        if (e < E)
+            for (int t = sub; t < tiles2; t += 8) sacc += __ldcg(a.part + (size_t)t * E + e);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (e < E && sub == 0) a.out[e] = sacc;
+    }
+}
+}  // namespace
+
+// out = new interface stack [64][3][64] from the prepared image of (old stack, operator core) and the solution core in
+// the tiled layout.  T1p as for the matvec; part: r * (m / 32) * 12288 doubles.
+int sktt_fused_stack_update(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                            const double* xt, double* out, double* T1p, double* part) {
+    StackParams a;
+    a.image = image;
+    a.na = img_a_elems(R, m, n);
+    a.nr = img_r_elems();
+    a.nl = img_l_elems(r, R);
+    a.r = (int)r;
+    a.R = (int)R;
+    a.mtot = (int)m;
+    a.ntot = (int)n;
+    a.xt = xt;
+    a.T1p = T1p;
+    a.part = part;
+    a.out = out;
+    const size_t smem = pcg_phase_bytes((int)r) + 128;
+    static bool configured = false;
+    if (!configured) {
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(stack_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    void* args[] = {&a};
+    SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)stack_persistent_kernel, dim3(ctx->sm_count), dim3(THREADS), args, smem,
                                                ctx->stream));
     ctx->launches++;
     return 0;

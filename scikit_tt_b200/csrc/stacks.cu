@@ -20,9 +20,38 @@ int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m
 
 static inline Idx2 two(long long d, long long s_hi, long long s_lo) { return mk_idx(d, s_hi, s_lo); }
 
+int sktt_fused_prepare_ex(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* Lst,
+                          const double* A, const double* Rst, double* image, int swap);
+int sktt_fused_to_tiled_ex(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst, int swap);
+int sktt_fused_stack_update(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                            const double* xt, double* out, double* T1p, double* part);
+
+// scratch of the persistent stack-update kernel for an input side (rin, Rin): T1 (padded) | tiled core | tile partials
+static int64_t fused_stack_need(int64_t rin, int64_t Rin, int64_t m, int64_t n) {
+    return Rin * rin * n * 68 + n * rin * 68 + rin * ((m + 31) / 32) * 12288;
+}
+
 extern "C" int64_t sktt_stack_op_work(int64_t r, int64_t R, int64_t m, int64_t n, int64_t r2, int64_t R2) {
     int64_t t1 = R * r * n * r2, t2 = r * m * r2 * R2;
-    return t1 + t2;
+    int64_t need = t1 + t2;
+    if (r2 == 64 && R2 == 3 && fused_stack_need(r, R, m, n) > need) need = fused_stack_need(r, R, m, n);
+    if (r == 64 && R == 3 && fused_stack_need(r2, R2, m, n) > need) need = fused_stack_need(r2, R2, m, n);
+    return need;
+}
+
+// The persistent fused stack update (fused.cu) for the shapes it covers; `mirror` runs the right-stack update as the
+// left-stack update of the mirrored cores.  (rin, Rin): ranks on the side of the OLD stack.
+static int fused_stack(sktt_ctx* ctx, long long rin, long long Rin, long long m, long long n, const void* stack,
+                       const void* x, const void* A, void* out, void* work, int mirror) {
+    const size_t img_bytes = (size_t)sktt_fused_image_elems(rin, Rin, m, n) * sizeof(double);
+    SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + img_bytes));
+    double* image = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
+    double* T1p = (double*)work;
+    double* xt = T1p + Rin * rin * n * 68;
+    double* part = xt + n * rin * 68;
+    SKTT_TRY(sktt_fused_prepare_ex(ctx, rin, Rin, m, n, (const double*)stack, (const double*)A, nullptr, image, mirror));
+    SKTT_TRY(sktt_fused_to_tiled_ex(ctx, rin, n, (const double*)x, xt, mirror));
+    return sktt_fused_stack_update(ctx, rin, Rin, m, n, image, xt, (double*)out, T1p, part);
 }
 
 // T1[(b,c),(n,a2)] = sum_a L[a,(b,c)] X[a,(n,a2)]            (first tensordot of sle.py:217)
@@ -53,6 +82,8 @@ extern "C" int sktt_stack_left_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t R
     char* T1 = (char*)work;
     char* T2 = T1 + (size_t)(R * r * n * r2) * es;
     const int conj_col = (conj_mode == SKTT_CONJ_COL), conj_row = !conj_col;
+    if (!(ctx->debug & 32) && sktt_fused_supported(ctx, dtype, r, R, m, n, r2, R2))   // real: conjugation is the identity
+        return fused_stack(ctx, r, R, m, n, Lst, x, A, out, work, 0);
     SKTT_TRY(left_step1(ctx, dtype, r, R, n * r2, Lst, x, conj_col, T1));
     SKTT_TRY(left_step2(ctx, dtype, r, R, m, n, r2, R2, T1, A, T2));
     // out[(a2,b2),c2] = sum_{(c,m)} T2[(c,m),(a2,b2)] X2[(c,m),c2]     (third tensordot, sle.py:219)
@@ -68,6 +99,8 @@ extern "C" int sktt_stack_right_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t 
     SKTT_TRY(check_dtype(ctx, dtype));
     if (m != n) return sktt_fail(ctx, SKTT_ERR_ARG, "stack_right_op: row and column mode sizes must agree");
     size_t es = dtype_size(dtype);
+    if (!(ctx->debug & 32) && sktt_fused_supported(ctx, dtype, r2, R2, m, n, r, R))
+        return fused_stack(ctx, r2, R2, m, n, Rst, x, A, out, work, 1);
     char* U1 = (char*)work;                                  // [c, m, a2, b2]
     char* U2 = U1 + (size_t)(r * m * r2 * R2) * es;          // [n, a2, b, c]
     // U1[(c,m),(a2,b2)] = sum_c2 conj(x)[(c,m),c2] Rst[(a2,b2),c2]          (sle.py:274)

@@ -75,7 +75,7 @@ def test_gemm2_plain_and_strided(dev, cplx, mode):
 # ------------------------------------------------------------------------------------------------ stacks
 STACK_SHAPES = [  # r, R, n, r2, R2
     (1, 1, 3, 2, 2), (3, 2, 4, 5, 3), (4, 4, 64, 4, 4), (8, 21, 3, 8, 21), (16, 3, 16, 16, 3), (64, 3, 64, 64, 3),
-    (7, 5, 9, 1, 1)]
+    (7, 5, 9, 1, 1), (32, 3, 64, 64, 3), (64, 3, 64, 32, 3), (8, 2, 32, 64, 3), (64, 3, 96, 4, 5)]
 
 
 @pytest.mark.parametrize("cplx", [False, True])
