@@ -361,13 +361,36 @@ __device__ __noinline__ void cq_cholesky(T* Gs, const int LD, const int NN, cons
 // below: small (K = 4 n rows), so the serial chain of n reflectors costs tens of microseconds, not a millisecond.
 template <typename T>
 __device__ __noinline__ void cq_house_r(T* Y, const int LD, const int K, const int n, double* red, T* wv, T* wpart) {
-    // n <= 64.  Threads form a 16 x 16 grid: ty strides the rows, tx the trailing columns (at most four per thread).
+    // n <= 64.  Threads form a 16 x 16 grid: ty strides the rows, tx the columns j .. n-1 (at most four per thread).
+    // One pass per reflector gives g[c] = sum_{i>j} conj(y_ij) y_ic for every c >= j: g[j] is the tail norm, and
+    // v^H y_c = y_jc + conj(scl) g[c], so tau, beta and w = tau^H v^H Y are known after a single reduction -- three
+    // CTA barriers per reflector.
+    (void)red;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int kk = min(K, n);
     for (int j = 0; j < kk; ++j) {
-        double part = 0.0;
-        for (int i = j + 1 + tid; i < K; i += CQ_THREADS) part += Num<T>::abs2(Y[i * LD + j]);
-        const double sigma = block_sum<double>(part, red);
+        T acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = Num<T>::zero();
+        for (int i = j + 1 + ty; i < K; i += 16) {
+            const T cy = Num<T>::conj(Y[i * LD + j]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = j + tx + 16 * q;
+                if (c < n) Num<T>::fma(acc[q], cy, Y[i * LD + c]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = j + tx + 16 * q;
+            if (c < n) wpart[ty * 64 + (c - j)] = acc[q];
+        }
+        __syncthreads();
+        // every thread derives the reflector scalars from g[j] (same bits everywhere); threads c - j < n - j finish w
+        T gj = Num<T>::zero();
+#pragma unroll
+        for (int t = 0; t < 16; ++t) gj = Num<T>::add(gj, wpart[t * 64]);
+        const double sigma = Num<T>::real(gj);
         const T alpha = Y[j * LD + j];
         const double ar = Num<T>::real(alpha), ai = Num<T>::imag(alpha);
         T tau = Num<T>::zero(), scl = Num<T>::zero();
@@ -378,30 +401,13 @@ __device__ __noinline__ void cq_house_r(T* Y, const int LD, const int K, const i
             tau = Num<T>::from((beta - ar) / beta, -ai / beta);
             scl = Num<T>::div(Num<T>::one(), Num<T>::from(ar - beta, ai));
         }
-        // partial w[c] = sum over this thread's rows of conj(v_i) y_ic   (v_j = 1, v_i = y_ij * scl)
-        T acc[4];
+        if (tid >= 1 && tid < n - j) {
+            const int c = j + tid;
+            T g = Num<T>::zero();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] = Num<T>::zero();
-        for (int i = j + ty; i < K; i += 16) {
-            const T cvi = i == j ? Num<T>::one() : Num<T>::conj(Num<T>::mul(Y[i * LD + j], scl));
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int c = j + 1 + tx + 16 * q;
-                if (c < n) Num<T>::fma(acc[q], cvi, Y[i * LD + c]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c = j + 1 + tx + 16 * q;
-            if (c < n) wpart[ty * 64 + c] = acc[q];
-        }
-        __syncthreads();
-        if (tid < n - j - 1) {
-            const int c = j + 1 + tid;
-            T sacc = Num<T>::zero();
-#pragma unroll
-            for (int t = 0; t < 16; ++t) sacc = Num<T>::add(sacc, wpart[t * 64 + c]);
-            wv[c] = Num<T>::mul(Num<T>::conj(tau), sacc);
+            for (int t = 0; t < 16; ++t) g = Num<T>::add(g, wpart[t * 64 + tid]);
+            const T vhy = Num<T>::add(Y[j * LD + c], Num<T>::mul(Num<T>::conj(scl), g));
+            wv[c] = Num<T>::mul(Num<T>::conj(tau), vhy);
         }
         __syncthreads();
         for (int i = j + ty; i < K; i += 16) {
