@@ -179,3 +179,8 @@ static inline int check_dtype(sktt_ctx* ctx, int dtype) {
 }
 
 int sktt_scratch_reserve(sktt_ctx* ctx, size_t bytes);
+
+// The fused matvec / stack kernels (fused.cu) work on an input-side solution rank padded to a multiple of 4 and on an
+// output side padded to (r2, R2) = (64, 3); the image / tiling kernels fill the padding with zeros, so edge cores
+// (r = 1 or r2 = 1) and small operator ranks run through the same kernels.
+static inline long long fused_rpad(long long r) { return (r + 3) & ~3LL; }

@@ -204,7 +204,10 @@ struct S23 {
 template <int RB, int NA, int MB>
 __global__ void mv_prepare_kernel(const double* __restrict__ A, const double* __restrict__ Rt, const double* __restrict__ L,
                                   double* __restrict__ Aimg, double* __restrict__ Rimg, double* __restrict__ Limg, int r,
-                                  int R, int mtot, int ntot, int swap) {
+                                  int R, int mtot, int ntot, int swap, int r_act, int r2_act, int R2_act,
+                                  unsigned long long* __restrict__ mask) {
+    // r is the PADDED input-side rank; (r_act, r2_act, R2_act) are the extents of the operands in memory, everything
+    // beyond them is zero in the images
     // swap: the operator core is read with its two rank indices exchanged, image A~[b', m, n, b] = A[b, m, n, b'] stored
     // as [RB][m][n][R] in memory (the right-stack update is the left-stack update of the mirrored core)
     using P = S23<RB, NA, MB>;
@@ -220,7 +223,8 @@ __global__ void mv_prepare_kernel(const double* __restrict__ A, const double* __
             long long t = f / S1_LDA;
             int a = (int)(t % r), mt = (int)(t / r);
             int m = mt * S1_BM + mm;
-            Limg[f] = (mm < S1_BM && m < M1) ? L[(size_t)a * M1 + m] : 0.0;
+            const int bb = m / r, cc = m % r;
+            Limg[f] = (mm < S1_BM && m < M1 && a < r_act && cc < r_act) ? L[((size_t)a * R + bb) * r_act + cc] : 0.0;
         } else if (e < na) {
             int kk = (int)(e % P::LDA);
             long long t = e / P::LDA;
@@ -233,23 +237,32 @@ __global__ void mv_prepare_kernel(const double* __restrict__ A, const double* __
             int mblk = (int)(t % (mtot / MB));
             int b = (int)(t / (mtot / MB));
             double v = 0.0;
-            if (kk < P::KC)
+            if (kk < P::KC && (swap || q < R2_act))
                 v = swap ? A[(((size_t)q * mtot + mblk * MB + mm) * ntot + nc * P::KC + kk) * R + b]
-                         : A[(((size_t)b * mtot + mblk * MB + mm) * ntot + nc * P::KC + kk) * RB + q];
+                         : A[(((size_t)b * mtot + mblk * MB + mm) * ntot + nc * P::KC + kk) * R2_act + q];
             Aimg[e] = v;
+            // block mask (zeroed before the launch): bit b * RB + q <- A[b, :, :, q] has a non-zero entry.  Once a bit
+            // is visible nobody writes it again, so a dense core costs a handful of atomics per block, not one per entry.
+            if (v != 0.0) {
+                const unsigned long long bit = 1ull << (b * RB + q);
+                if (!(*reinterpret_cast<volatile unsigned long long*>(mask) & bit)) atomicOr(mask, bit);
+            }
         } else {
             long long f = e - na;
             int col = (int)(f % P::LDB);
             long long row = f / P::LDB;
-            Rimg[f] = (Rt && col < NA) ? Rt[(size_t)row * NA + col] : 0.0;
+            const int a2 = (int)(row / RB), b2 = (int)(row % RB);
+            Rimg[f] = (Rt && col < r2_act && a2 < r2_act && b2 < R2_act) ? Rt[((size_t)a2 * R2_act + b2) * r2_act + col] : 0.0;
         }
     }
 }
 
 // natural [a][n][NA]  <->  tiled [n][a][NA + 4] (padding columns zero)
 template <int NA>
-__global__ void to_tiled_kernel(const double* __restrict__ src, double* __restrict__ dst, int r, int ntot, int swap) {
-    // swap: src is [NA][n][r] and the tiled vector holds its mirror x~[a][n][col] = src[col][n][a]
+__global__ void to_tiled_kernel(const double* __restrict__ src, double* __restrict__ dst, int r, int ntot, int swap,
+                                int r_act, int c_act) {
+    // r: padded row count of the tiled vector; src is [r_act][n][c_act] (rows / columns beyond that are zero).
+    // swap: src is [c_act][n][r_act] and the tiled vector holds its mirror x~[a][n][col] = src[col][n][a]
     const long long total = (long long)ntot * r * (NA + 4);
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
@@ -257,17 +270,19 @@ __global__ void to_tiled_kernel(const double* __restrict__ src, double* __restri
         long long t = e / (NA + 4);
         int a = (int)(t % r), nn = (int)(t / r);
         double v = 0.0;
-        if (col < NA) v = swap ? src[((size_t)col * ntot + nn) * r + a] : src[((size_t)a * ntot + nn) * NA + col];
+        if (col < c_act && a < r_act)
+            v = swap ? src[((size_t)col * ntot + nn) * r_act + a] : src[((size_t)a * ntot + nn) * c_act + col];
         dst[e] = v;
     }
 }
 template <int NA>
-__global__ void from_tiled_kernel(const double* __restrict__ src, double* __restrict__ dst, int r, int ntot) {
-    const long long total = (long long)r * ntot * NA;
+__global__ void from_tiled_kernel(const double* __restrict__ src, double* __restrict__ dst, int r, int ntot, int r_act,
+                                  int c_act) {
+    const long long total = (long long)r_act * ntot * c_act;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
-        int col = (int)(e % NA);
-        long long t = e / NA;
+        int col = (int)(e % c_act);
+        long long t = e / c_act;
         int nn = (int)(t % ntot), a = (int)(t / ntot);
         dst[e] = src[((size_t)nn * r + a) * (NA + 4) + col];
     }
@@ -500,19 +515,8 @@ mv_stage23_kernel(const double* __restrict__ T1p, const double* __restrict__ Aim
 }
 
 // Operator cores of SLIM / MPO type are block-sparse in their rank indices (the bench operator has 5 non-zero blocks of
-// 9): one CTA per (b, q) block ORs a bit into the mask word, and the second contraction skips the zero blocks -- adding
-// exact zeros changes no sum.
-__global__ void mv_mask_kernel(const double* __restrict__ A, unsigned long long* __restrict__ mask, int RB, int mtot,
-                               int ntot, int swap) {
-    const int R = gridDim.x / RB;
-    const int b = blockIdx.x / RB, q = blockIdx.x % RB;
-    int nz = 0;
-    for (int e = threadIdx.x; e < mtot * ntot; e += blockDim.x)
-        nz |= (swap ? A[((size_t)q * mtot * ntot + e) * R + b] : A[((size_t)b * mtot * ntot + e) * RB + q]) != 0.0;
-    nz = __syncthreads_or(nz);
-    if (threadIdx.x == 0 && nz) atomicOr(mask, 1ull << (b * RB + q));
-}
-
+// 9): mv_prepare_kernel ORs one bit per non-zero (b, q) block into the mask word of the image, and the second contraction
+// skips the zero blocks -- adding exact zeros changes no sum.
 using Cfg = S23<3, 64, 32>;
 
 
@@ -1126,11 +1130,13 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
     const double target2 = 0.25 * a.tol * a.tol * fn2;
     double prev = 1e300, relres = sqrt(rr / fn2);
     int iters = 0, cycles = 0, status = 0;
+    bool hit_limit = false, broke = false;
     for (int cycle = 0; cycle < a.max_cycles; ++cycle) {
         if (relres <= a.tol || relres > 0.5 * prev) break;
         prev = relres;
         double gamma_old = -1.0, alpha_old = 0.0, rr_rec = rr;
         bool conv = false;
+        broke = false;
         for (int it = 0; it < a.max_iters; ++it) {
             if (rr_rec <= target2) {
                 conv = true;
@@ -1143,7 +1149,10 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
             const double beta = firstit ? 0.0 : gamma / gamma_old;
             const double denom = firstit ? delta : delta - beta * gamma / alpha_old;
             if (!(denom > 0.0)) {
-                status = 2;
+                // the recurrence for p^H A p lost its sign (the one weak spot of the single-reduction form, seen once the
+                // residual has dropped ~8 digits) or the operator is not positive definite: leave the run and restart from
+                // the true residual below -- a restart that brings no progress ends the solve with status 2
+                broke = true;
                 break;
             }
             const double alpha = gamma / denom;
@@ -1167,12 +1176,12 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
         true_residual();
         relres = sqrt(rr / fn2);
         cycles = cycle + 1;
-        if (status == 2) break;
-        if (!conv) {
-            status = 1;
+        if (!conv && !broke) {                                 // iteration budget of a run exhausted
+            hit_limit = true;
             break;
         }
     }
+    if (!(relres <= a.tol)) status = hit_limit ? 1 : (broke ? 2 : 0);   // 0 with relres > tol: stagnated at the eps * cond floor
     if (gtid == 0) {
         a.out[0] = (double)iters;
         a.out[1] = relres;
@@ -1189,9 +1198,9 @@ bool sktt_fused_supported(const sktt_ctx* ctx, int dtype, long long r, long long
                           long long r2, long long R2) {
     if (dtype != SKTT_F64 || ctx->gemm_mode == 1) return false;
     if (m != n || n % 16 != 0 || m % 32 != 0) return false;
-    if (r % 4 != 0 || r > 128 || R > 14) return false;
-    if (!(R2 == 3 && r2 == 64)) return false;
-    return s1_smem_bytes((int)r) <= 200 * 1024;
+    if (r < 1 || fused_rpad(r) > 128 || R < 1 || R > 14) return false;
+    if (R2 < 1 || R2 > 3 || r2 < 1 || r2 > 64) return false;            // output side: padded to (64, 3)
+    return s1_smem_bytes((int)fused_rpad(r)) <= 200 * 1024;
 }
 
 static long long img_a_elems(long long R, long long m, long long n) { return R * (m / 32) * (n / Cfg::KC) * Cfg::A_ELEMS; }
@@ -1211,35 +1220,45 @@ static inline int ew_grid(const sktt_ctx* ctx, long long total) {
 }
 
 // image = [Aimg | Rimg | Limg]
+// r: PADDED input-side rank (fused_rpad); r_act, r2_act, R2_act: extents of Lst / A / Rst in memory
 int sktt_fused_prepare_ex(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* Lst,
-                          const double* A, const double* Rst, double* image, int swap) {
+                          const double* A, const double* Rst, double* image, int swap, long long r_act, long long r2_act,
+                          long long R2_act) {
     const long long na = img_a_elems(R, m, n), nr = img_r_elems();
     const long long total = sktt_fused_image_elems(r, R, m, n);
-    mv_prepare_kernel<3, 64, 32><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(A, Rst, Lst, image, image + na,
-                                                                                image + na + nr, (int)r, (int)R, (int)m,
-                                                                                (int)n, swap);
-    SKTT_LAUNCH_CHECK(ctx);
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(image + total - 8);
     SKTT_CUDA(ctx, cudaMemsetAsync(mask, 0, 8 * sizeof(double), ctx->stream));
-    mv_mask_kernel<<<(unsigned)(R * 3), 256, 0, ctx->stream>>>(A, mask, 3, (int)m, (int)n, swap);
+    mv_prepare_kernel<3, 64, 32><<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(A, Rst, Lst, image, image + na,
+                                                                                image + na + nr, (int)r, (int)R, (int)m,
+                                                                                (int)n, swap, (int)r_act, (int)r2_act,
+                                                                                (int)R2_act, mask);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
 }
 int sktt_fused_prepare(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* Lst,
                        const double* A, const double* Rst, double* image) {
-    return sktt_fused_prepare_ex(ctx, r, R, m, n, Lst, A, Rst, image, 0);
+    return sktt_fused_prepare_ex(ctx, r, R, m, n, Lst, A, Rst, image, 0, r, 64, 3);
 }
 
-int sktt_fused_to_tiled_ex(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst, int swap) {
-    to_tiled_kernel<64><<<ew_grid(ctx, sktt_fused_tiled_len(r, n)), 256, 0, ctx->stream>>>(src, dst, (int)r, (int)n, swap);
+int sktt_fused_to_tiled_ex(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst, int swap,
+                           long long r_act, long long c_act) {
+    to_tiled_kernel<64><<<ew_grid(ctx, sktt_fused_tiled_len(r, n)), 256, 0, ctx->stream>>>(src, dst, (int)r, (int)n, swap,
+                                                                                           (int)r_act, (int)c_act);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
 }
 int sktt_fused_to_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst) {
-    return sktt_fused_to_tiled_ex(ctx, r, n, src, dst, 0);
+    return sktt_fused_to_tiled_ex(ctx, r, n, src, dst, 0, r, 64);
 }
 int sktt_fused_from_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst) {
-    from_tiled_kernel<64><<<ew_grid(ctx, r * n * 64), 256, 0, ctx->stream>>>(src, dst, (int)r, (int)n);
+    from_tiled_kernel<64><<<ew_grid(ctx, r * n * 64), 256, 0, ctx->stream>>>(src, dst, (int)r, (int)n, (int)r, 64);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}
+int sktt_fused_from_tiled_ex(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst, long long r_act,
+                             long long c_act) {
+    from_tiled_kernel<64><<<ew_grid(ctx, r_act * n * c_act), 256, 0, ctx->stream>>>(src, dst, (int)r, (int)n, (int)r_act,
+                                                                                    (int)c_act);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -1278,14 +1297,19 @@ int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m
 }
 
 // natural-layout wrapper: v [r][n][64] -> y [r][m][64]; work holds T1p followed by the two tiled vectors
-int sktt_fused_matvec(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
-                      const double* v, double* y, double* work) {
+int sktt_fused_matvec_ex(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                         const double* v, double* y, double* work, long long r_act, long long r2_act) {
     double* T1p = work;
     double* vt = T1p + R * r * n * Cfg::LDB;
     double* yt = vt + sktt_fused_tiled_len(r, n);
-    SKTT_TRY(sktt_fused_to_tiled(ctx, r, n, v, vt));
+    SKTT_TRY(sktt_fused_to_tiled_ex(ctx, r, n, v, vt, 0, r_act, r2_act));
+    SKTT_CUDA(ctx, cudaMemsetAsync(yt, 0, (size_t)sktt_fused_tiled_len(r, n) * sizeof(double), ctx->stream));
     SKTT_TRY(sktt_fused_matvec_tiled(ctx, r, R, m, n, image, vt, yt, T1p));
-    return sktt_fused_from_tiled(ctx, r, m, yt, y);
+    return sktt_fused_from_tiled_ex(ctx, r, m, yt, y, r_act, r2_act);
+}
+int sktt_fused_matvec(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                      const double* v, double* y, double* work) {
+    return sktt_fused_matvec_ex(ctx, r, R, m, n, image, v, y, work, r, 64);
 }
 
 // ------------------------------------------------------------------------------------------------ persistent CG, host side

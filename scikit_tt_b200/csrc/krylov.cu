@@ -10,8 +10,10 @@
 
 // fused.cu: TMA-staged matvec on vectors in the tiled layout [n][a][r2 + 4]
 long long sktt_fused_tiled_len(long long r, long long n);
-int sktt_fused_to_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst);
-int sktt_fused_from_tiled(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst);
+int sktt_fused_to_tiled_ex(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst, int swap,
+                           long long r_act, long long c_act);
+int sktt_fused_from_tiled_ex(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst, long long r_act,
+                             long long c_act);
 int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
                             const double* vt, double* yt, double* T1p);
 int sktt_fused_matvec_tiled_dots(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
@@ -33,7 +35,7 @@ struct KOp {
 
 static int kop_matvec(sktt_ctx* ctx, int dtype, const KOp& k, const void* v, void* y, void* work) {
     if (k.tiled)
-        return sktt_fused_matvec_tiled(ctx, k.op.r, k.op.R, k.op.m, k.op.n, (const double*)k.op.image, (const double*)v,
+        return sktt_fused_matvec_tiled(ctx, fused_rpad(k.op.r), k.op.R, k.op.m, k.op.n, (const double*)k.op.image, (const double*)v,
                                        (double*)y, (double*)work);
     return sktt_local_matvec(ctx, dtype, &k.op, v, y, work);
 }
@@ -43,17 +45,22 @@ static int64_t local_dim(const sktt_local_op* op) {
 }
 // bound of the vector length in either layout
 static int64_t local_dim_bound(const sktt_local_op* op) {
-    return op->sites == 1 ? op->r * op->n * (op->r3 + 4) : local_dim(op);
+    return op->sites == 1 ? fused_rpad(op->r) * op->n * 68 : local_dim(op);
 }
 static int64_t local_mv_work(const sktt_local_op* op) {
-    if (op->sites == 1) return sktt_stack_op_work(op->r, op->R, op->m, op->n, op->r3, op->R2);
+    if (op->sites == 1) {
+        const int64_t generic = sktt_stack_op_work(op->r, op->R, op->m, op->n, op->r3, op->R2);
+        const int64_t fused = op->R * fused_rpad(op->r) * op->n * 68 + 2 * op->n * fused_rpad(op->r) * 68;   // T1 (padded) + tiled pair
+        return generic > fused ? generic : fused;
+    }
     return sktt_micro_matvec_mals_work(op->r, op->R, op->m, op->n, op->R2, op->m2, op->n2, op->R3, op->r3);
 }
 
 // upper bound of the prepared-operator image (fused.cu) for one-site operators, 0 otherwise
 static int64_t local_image_bound(const sktt_local_op* op) {
     if (op->sites != 1 || op->image) return 0;
-    return op->R * ((op->m + 31) / 32) * ((op->n + 15) / 16) * 1920 + 12 * 16 * 68 + ((op->R * op->r + 95) / 96) * op->r * 100 + 64 + 8;
+    const int64_t rp = fused_rpad(op->r);
+    return op->R * ((op->m + 31) / 32) * ((op->n + 15) / 16) * 1920 + 12 * 16 * 68 + ((op->R * rp + 95) / 96) * rp * 100 + 64 + 8;
 }
 
 // elements used by the solver proper (vectors of length Nb + small state), excluding matvec scratch
@@ -463,7 +470,7 @@ static int cg_tiled_core(sktt_ctx* ctx, const KOp& op, const CgTiledBufs& b, dou
                                                                                                           b.r, b.z, flags);
                 ctx->launches++;
             }
-            status = sktt_fused_matvec_tiled_dots(ctx, o.r, o.R, o.m, o.n, (const double*)o.image, z, b.w, b.mvwork, z,
+            status = sktt_fused_matvec_tiled_dots(ctx, fused_rpad(o.r), o.R, o.m, o.n, (const double*)o.image, z, b.w, b.mvwork, z,
                                                   precond ? b.r : nullptr, dpart, counter, dots, flags);
             if (status) break;
             pcgear_update_kernel<<<nb, 256, 0, ctx->stream>>>(N, u, b.r, b.p, b.s, b.w, z, dots, st + 2 * (launched & 1),
@@ -502,7 +509,7 @@ static int cg_tiled_residual(sktt_ctx* ctx, const KOp& op, const CgTiledBufs& b,
     double* mbox = (double*)ctx->mailbox;
     const int nb = ew_blocks(ctx, N);
     if (fnorm2) SKTT_TRY(blas1_dot(ctx, SKTT_F64, N, f, f, slots + 5));
-    SKTT_TRY(sktt_fused_matvec_tiled(ctx, o.r, o.R, o.m, o.n, (const double*)o.image, u, b.w, b.mvwork));
+    SKTT_TRY(sktt_fused_matvec_tiled(ctx, fused_rpad(o.r), o.R, o.m, o.n, (const double*)o.image, u, b.w, b.mvwork));
     residual_init_kernel<double><<<nb, 256, 0, ctx->stream>>>(N, f, b.w, b.r, (double*)nullptr);
     SKTT_LAUNCH_CHECK(ctx);
     SKTT_TRY(blas1_dot(ctx, SKTT_F64, N, b.r, b.r, slots + 2));
@@ -588,7 +595,7 @@ static int cg_tiled_refined_host(sktt_ctx* ctx, const KOp& op, const double* f, 
 // The persistent-kernel form of the same solve (fused.cu): one cooperative launch, one host synchronisation.  Returns 0
 // with *finished = false when a CG run hit PERSISTENT_CG_ITERS without converging -- the caller then continues with
 // the host-driven, preconditioned loop from the iterate left in u.
-#define PERSISTENT_CG_ITERS 48
+#define PERSISTENT_CG_ITERS 300
 static int cg_tiled_persistent(sktt_ctx* ctx, const KOp& op, const double* f, double* u, double tol, int max_cycles,
                                double* work, int* iters_host, double* relres_host, int* cycles_host, bool* finished) {
     const CgTiledBufs b = cg_tiled_bufs(op, work);
@@ -599,7 +606,9 @@ static int cg_tiled_persistent(sktt_ctx* ctx, const KOp& op, const double* f, do
     SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (4 * 256 + 128) * sizeof(double)));
     part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
     outd = part + 4 * 256;
-    SKTT_TRY(sktt_fused_pcg_persistent(ctx, o.r, o.R, o.m, o.n, (const double*)o.image, f, u, b.r, b.p, b.s, b.w, b.mvwork,
+    // the matvec never writes the four padding columns of w; they enter r = f - w and every norm, so they must be zero
+    SKTT_CUDA(ctx, cudaMemsetAsync(b.w, 0, (size_t)op.N * sizeof(double), ctx->stream));
+    SKTT_TRY(sktt_fused_pcg_persistent(ctx, fused_rpad(o.r), o.R, o.m, o.n, (const double*)o.image, f, u, b.r, b.p, b.s, b.w, b.mvwork,
                                        tol, PERSISTENT_CG_ITERS, max_cycles, 0, 0, part, outd));
     SKTT_CUDA(ctx, cudaMemcpyAsync(mbox + 40, outd, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SKTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -819,9 +828,9 @@ static int krylov_dispatch(sktt_ctx* ctx, int dtype, const sktt_local_op* op_in,
     if (k.op.image && k.op.sites == 1 && dtype == SKTT_F64) {
         // iterate on tiled-layout vectors: convert the right-hand side and the initial guess, convert the result back
         k.tiled = true;
-        k.N = sktt_fused_tiled_len(k.op.r, k.op.n);
-        SKTT_TRY(sktt_fused_to_tiled(ctx, k.op.r, k.op.n, (const double*)f, (double*)ft));
-        SKTT_TRY(sktt_fused_to_tiled(ctx, k.op.r, k.op.n, (const double*)u, (double*)ut));
+        k.N = sktt_fused_tiled_len(fused_rpad(k.op.r), k.op.n);
+        SKTT_TRY(sktt_fused_to_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, (const double*)f, (double*)ft, 0, k.op.r, k.op.r3));
+        SKTT_TRY(sktt_fused_to_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, (const double*)u, (double*)ut, 0, k.op.r, k.op.r3));
     }
     const T* fs = k.tiled ? ft : f;
     T* us = k.tiled ? ut : u;
@@ -832,7 +841,7 @@ static int krylov_dispatch(sktt_ctx* ctx, int dtype, const sktt_local_op* op_in,
         st = method == 0 ? cg_impl<T>(ctx, dtype, k, fs, us, tol, max_iters, work, iters_host, relres_host)
                          : gmres_impl<T>(ctx, dtype, k, restart, fs, us, tol, max_iters, work, iters_host, relres_host);
     if (k.tiled) {
-        int st2 = sktt_fused_from_tiled(ctx, k.op.r, k.op.n, (const double*)us, (double*)u);
+        int st2 = sktt_fused_from_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, (const double*)us, (double*)u, k.op.r, k.op.r3);
         if (st == 0) st = st2;
     }
     return st;
@@ -872,10 +881,10 @@ extern "C" int sktt_krylov_solve_refined(sktt_ctx* ctx, int dtype, const sktt_lo
     if (!k.op.image) SKTT_TRY(sktt_local_op_prepare(ctx, dtype, &k.op, (void*)image));
     if (!k.op.image) return sktt_fail(ctx, SKTT_ERR_ARG, "krylov_solve_refined: unsupported operator");
     k.tiled = true;
-    k.N = sktt_fused_tiled_len(k.op.r, k.op.n);
-    SKTT_TRY(sktt_fused_to_tiled(ctx, k.op.r, k.op.n, (const double*)f, ft));
-    SKTT_TRY(sktt_fused_to_tiled(ctx, k.op.r, k.op.n, (const double*)u, ut));
+    k.N = sktt_fused_tiled_len(fused_rpad(k.op.r), k.op.n);
+    SKTT_TRY(sktt_fused_to_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, (const double*)f, ft, 0, k.op.r, k.op.r3));
+    SKTT_TRY(sktt_fused_to_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, (const double*)u, ut, 0, k.op.r, k.op.r3));
     int st = cg_tiled_refined(ctx, k, ft, ut, tol, max_iters, max_cycles, w, iters_host, relres_host, cycles_host);
-    int st2 = sktt_fused_from_tiled(ctx, k.op.r, k.op.n, ut, (double*)u);
+    int st2 = sktt_fused_from_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, ut, (double*)u, k.op.r, k.op.r3);
     return st ? st : st2;
 }

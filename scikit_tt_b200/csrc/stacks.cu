@@ -21,14 +21,24 @@ int sktt_fused_matvec_tiled(sktt_ctx* ctx, long long r, long long R, long long m
 static inline Idx2 two(long long d, long long s_hi, long long s_lo) { return mk_idx(d, s_hi, s_lo); }
 
 int sktt_fused_prepare_ex(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* Lst,
-                          const double* A, const double* Rst, double* image, int swap);
-int sktt_fused_to_tiled_ex(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst, int swap);
+                          const double* A, const double* Rst, double* image, int swap, long long r_act, long long r2_act,
+                          long long R2_act);
+int sktt_fused_to_tiled_ex(sktt_ctx* ctx, long long r, long long n, const double* src, double* dst, int swap,
+                           long long r_act, long long c_act);
+int sktt_fused_matvec_ex(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
+                         const double* v, double* y, double* work, long long r_act, long long r2_act);
 int sktt_fused_stack_update(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
                             const double* xt, double* out, double* T1p, double* part);
 
 // scratch of the persistent stack-update kernel for an input side (rin, Rin): T1 (padded) | tiled core | tile partials
 static int64_t fused_stack_need(int64_t rin, int64_t Rin, int64_t m, int64_t n) {
-    return Rin * rin * n * 68 + n * rin * 68 + rin * ((m + 31) / 32) * 12288;
+    const int64_t rp = fused_rpad(rin);
+    return Rin * rp * n * 68 + n * rp * 68 + rp * ((m + 31) / 32) * 12288;
+}
+// scratch of the fused matvec on natural-layout vectors: T1 (padded) | two tiled vectors
+static int64_t fused_matvec_need(int64_t r, int64_t R, int64_t n) {
+    const int64_t rp = fused_rpad(r);
+    return R * rp * n * 68 + 2 * n * rp * 68;
 }
 
 extern "C" int64_t sktt_stack_op_work(int64_t r, int64_t R, int64_t m, int64_t n, int64_t r2, int64_t R2) {
@@ -36,6 +46,7 @@ extern "C" int64_t sktt_stack_op_work(int64_t r, int64_t R, int64_t m, int64_t n
     int64_t need = t1 + t2;
     if (r2 == 64 && R2 == 3 && fused_stack_need(r, R, m, n) > need) need = fused_stack_need(r, R, m, n);
     if (r == 64 && R == 3 && fused_stack_need(r2, R2, m, n) > need) need = fused_stack_need(r2, R2, m, n);
+    if (r2 <= 64 && R2 <= 3 && fused_matvec_need(r, R, n) > need) need = fused_matvec_need(r, R, n);
     return need;
 }
 
@@ -43,15 +54,17 @@ extern "C" int64_t sktt_stack_op_work(int64_t r, int64_t R, int64_t m, int64_t n
 // left-stack update of the mirrored cores.  (rin, Rin): ranks on the side of the OLD stack.
 static int fused_stack(sktt_ctx* ctx, long long rin, long long Rin, long long m, long long n, const void* stack,
                        const void* x, const void* A, void* out, void* work, int mirror) {
-    const size_t img_bytes = (size_t)sktt_fused_image_elems(rin, Rin, m, n) * sizeof(double);
+    const long long rp = fused_rpad(rin);                    // the output side is exactly (64, 3) here
+    const size_t img_bytes = (size_t)sktt_fused_image_elems(rp, Rin, m, n) * sizeof(double);
     SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + img_bytes));
     double* image = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
     double* T1p = (double*)work;
-    double* xt = T1p + Rin * rin * n * 68;
-    double* part = xt + n * rin * 68;
-    SKTT_TRY(sktt_fused_prepare_ex(ctx, rin, Rin, m, n, (const double*)stack, (const double*)A, nullptr, image, mirror));
-    SKTT_TRY(sktt_fused_to_tiled_ex(ctx, rin, n, (const double*)x, xt, mirror));
-    return sktt_fused_stack_update(ctx, rin, Rin, m, n, image, xt, (double*)out, T1p, part);
+    double* xt = T1p + Rin * rp * n * 68;
+    double* part = xt + n * rp * 68;
+    SKTT_TRY(sktt_fused_prepare_ex(ctx, rp, Rin, m, n, (const double*)stack, (const double*)A, nullptr, image, mirror, rin, 64,
+                                   3));
+    SKTT_TRY(sktt_fused_to_tiled_ex(ctx, rp, n, (const double*)x, xt, mirror, rin, 64));
+    return sktt_fused_stack_update(ctx, rp, Rin, m, n, image, xt, (double*)out, T1p, part);
 }
 
 // T1[(b,c),(n,a2)] = sum_a L[a,(b,c)] X[a,(n,a2)]            (first tensordot of sle.py:217)
@@ -82,7 +95,8 @@ extern "C" int sktt_stack_left_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t R
     char* T1 = (char*)work;
     char* T2 = T1 + (size_t)(R * r * n * r2) * es;
     const int conj_col = (conj_mode == SKTT_CONJ_COL), conj_row = !conj_col;
-    if (!(ctx->debug & 32) && sktt_fused_supported(ctx, dtype, r, R, m, n, r2, R2))   // real: conjugation is the identity
+    if (!(ctx->debug & 32) && r2 == 64 && R2 == 3 &&
+        sktt_fused_supported(ctx, dtype, r, R, m, n, r2, R2))              // real: conjugation is the identity
         return fused_stack(ctx, r, R, m, n, Lst, x, A, out, work, 0);
     SKTT_TRY(left_step1(ctx, dtype, r, R, n * r2, Lst, x, conj_col, T1));
     SKTT_TRY(left_step2(ctx, dtype, r, R, m, n, r2, R2, T1, A, T2));
@@ -99,7 +113,7 @@ extern "C" int sktt_stack_right_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t 
     SKTT_TRY(check_dtype(ctx, dtype));
     if (m != n) return sktt_fail(ctx, SKTT_ERR_ARG, "stack_right_op: row and column mode sizes must agree");
     size_t es = dtype_size(dtype);
-    if (!(ctx->debug & 32) && sktt_fused_supported(ctx, dtype, r2, R2, m, n, r, R))
+    if (!(ctx->debug & 32) && r == 64 && R == 3 && sktt_fused_supported(ctx, dtype, r2, R2, m, n, r, R))
         return fused_stack(ctx, r2, R2, m, n, Rst, x, A, out, work, 1);
     char* U1 = (char*)work;                                  // [c, m, a2, b2]
     char* U2 = U1 + (size_t)(r * m * r2 * R2) * es;          // [n, a2, b, c]
@@ -195,11 +209,13 @@ extern "C" int sktt_micro_matvec_als(sktt_ctx* ctx, int dtype, int64_t r, int64_
     char* T2 = T1 + (size_t)(R * r * n * r2) * es;
     if (sktt_fused_supported(ctx, dtype, r, R, m, n, r2, R2)) {
         // stateless call: build the tile images in context scratch, then the two TMA-staged kernels (fused.cu)
-        const size_t img_bytes = (size_t)sktt_fused_image_elems(r, R, m, n) * sizeof(double);
+        const long long rp = fused_rpad(r);
+        const size_t img_bytes = (size_t)sktt_fused_image_elems(rp, R, m, n) * sizeof(double);
         SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + img_bytes));
         double* image = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
-        SKTT_TRY(sktt_fused_prepare(ctx, r, R, m, n, (const double*)Lst, (const double*)A, (const double*)Rst, image));
-        return sktt_fused_matvec(ctx, r, R, m, n, image, (const double*)v, (double*)y, (double*)work);
+        SKTT_TRY(sktt_fused_prepare_ex(ctx, rp, R, m, n, (const double*)Lst, (const double*)A, (const double*)Rst, image, 0, r,
+                                       r2, R2));
+        return sktt_fused_matvec_ex(ctx, rp, R, m, n, image, (const double*)v, (double*)y, (double*)work, r, r2);
     }
     SKTT_TRY(left_step1(ctx, dtype, r, R, n * r2, Lst, v, 0, T1));
     SKTT_TRY(left_step2(ctx, dtype, r, R, m, n, r2, R2, T1, A, T2));
@@ -370,7 +386,7 @@ extern "C" int64_t sktt_local_op_image_size(sktt_ctx* ctx, int dtype, const sktt
     if (!ctx || !op) return -1;
     if (op->sites != 1) return 0;
     if (!sktt_fused_supported(ctx, dtype, op->r, op->R, op->m, op->n, op->r3, op->R2)) return 0;
-    return sktt_fused_image_elems(op->r, op->R, op->m, op->n);
+    return sktt_fused_image_elems(fused_rpad(op->r), op->R, op->m, op->n);
 }
 
 extern "C" int sktt_local_op_prepare(sktt_ctx* ctx, int dtype, sktt_local_op* op, void* image) {
@@ -379,8 +395,8 @@ extern "C" int sktt_local_op_prepare(sktt_ctx* ctx, int dtype, sktt_local_op* op
     op->image = nullptr;
     if (sktt_local_op_image_size(ctx, dtype, op) <= 0) return 0;      // nothing to prepare for this shape
     if (!image) return sktt_fail(ctx, SKTT_ERR_ARG, "local_op_prepare: image buffer is null");
-    SKTT_TRY(sktt_fused_prepare(ctx, op->r, op->R, op->m, op->n, (const double*)op->Lst, (const double*)op->A1,
-                                (const double*)op->Rst, (double*)image));
+    SKTT_TRY(sktt_fused_prepare_ex(ctx, fused_rpad(op->r), op->R, op->m, op->n, (const double*)op->Lst,
+                                   (const double*)op->A1, (const double*)op->Rst, (double*)image, 0, op->r, op->r3, op->R2));
     op->image = image;
     return 0;
 }
@@ -390,8 +406,8 @@ extern "C" int sktt_local_matvec(sktt_ctx* ctx, int dtype, const sktt_local_op* 
     SKTT_TRY(check_dtype(ctx, dtype));
     if (op->sites == 1) {
         if (op->image && sktt_fused_supported(ctx, dtype, op->r, op->R, op->m, op->n, op->r3, op->R2))
-            return sktt_fused_matvec(ctx, op->r, op->R, op->m, op->n, (const double*)op->image, (const double*)v,
-                                     (double*)y, (double*)work);
+            return sktt_fused_matvec_ex(ctx, fused_rpad(op->r), op->R, op->m, op->n, (const double*)op->image,
+                                        (const double*)v, (double*)y, (double*)work, op->r, op->r3);
         return sktt_micro_matvec_als(ctx, dtype, op->r, op->R, op->m, op->n, op->r3, op->R2, op->Lst, op->A1, op->Rst, v,
                                      y, work);
     }
@@ -405,7 +421,7 @@ extern "C" int64_t sktt_local_op_tiled_len(sktt_ctx* ctx, int dtype, const sktt_
     if (!ctx || !op) return -1;
     if (op->sites != 1 || !op->image) return 0;
     if (!sktt_fused_supported(ctx, dtype, op->r, op->R, op->m, op->n, op->r3, op->R2)) return 0;
-    return sktt_fused_tiled_len(op->r, op->n);
+    return sktt_fused_tiled_len(fused_rpad(op->r), op->n);
 }
 
 extern "C" int sktt_local_matvec_tiled(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* vt, void* yt,
@@ -413,7 +429,7 @@ extern "C" int sktt_local_matvec_tiled(sktt_ctx* ctx, int dtype, const sktt_loca
     if (!ctx || !op || !vt || !yt || !work) return SKTT_ERR_ARG;
     if (sktt_local_op_tiled_len(ctx, dtype, op) <= 0)
         return sktt_fail(ctx, SKTT_ERR_ARG, "local_matvec_tiled: operator is not prepared for the tiled path");
-    return sktt_fused_matvec_tiled(ctx, op->r, op->R, op->m, op->n, (const double*)op->image, (const double*)vt,
+    return sktt_fused_matvec_tiled(ctx, fused_rpad(op->r), op->R, op->m, op->n, (const double*)op->image, (const double*)vt,
                                    (double*)yt, (double*)work);
 }
 
@@ -431,7 +447,7 @@ extern "C" int sktt_local_matvec_tiled_repeat(sktt_ctx* ctx, int dtype, const sk
         return sktt_fail(ctx, SKTT_ERR_ARG, "local_matvec_tiled_repeat: operator is not prepared for the tiled path");
     SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (4 * 256 + 128) * sizeof(double)));
     double* part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
-    return sktt_fused_pcg_persistent(ctx, op->r, op->R, op->m, op->n, (const double*)op->image, (const double*)vt, nullptr,
+    return sktt_fused_pcg_persistent(ctx, fused_rpad(op->r), op->R, op->m, op->n, (const double*)op->image, (const double*)vt, nullptr,
                                      nullptr, nullptr, nullptr, (double*)yt, (double*)work, 0.0, 0, 0, 1, reps, part,
                                      part + 4 * 256);
 }

@@ -27,7 +27,10 @@ def wrap(name):
         torch.cuda.synchronize()
         info = dict(fn=name, ms=round((time.perf_counter() - t) * 1e3, 3), launches=dev.launches() - l0)
         if name in ('krylov_solve', 'krylov_solve_refined'):
-            info.update(N=a[1].numel(), iters=out[1], relres=out[2], status=out[0])
+            info.update(N=a[1].numel(), iters=out[1], relres=out[2], status=out[0], cycles=(out[3] if len(out) > 3 else None))
+            if name == 'krylov_solve_refined':
+                import ctypes
+                info['persistent_out'] = [float(v) for v in dev.scratch_peek(65536 + 4 * 256 * 8, 4, ctype=ctypes.c_double)]
         rec.append(info)
         return out
     setattr(dev, name, g)
