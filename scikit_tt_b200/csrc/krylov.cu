@@ -509,6 +509,7 @@ static int cg_tiled_residual(sktt_ctx* ctx, const KOp& op, const CgTiledBufs& b,
     double* mbox = (double*)ctx->mailbox;
     const int nb = ew_blocks(ctx, N);
     if (fnorm2) SKTT_TRY(blas1_dot(ctx, SKTT_F64, N, f, f, slots + 5));
+    SKTT_CUDA(ctx, cudaMemsetAsync(b.w, 0, (size_t)N * sizeof(double), ctx->stream));   // padding columns are never written
     SKTT_TRY(sktt_fused_matvec_tiled(ctx, fused_rpad(o.r), o.R, o.m, o.n, (const double*)o.image, u, b.w, b.mvwork));
     residual_init_kernel<double><<<nb, 256, 0, ctx->stream>>>(N, f, b.w, b.r, (double*)nullptr);
     SKTT_LAUNCH_CHECK(ctx);
