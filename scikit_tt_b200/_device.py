@@ -96,6 +96,58 @@ class Device:
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    # -- bulk transfers through one pinned staging buffer (one DMA per direction instead of one pageable copy per core)
+    def _pinned(self, nbytes):
+        buf = getattr(self, "_pin", None)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8).pin_memory()
+            self._pin = buf
+        return buf
+
+    def upload_many(self, arrays, dtype):
+        """List of numpy arrays -> list of contiguous device tensors of `dtype` (float64 / complex128)."""
+        npdt = np.complex128 if dtype == torch.complex128 else np.float64
+        item = np.dtype(npdt).itemsize
+        sizes = [int(np.prod(a.shape)) for a in arrays]
+        total = sum(sizes)
+        if total == 0:
+            return [self.empty(a.shape, dtype) for a in arrays]
+        self.sync()                                            # the staging buffer may still feed an earlier copy
+        host = self._pinned(total * item)[: total * item].view(dtype)
+        hnp = host.numpy()
+        off = 0
+        for a, n in zip(arrays, sizes):
+            np.copyto(hnp[off:off + n].reshape(a.shape), a, casting="same_kind")
+            off += n
+        devbuf = torch.empty(total, dtype=dtype, device=self.device)
+        devbuf.copy_(host, non_blocking=True)
+        out, off = [], 0
+        for a, n in zip(arrays, sizes):
+            out.append(devbuf[off:off + n].view(a.shape))
+            off += n
+        return out
+
+    def download_many(self, tensors):
+        """List of device tensors (one dtype) -> list of fresh numpy arrays, one synchronisation."""
+        if not tensors:
+            return []
+        dtype = tensors[0].dtype
+        item = tensors[0].element_size()
+        sizes = [t.numel() for t in tensors]
+        total = sum(sizes)
+        host = self._pinned(total * item)[: total * item].view(dtype)
+        off = 0
+        for t, n in zip(tensors, sizes):
+            host[off:off + n].copy_(t.contiguous().reshape(-1), non_blocking=True)
+            off += n
+        self.sync()
+        hnp = host.numpy()
+        out, off = [], 0
+        for t, n in zip(tensors, sizes):
+            out.append(hnp[off:off + n].reshape(tuple(t.shape)).copy())
+            off += n
+        return out
+
     # ------------------------------------------------------------------ stacks
     def stack_left_op(self, Lst, x, A, conj_mode=CONJ_ROW):
         r, n, r2 = x.shape

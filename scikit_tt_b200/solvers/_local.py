@@ -56,10 +56,7 @@ class Uploaded:
     """Device copies of the cores of a TT: operators as [R, m, n, R2], vectors as [r, n, r2]."""
 
     def __init__(self, dev, tt, dtype, vector):
-        self.cores = []
-        for c in tt.cores:
-            t = dev.to_device(c[:, :, 0, :] if vector else c, dtype)
-            self.cores.append(t)
+        self.cores = dev.upload_many([c[:, :, 0, :] if vector else c for c in tt.cores], dtype)
 
     def __getitem__(self, i):
         return self.cores[i]
@@ -175,8 +172,7 @@ def solve_micro(dev, solver, dense_builder, op, f, guess, cache=None):
 
 def download_vector_cores(cores):
     """[r, n, r2] device tensors -> list of host [r, n, 1, r2] numpy cores."""
-    out = []
-    for c in cores:
-        h = c.detach().cpu().numpy()
-        out.append(np.ascontiguousarray(h.reshape(h.shape[0], h.shape[1], 1, h.shape[2])))
-    return out
+    if not cores:
+        return []
+    dev = _device.get_device()
+    return [h.reshape(h.shape[0], h.shape[1], 1, h.shape[2]) for h in dev.download_many([c.detach() for c in cores])]
