@@ -221,7 +221,8 @@ def run_ours(args, cfg):
     clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end through the public API (host TT in, host TT out)
-    step_e2e()
+    for _ in range(2):                                        # untimed: page-locked result blocks enter torch's host cache
+        step_e2e()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
@@ -353,7 +354,7 @@ def main():
     ap.add_argument("--rank", type=int, default=64)
     ap.add_argument("--solver", default="solve")
     ap.add_argument("--sample-rank", type=int, default=4, dest="sample_rank")
-    ap.add_argument("--e2e-steps", type=int, default=1, dest="e2e_steps")
+    ap.add_argument("--e2e-steps", type=int, default=3, dest="e2e_steps")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
     args = ap.parse_args()
     cfg = {"d": args.d, "n": args.n, "r": args.rank, "gpus": args.gpus}

@@ -96,7 +96,11 @@ class Device:
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
-    # -- bulk transfers through one pinned staging buffer (one DMA per direction instead of one pageable copy per core)
+    # -- bulk transfers: DMA straight from / into page-locked host memory.  Inputs that already live in page-locked
+    #    memory (e.g. the cores a previous solver call returned) are copied from where they are; pageable inputs are
+    #    staged through one reusable pinned buffer by a few host threads (numpy releases the GIL inside copyto).
+    PIN_RESULT_MIN_BYTES = 1 << 20
+
     def _pinned(self, nbytes):
         buf = getattr(self, "_pin", None)
         if buf is None or buf.numel() < nbytes:
@@ -104,49 +108,89 @@ class Device:
             self._pin = buf
         return buf
 
+    def _pool(self):
+        pool = getattr(self, "_threads", None)
+        if pool is None:
+            import os
+            from concurrent.futures import ThreadPoolExecutor
+            pool = self._threads = ThreadPoolExecutor(max_workers=max(1, min(8, len(os.sched_getaffinity(0)))))
+        return pool
+
+    @staticmethod
+    def _page_locked(a, npdt):
+        """numpy array that can be handed to the DMA engine as it is: right dtype, contiguous, in page-locked memory."""
+        if a.dtype != npdt or not a.flags.c_contiguous or a.size == 0 or not a.flags.writeable:
+            return None
+        t = torch.from_numpy(a.reshape(-1))
+        return t if t.is_pinned() else None
+
     def upload_many(self, arrays, dtype):
         """List of numpy arrays -> list of contiguous device tensors of `dtype` (float64 / complex128)."""
         npdt = np.complex128 if dtype == torch.complex128 else np.float64
         item = np.dtype(npdt).itemsize
-        sizes = [int(np.prod(a.shape)) for a in arrays]
+        arrays = [np.asarray(a) for a in arrays]
+        sizes = [int(a.size) for a in arrays]
         total = sum(sizes)
         if total == 0:
             return [self.empty(a.shape, dtype) for a in arrays]
-        self.sync()                                            # the staging buffer may still feed an earlier copy
-        host = self._pinned(total * item)[: total * item].view(dtype)
-        hnp = host.numpy()
-        off = 0
-        for a, n in zip(arrays, sizes):
-            np.copyto(hnp[off:off + n].reshape(a.shape), a, casting="same_kind")
-            off += n
         devbuf = torch.empty(total, dtype=dtype, device=self.device)
-        devbuf.copy_(host, non_blocking=True)
-        out, off = [], 0
-        for a, n in zip(arrays, sizes):
-            out.append(devbuf[off:off + n].view(a.shape))
-            off += n
-        return out
+        offs = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+        direct = [self._page_locked(a, npdt) if n * item >= 65536 else None for a, n in zip(arrays, sizes)]
+        staged = [k for k, (t, n) in enumerate(zip(direct, sizes)) if t is None and n > 0]
+        for k, t in enumerate(direct):
+            if t is not None:
+                devbuf[offs[k]:offs[k + 1]].copy_(t if dtype == t.dtype else t.view(dtype), non_blocking=True)
+        if staged:
+            nst = sum(sizes[k] for k in staged)
+            self.sync()                                        # the staging buffer may still feed an earlier copy
+            host = self._pinned(nst * item)[: nst * item].view(dtype)
+            hnp = host.numpy()
+            soff, pos = {}, 0
+            for k in staged:
+                soff[k] = pos
+                pos += sizes[k]
+
+            def stage(k):
+                np.copyto(hnp[soff[k]:soff[k] + sizes[k]].reshape(arrays[k].shape), arrays[k], casting="same_kind")
+            if nst * item >= (4 << 20) and len(staged) > 1:
+                list(self._pool().map(stage, staged))
+            else:
+                for k in staged:
+                    stage(k)
+            for k in staged:
+                devbuf[offs[k]:offs[k + 1]].copy_(host[soff[k]:soff[k] + sizes[k]], non_blocking=True)
+        return [devbuf[offs[k]:offs[k + 1]].view(arrays[k].shape) for k in range(len(arrays))]
 
     def download_many(self, tensors):
-        """List of device tensors (one dtype) -> list of fresh numpy arrays, one synchronisation."""
+        """List of device tensors (one dtype) -> list of numpy arrays, one synchronisation.  Results of at least
+        PIN_RESULT_MIN_BYTES are views of ONE page-locked block from torch's caching host allocator (no second host
+        copy, no page faults; the block returns to the allocator when the last view dies), so they can be fed back
+        to the next solver call without staging.  Smaller results are ordinary numpy arrays."""
         if not tensors:
             return []
         dtype = tensors[0].dtype
         item = tensors[0].element_size()
         sizes = [t.numel() for t in tensors]
         total = sum(sizes)
-        host = self._pinned(total * item)[: total * item].view(dtype)
+        big = total * item >= self.PIN_RESULT_MIN_BYTES
+        host = torch.empty(max(total, 1), dtype=dtype, pin_memory=True) if big else \
+            self._pinned(max(total, 1) * item)[: max(total, 1) * item].view(dtype)
         off = 0
         for t, n in zip(tensors, sizes):
-            host[off:off + n].copy_(t.contiguous().reshape(-1), non_blocking=True)
+            if n:
+                host[off:off + n].copy_(t.contiguous().reshape(-1), non_blocking=True)
             off += n
         self.sync()
         hnp = host.numpy()
         out, off = [], 0
         for t, n in zip(tensors, sizes):
-            out.append(hnp[off:off + n].reshape(tuple(t.shape)).copy())
+            v = hnp[off:off + n].reshape(tuple(t.shape))
+            out.append(v if big else v.copy())
             off += n
         return out
+
+    def download(self, t):
+        return self.download_many([t])[0]
 
     # ------------------------------------------------------------------ stacks
     def stack_left_op(self, Lst, x, A, conj_mode=CONJ_ROW):

@@ -260,7 +260,7 @@ class TT(object):
 
 
 def _to_host(t):
-    return t.detach().cpu().numpy()
+    return _device.get_device().download(t.detach())
 
 
 def _tt_svd(x, threshold, max_rank):

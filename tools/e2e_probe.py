@@ -20,3 +20,7 @@ ms_run, _ = t(lambda: (st.reset(list(sle._State(op, x0, rhs).x)), sle._run_als(s
 ms_res, sol = t(lambda: st.result())
 ms_all, _ = t(lambda: sle.als(op, x0, rhs, repeats=1), n=3)
 print(f"upload (_State) {ms_state:.1f} ms, upload+sweep {ms_run:.1f} ms, download (result) {ms_res:.1f} ms, sle.als total {ms_all:.1f} ms")
+x0p = TT([np.array(c) for c in x0.cores])            # pageable copy of the same guess
+ms_pageable, _ = t(lambda: sle.als(op, x0p, rhs, repeats=1), n=3)
+print(f"pinned-guess sle.als {ms_all:.1f} ms, pageable-guess sle.als {ms_pageable:.1f} ms; guess core pinned: "
+      f"{torch.from_numpy(x0.cores[5].reshape(-1)).is_pinned()}, result core pinned: {torch.from_numpy(sol.cores[5].reshape(-1)).is_pinned()}")
