@@ -228,6 +228,12 @@ int sktt_krylov_solve(sktt_ctx* ctx, int dtype, const sktt_local_op* op, int met
 int sktt_krylov_solve_refined(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* f, void* u,
                               double tol, int max_iters, int max_cycles, void* work, int* iters_host,
                               double* relres_host, int* cycles_host);
+/* Deferred form of the same solve: one cooperative launch, NO host synchronisation.  result_dev (device memory, 4
+ * doubles) receives {iterations, true relative residual, cycles, status: 0 ok / 1 iteration limit / 2 breakdown};
+ * the caller queues the rest of the sweep (sle.py:65-90) behind it and inspects the outcomes once.  SKTT_ERR_ARG
+ * when the operator is not covered by the persistent kernel (use sktt_krylov_solve_refined then).                    */
+int sktt_krylov_solve_refined_async(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* f, void* u,
+                                    double tol, int max_cycles, void* work, double* result_dev);
 
 /* ------------------------------------------------------------------ orthonormalisation -------
  * scipy.linalg.qr(mode='economic') in sle.__update_core_als (scikit_tt/solvers/sle.py:517-525):

@@ -416,6 +416,18 @@ class Device:
                                                 C.byref(cycles))
         return st, iters.value, relres.value, cycles.value
 
+    def krylov_solve_refined_async(self, op, f, u, result, tol=1e-14, max_cycles=5):
+        """Deferred form of krylov_solve_refined: queued without a host synchronisation; `result` (device, 4 doubles)
+        receives (iterations, true relres, cycles, status).  Returns False when the operator is not covered."""
+        nwork = self.lib.sktt_krylov_work(C.byref(op), 0, 0)
+        w = self.work(nwork, f.dtype, tag="krylov")
+        st = self.lib.sktt_krylov_solve_refined_async(self.h, dtype_code(f), C.byref(op), _ptr(f), _ptr(u), float(tol),
+                                                      int(max_cycles), _ptr(w), _ptr(result))
+        if st == -1:                                           # SKTT_ERR_ARG: operator not covered by the persistent kernel
+            return False
+        self._check(st)
+        return True
+
     # ------------------------------------------------------------------ orthonormalisation
     def qr(self, A, want_r=False):
         m, n = A.shape

@@ -598,7 +598,8 @@ static int cg_tiled_refined_host(sktt_ctx* ctx, const KOp& op, const double* f, 
 // the host-driven, preconditioned loop from the iterate left in u.
 #define PERSISTENT_CG_ITERS 300
 static int cg_tiled_persistent(sktt_ctx* ctx, const KOp& op, const double* f, double* u, double tol, int max_cycles,
-                               double* work, int* iters_host, double* relres_host, int* cycles_host, bool* finished) {
+                               double* work, int* iters_host, double* relres_host, int* cycles_host, bool* finished,
+                               double* result_dev = nullptr) {
     const CgTiledBufs b = cg_tiled_bufs(op, work);
     const sktt_local_op& o = op.op;
     double* part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
@@ -609,6 +610,10 @@ static int cg_tiled_persistent(sktt_ctx* ctx, const KOp& op, const double* f, do
     outd = part + 4 * 256;
     // the matvec never writes the four padding columns of w; they enter r = f - w and every norm, so they must be zero
     SKTT_CUDA(ctx, cudaMemsetAsync(b.w, 0, (size_t)op.N * sizeof(double), ctx->stream));
+    if (result_dev) {                                          // deferred form: the outcome stays on the device
+        return sktt_fused_pcg_persistent(ctx, fused_rpad(o.r), o.R, o.m, o.n, (const double*)o.image, f, u, b.r, b.p, b.s, b.w,
+                                         b.mvwork, tol, PERSISTENT_CG_ITERS, max_cycles, 0, 0, part, result_dev);
+    }
     SKTT_TRY(sktt_fused_pcg_persistent(ctx, fused_rpad(o.r), o.R, o.m, o.n, (const double*)o.image, f, u, b.r, b.p, b.s, b.w, b.mvwork,
                                        tol, PERSISTENT_CG_ITERS, max_cycles, 0, 0, part, outd));
     SKTT_CUDA(ctx, cudaMemcpyAsync(mbox + 40, outd, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -636,6 +641,37 @@ static int cg_tiled_refined(sktt_ctx* ctx, const KOp& op, const double* f, doubl
         return st;
     }
     return cg_tiled_refined_host(ctx, op, f, u, tol, max_iters, max_cycles, work, iters_host, relres_host, cycles_host);
+}
+
+// Deferred form of sktt_krylov_solve_refined: the same solve as ONE cooperative launch with no host synchronisation.  The
+// outcome {iterations, true relative residual, cycles, status (0 ok, 1 iteration limit, 2 breakdown)} is left in
+// result_dev[0..3] (device memory) for the caller to inspect later -- a sweep queues all its micro steps and looks at the
+// outcomes once, instead of draining the GPU after every solve.  There is no host-driven continuation here: status 1 / 2
+// or a residual above the caller's acceptance level mean "redo this solve synchronously".
+extern "C" int sktt_krylov_solve_refined_async(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* f, void* u,
+                                               double tol, int max_cycles, void* work, double* result_dev) {
+    if (!ctx || !op || !f || !u || !work || !result_dev) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    if (dtype != SKTT_F64 || op->sites != 1 || (ctx->debug & 16) || ctx->sm_count > 256)
+        return sktt_fail(ctx, SKTT_ERR_ARG, "krylov_solve_refined_async: unsupported operator");
+    KOp k;
+    k.op = *op;
+    const int64_t Nb = local_dim_bound(op);
+    int64_t off = local_mv_work(op) + solver_core_work(0, 0, Nb);
+    off += off & 1;
+    double* w = (double*)work;
+    double* ft = w + off;
+    double* ut = ft + Nb + (Nb & 1);
+    double* image = ut + Nb + (Nb & 1) + 16;
+    if (!k.op.image) SKTT_TRY(sktt_local_op_prepare(ctx, dtype, &k.op, (void*)image));
+    if (!k.op.image) return sktt_fail(ctx, SKTT_ERR_ARG, "krylov_solve_refined_async: unsupported operator");
+    k.tiled = true;
+    k.N = sktt_fused_tiled_len(fused_rpad(k.op.r), k.op.n);
+    SKTT_TRY(sktt_fused_to_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, (const double*)f, ft, 0, k.op.r, k.op.r3));
+    SKTT_TRY(sktt_fused_to_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, (const double*)u, ut, 0, k.op.r, k.op.r3));
+    bool finished = false;
+    SKTT_TRY(cg_tiled_persistent(ctx, k, ft, ut, tol, max_cycles, w, nullptr, nullptr, nullptr, &finished, result_dev));
+    return sktt_fused_from_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, ut, (double*)u, k.op.r, k.op.r3);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -424,6 +424,142 @@ __device__ __noinline__ void cq_house_r(T* Y, const int LD, const int K, const i
     __syncthreads();
 }
 
+// Panel form of cq_house_r (same reflectors, same conventions; K <= 32 RPL rows, n <= 64 columns).  The serial chain of
+// the routine above costs three CTA barriers per reflector (2 us each at 128 x 64); here a panel of 8 columns is factored
+// by ONE warp out of registers -- rows spread over the lanes, a single shuffle reduction per reflector delivers the tail
+// norm and every v^H y_c of the panel -- and the 8 reflectors are then applied to the remaining columns by all warps, a
+// warp owning up to 7 columns (each lane RPL rows of them) with one shuffle reduction per reflector for all of its
+// columns at once.  Two CTA barriers per panel instead of 24.  The scaled reflector vectors stay below the diagonal of Y,
+// R in the upper triangle of the first n rows.
+template <typename T, int RPL>
+__device__ __noinline__ void cq_house_r_panel(T* Y, const int LD, const int K, const int n, T* taus) {
+    // requires K >= n (every column gets a reflector); the sketch has at least 2 n rows
+    constexpr int PW = 8, NW = CQ_THREADS / 32, CPW = (64 - PW + NW - 1) / NW;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kk = min(K, n);
+    for (int j0 = 0; j0 < kk; j0 += PW) {
+        const int pw = min(PW, n - j0), nref = min(PW, kk - j0);
+        if (warp == 0) {
+            T a[RPL][PW];
+#pragma unroll
+            for (int q = 0; q < RPL; ++q)
+#pragma unroll
+                for (int c = 0; c < PW; ++c) {
+                    const int i = lane + 32 * q;
+                    a[q][c] = (i < K && c < pw) ? Y[i * LD + j0 + c] : Num<T>::zero();
+                }
+            // the loop body is the same code for every reflector (kept rolled: a serial chain run by one warp lives on a
+            // warm instruction cache): the current column is always a[.][0]; once its reflector is applied it goes
+            // back to shared memory and the panel is shifted left by one column
+#pragma unroll 1
+            for (int jj = 0; jj < nref; ++jj) {
+                const int j = j0 + jj, owner = j & 31, qj = j >> 5;
+                T g[PW], prow[PW];
+#pragma unroll
+                for (int c = 0; c < PW; ++c) {
+                    g[c] = Num<T>::zero();
+                    prow[c] = Num<T>::zero();
+                }
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    const int i = lane + 32 * q;
+                    if (i > j) {
+                        const T cy = Num<T>::conj(a[q][0]);
+#pragma unroll
+                        for (int c = 0; c < PW; ++c) Num<T>::fma(g[c], cy, a[q][c]);
+                    }
+                    if (q == qj) {
+#pragma unroll
+                        for (int c = 0; c < PW; ++c) prow[c] = a[q][c];
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int c = 0; c < PW; ++c) g[c] = Num<T>::add(g[c], shfl_xor_num<T>(g[c], o));
+#pragma unroll
+                for (int c = 0; c < PW; ++c) prow[c] = lane_bcast<T>(prow[c], owner);
+                const double sigma = Num<T>::real(g[0]);
+                const T alpha = prow[0];
+                const double ar = Num<T>::real(alpha), ai = Num<T>::imag(alpha);
+                T tau = Num<T>::zero(), scl = Num<T>::zero();
+                double beta = ar;
+                if (!(sigma == 0.0 && ai == 0.0)) {
+                    const double nrm = sqrt(ar * ar + ai * ai + sigma);
+                    beta = ar >= 0.0 ? -nrm : nrm;
+                    tau = Num<T>::from((beta - ar) / beta, -ai / beta);
+                    scl = Num<T>::div(Num<T>::one(), Num<T>::from(ar - beta, ai));
+                }
+                T w[PW];
+#pragma unroll
+                for (int c = 1; c < PW; ++c)
+                    w[c] = Num<T>::mul(Num<T>::conj(tau), Num<T>::add(prow[c], Num<T>::mul(Num<T>::conj(scl), g[c])));
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    const int i = lane + 32 * q;
+                    if (i >= j) {
+                        const T vi = i == j ? Num<T>::one() : Num<T>::mul(a[q][0], scl);
+#pragma unroll
+                        for (int c = 1; c < PW; ++c) a[q][c] = Num<T>::sub(a[q][c], Num<T>::mul(vi, w[c]));
+                        a[q][0] = i == j ? Num<T>::from(beta, 0.0) : vi;
+                    }
+                    if (i < K) Y[i * LD + j] = a[q][0];
+#pragma unroll
+                    for (int c = 0; c + 1 < PW; ++c) a[q][c] = a[q][c + 1];
+                    a[q][PW - 1] = Num<T>::zero();
+                }
+                if (lane == 0) taus[j] = tau;
+            }
+        }
+        __syncthreads();
+        const int c0 = j0 + PW;
+        if (c0 + warp < n) {
+            T y[CPW][RPL];
+#pragma unroll
+            for (int t = 0; t < CPW; ++t)
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    const int c = c0 + warp + NW * t, i = lane + 32 * q;
+                    y[t][q] = (c < n && i < K) ? Y[i * LD + c] : Num<T>::zero();
+                }
+            for (int jj = 0; jj < nref; ++jj) {
+                const int j = j0 + jj;
+                T v[RPL], dot[CPW];
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    const int i = lane + 32 * q;
+                    v[q] = i == j ? Num<T>::one() : ((i > j && i < K) ? Y[i * LD + j] : Num<T>::zero());
+                }
+#pragma unroll
+                for (int t = 0; t < CPW; ++t) {
+                    dot[t] = Num<T>::zero();
+#pragma unroll
+                    for (int q = 0; q < RPL; ++q) Num<T>::fma(dot[t], Num<T>::conj(v[q]), y[t][q]);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int t = 0; t < CPW; ++t) dot[t] = Num<T>::add(dot[t], shfl_xor_num<T>(dot[t], o));
+                const T ctau = Num<T>::conj(taus[j]);
+#pragma unroll
+                for (int t = 0; t < CPW; ++t) {
+                    const T w = Num<T>::mul(ctau, dot[t]);
+#pragma unroll
+                    for (int q = 0; q < RPL; ++q) y[t][q] = Num<T>::sub(y[t][q], Num<T>::mul(v[q], w));
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < CPW; ++t)
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    const int c = c0 + warp + NW * t, i = lane + 32 * q;
+                    if (c < n && i < K) Y[i * LD + c] = y[t][q];
+                }
+        }
+        __syncthreads();
+    }
+}
+
 __device__ __forceinline__ unsigned cq_hash(unsigned x) {
     x ^= x >> 16;
     x *= 0x7feb352du;
@@ -555,7 +691,9 @@ cholqr_kernel(const T* __restrict__ src, QrView lv, int m, int n, int rows_per_c
         for (int e = tid; e < sketch_k * NN; e += CQ_THREADS) Ys[(e / NN) * LD + e % NN] = ld_cg<T>(ysk + e);
         __syncthreads();
         stamp();
-        cq_house_r<T>(Ys, LD, sketch_k, n, red, wv, wpart);
+        if (sketch_k <= 128 && sketch_k >= n) cq_house_r_panel<T, 4>(Ys, LD, sketch_k, n, wv);
+        else if (!Num<T>::is_complex && sketch_k <= 256 && sketch_k >= n) cq_house_r_panel<double, 8>((double*)Ys, LD, sketch_k, n, (double*)wv);
+        else cq_house_r<T>(Ys, LD, sketch_k, n, red, wv, wpart);
         stamp();
         // R_s -> Gs; diagonals below 1e-15 of the largest are floored and their rows decoupled (numerically null columns)
         double dmax = 0.0;

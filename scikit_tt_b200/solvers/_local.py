@@ -122,6 +122,33 @@ def _krylov_refined(dev, op, f, u, method):
     return relres, total
 
 
+class Deferred:
+    """Outcome slots of micro solves that were queued without a host synchronisation (one row of 4 doubles per solve:
+    iterations, true relative residual, cycles, status)."""
+
+    def __init__(self, dev, capacity):
+        self.slots = torch.zeros((max(int(capacity), 1), 4), dtype=torch.float64, device=dev.device)
+        self.used = 0
+
+    def solve(self, dev, op, f, u):
+        if self.used >= self.slots.shape[0]:
+            return False
+        if not dev.krylov_solve_refined_async(op, f, u, self.slots[self.used], tol=KRYLOV_TOL, max_cycles=KRYLOV_MAX_CYCLES):
+            return False
+        self.used += 1
+        return True
+
+    def check(self):
+        """One synchronisation for the whole sweep: True when every queued solve ended with status 0 and an acceptable
+        true residual."""
+        if self.used == 0:
+            return True
+        out = self.slots[: self.used].cpu().numpy()
+        self.iterations = int(out[:, 0].sum())
+        self.used = 0
+        return bool(np.all(out[:, 3] == 0.0) and np.all(out[:, 1] <= KRYLOV_ACCEPT))
+
+
 def solve_micro(dev, solver, dense_builder, op, f, guess, cache=None):
     """Solve the micro system M u = f.  `dense_builder()` returns the dense matrix (destroyed by the LU),
     `op` is the matrix-free description of the same M, `f` / `guess` have the unknown's tensor shape.
@@ -150,6 +177,12 @@ def solve_micro(dev, solver, dense_builder, op, f, guess, cache=None):
         method = 'cg' if herm else 'gmres'
     if _TRACE:
         print(f"  [micro] N={N} {method}", flush=True)
+    if method == 'cg' and f.dtype == torch.float64 and dev.tiled_len(op) > 0 and cache is not None \
+            and cache.get('defer') is not None and not _TRACE:
+        # deferred outcome: the solve is queued as one cooperative launch and the sweep goes on queueing behind it; the
+        # caller looks at all outcomes once (Deferred.check) and redoes the sweep synchronously if one of them is bad
+        if cache['defer'].solve(dev, op, f, u):
+            return u
     if method == 'cg' and f.dtype == torch.float64 and dev.tiled_len(op) > 0:
         # prepared operator: the whole solve (warm start, CG, true-residual restarts) is one C call
         st, iters, relres, cycles = dev.krylov_solve_refined(op, f, u, tol=KRYLOV_TOL, max_iters=KRYLOV_MAX_ITERS,
