@@ -133,11 +133,149 @@ extern "C" int sktt_stack_right_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t 
     return sktt_gemm_run(ctx, dtype, g3);
 }
 
+// ---------------------------------------------------------------------- small rhs ranks: one kernel per chain --
+// Right-hand sides of the sweeps have tiny TT ranks (1 for the synthetic configurations, 4 in the cascade example): the
+// two-GEMM chains below then move a few megabytes but cost two to four launches of a general GEMM each (40 us per
+// call at the bench shape, 150 calls per sweep).  For p, p2 <= RHS_PMAX each chain is one elementwise / reduction kernel
+// with the summation order of the reference's tensordots (over p first, then over the second index).
+#define RHS_PMAX 4
+#define RHS_COUNTER_OFF (SKTT_SCRATCH_COUNTER_OFF + 1024)
+
+// f[(c,m),c2] = sum_p2 (sum_p bL[p,c] b[p,m,p2]) bR[p2,c2]
+template <typename T>
+__global__ void rhs_micro_small_kernel(int p, int r, int m, int p2, int r2, const T* __restrict__ bL,
+                                       const T* __restrict__ b, const T* __restrict__ bR, T* __restrict__ f) {
+    const long long total = (long long)r * m * r2;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c2 = (int)(idx % r2), mm = (int)((idx / r2) % m), c = (int)(idx / ((long long)r2 * m));
+        T acc = Num<T>::zero();
+        for (int q2 = 0; q2 < p2; ++q2) {
+            T t = Num<T>::zero();
+            for (int q = 0; q < p; ++q) Num<T>::fma(t, bL[q * r + c], b[((long long)q * m + mm) * p2 + q2]);
+            Num<T>::fma(acc, t, bR[q2 * r2 + c2]);
+        }
+        f[idx] = acc;
+    }
+}
+
+// out[p2,c2] = sum_{(c,m)} (sum_p bL[p,c] b[p,m,p2]) conj(x)[(c,m),c2]: CTAs own row chunks, lanes own columns; the CTA
+// partials are summed in CTA order by the CTA that finishes last (deterministic whatever the arrival order).
+template <typename T>
+__global__ void __launch_bounds__(256)
+rhs_left_small_kernel(int p, int r, int m, int p2, int r2, const T* __restrict__ bL, const T* __restrict__ b,
+                      const T* __restrict__ x, T* __restrict__ out, T* part, unsigned* counter) {
+    __shared__ T sh[8][RHS_PMAX][32];
+    __shared__ bool last;
+    const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long K = (long long)r * m, rows_per = (K + G - 1) / G;
+    const long long row0 = cta * rows_per, row1 = row0 + rows_per < K ? row0 + rows_per : K;
+    for (int cb = 0; cb < r2; cb += 32) {
+        const int c2 = cb + lane;
+        T acc[RHS_PMAX];
+#pragma unroll
+        for (int q2 = 0; q2 < RHS_PMAX; ++q2) acc[q2] = Num<T>::zero();
+        for (long long row = row0 + warp; row < row1; row += 8) {
+            const int c = (int)(row / m), mm = (int)(row % m);
+            const T xv = c2 < r2 ? Num<T>::conj(x[row * r2 + c2]) : Num<T>::zero();
+#pragma unroll
+            for (int q2 = 0; q2 < RHS_PMAX; ++q2)
+                if (q2 < p2) {
+                    T t = Num<T>::zero();
+                    for (int q = 0; q < p; ++q) Num<T>::fma(t, bL[q * r + c], b[((long long)q * m + mm) * p2 + q2]);
+                    Num<T>::fma(acc[q2], t, xv);
+                }
+        }
+#pragma unroll
+        for (int q2 = 0; q2 < RHS_PMAX; ++q2) sh[warp][q2][lane] = acc[q2];
+        __syncthreads();
+        if (warp == 0 && c2 < r2)
+            for (int q2 = 0; q2 < p2; ++q2) {
+                T sacc = sh[0][q2][lane];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) sacc = Num<T>::add(sacc, sh[w][q2][lane]);
+                part[((long long)cta * p2 + q2) * r2 + c2] = sacc;
+            }
+        __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last = atomicAdd(counter, 1u) == (unsigned)(G - 1);
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        const int E = p2 * r2;
+        for (int e = tid; e < E; e += 256) {
+            T sacc = Num<T>::zero();
+            for (int g = 0; g < G; ++g) sacc = Num<T>::add(sacc, ld_cg<T>(part + (long long)g * E + e));
+            out[e] = sacc;
+        }
+        if (tid == 0) *counter = 0;
+    }
+}
+
+// out[p,c] = sum_{(m,p2)} b[p,(m,p2)] (sum_c2 conj(x)[(c,m),c2] bR[p2,c2]): one CTA per c (a contiguous row of x)
+template <typename T>
+__global__ void __launch_bounds__(256)
+rhs_right_small_kernel(int p, int r, int m, int p2, int r2, const T* __restrict__ bR, const T* __restrict__ b,
+                       const T* __restrict__ x, T* __restrict__ out) {
+    __shared__ T sh[8][RHS_PMAX];
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long len = (long long)m * r2;
+    const T* xr = x + (long long)c * len;
+    T acc[RHS_PMAX];
+#pragma unroll
+    for (int q = 0; q < RHS_PMAX; ++q) acc[q] = Num<T>::zero();
+    for (long long e = tid; e < len; e += 256) {
+        const int mm = (int)(e / r2), c2 = (int)(e % r2);
+        const T xv = Num<T>::conj(xr[e]);
+        for (int q2 = 0; q2 < p2; ++q2) {
+            const T sv = Num<T>::mul(xv, bR[q2 * r2 + c2]);
+#pragma unroll
+            for (int q = 0; q < RHS_PMAX; ++q)
+                if (q < p) Num<T>::fma(acc[q], b[((long long)q * m + mm) * p2 + q2], sv);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < RHS_PMAX; ++q) {
+        acc[q] = warp_sum<T>(acc[q]);
+        if (lane == 0) sh[warp][q] = acc[q];
+    }
+    __syncthreads();
+    if (tid < p) {
+        T sacc = sh[0][tid];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) sacc = Num<T>::add(sacc, sh[w][tid]);
+        out[(long long)tid * r + c] = sacc;
+    }
+}
+
+static inline bool rhs_small(const sktt_ctx* ctx, int64_t p, int64_t p2, int64_t r, int64_t m, int64_t r2) {
+    return ctx->gemm_mode != 1 && p >= 1 && p2 >= 1 && p <= RHS_PMAX && p2 <= RHS_PMAX && r * m * r2 < (1LL << 31);
+}
+
 // ---------------------------------------------------------------------------------- rhs stacks --
 extern "C" int sktt_stack_left_rhs(sktt_ctx* ctx, int dtype, int64_t p, int64_t r, int64_t m, int64_t p2, int64_t r2,
                                    const void* bL, const void* b, const void* x, void* out, void* work) {
     if (!ctx) return SKTT_ERR_ARG;
     SKTT_TRY(check_dtype(ctx, dtype));
+    if (rhs_small(ctx, p, p2, r, m, r2)) {
+        const long long K = r * m;
+        int G = (int)((K + 31) / 32);
+        if (G > ctx->sm_count) G = ctx->sm_count;
+        SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (size_t)G * p2 * r2 * dtype_size(dtype)));
+        void* part = (char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF;
+        unsigned* counter = (unsigned*)((char*)ctx->scratch + RHS_COUNTER_OFF);
+        if (dtype == SKTT_F64)
+            rhs_left_small_kernel<double><<<G, 256, 0, ctx->stream>>>((int)p, (int)r, (int)m, (int)p2, (int)r2, (const double*)bL,
+                                                                      (const double*)b, (const double*)x, (double*)out,
+                                                                      (double*)part, counter);
+        else
+            rhs_left_small_kernel<cplx><<<G, 256, 0, ctx->stream>>>((int)p, (int)r, (int)m, (int)p2, (int)r2, (const cplx*)bL,
+                                                                    (const cplx*)b, (const cplx*)x, (cplx*)out, (cplx*)part,
+                                                                    counter);
+        SKTT_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     // Tb[c,(m,p2)] = sum_p bL[p,c] b[p,(m,p2)]                              (sle.py:246)
     GemmDesc g1 = gemm_desc(r, m * p2, p, bL, lin_idx(1), lin_idx(r), b, lin_idx(m * p2), lin_idx(1), work,
                             lin_idx(m * p2), lin_idx(1));
@@ -153,6 +291,18 @@ extern "C" int sktt_stack_right_rhs(sktt_ctx* ctx, int dtype, int64_t p, int64_t
                                     int64_t r2, const void* bR, const void* b, const void* x, void* out, void* work) {
     if (!ctx) return SKTT_ERR_ARG;
     SKTT_TRY(check_dtype(ctx, dtype));
+    if (rhs_small(ctx, p, p2, r, m, r2)) {
+        if (dtype == SKTT_F64)
+            rhs_right_small_kernel<double><<<(int)r, 256, 0, ctx->stream>>>((int)p, (int)r, (int)m, (int)p2, (int)r2,
+                                                                            (const double*)bR, (const double*)b,
+                                                                            (const double*)x, (double*)out);
+        else
+            rhs_right_small_kernel<cplx><<<(int)r, 256, 0, ctx->stream>>>((int)p, (int)r, (int)m, (int)p2, (int)r2,
+                                                                          (const cplx*)bR, (const cplx*)b, (const cplx*)x,
+                                                                          (cplx*)out);
+        SKTT_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     // Tb[(c,m),p2] = sum_c2 conj(x)[(c,m),c2] bR[p2,c2]                     (sle.py:303)
     GemmDesc g1 = gemm_desc(r * m, p2, r2, x, lin_idx(r2), lin_idx(1), bR, lin_idx(1), lin_idx(r2), work,
                             lin_idx(p2), lin_idx(1));
@@ -169,6 +319,21 @@ extern "C" int sktt_micro_rhs_als(sktt_ctx* ctx, int dtype, int64_t p, int64_t r
                                   const void* bL, const void* b, const void* bR, void* f, void* work) {
     if (!ctx) return SKTT_ERR_ARG;
     SKTT_TRY(check_dtype(ctx, dtype));
+    if (rhs_small(ctx, p, p2, r, m, r2)) {
+        const long long total = r * m * r2;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 8LL * ctx->sm_count) blocks = 8LL * ctx->sm_count;
+        if (dtype == SKTT_F64)
+            rhs_micro_small_kernel<double><<<(int)blocks, 256, 0, ctx->stream>>>((int)p, (int)r, (int)m, (int)p2, (int)r2,
+                                                                                 (const double*)bL, (const double*)b,
+                                                                                 (const double*)bR, (double*)f);
+        else
+            rhs_micro_small_kernel<cplx><<<(int)blocks, 256, 0, ctx->stream>>>((int)p, (int)r, (int)m, (int)p2, (int)r2,
+                                                                               (const cplx*)bL, (const cplx*)b,
+                                                                               (const cplx*)bR, (cplx*)f);
+        SKTT_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     // Tb[c,(m,p2)] = sum_p bL[p,c] b[p,(m,p2)]                              (sle.py:424)
     GemmDesc g1 = gemm_desc(r, m * p2, p, bL, lin_idx(1), lin_idx(r), b, lin_idx(m * p2), lin_idx(1), work,
                             lin_idx(m * p2), lin_idx(1));

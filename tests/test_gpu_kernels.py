@@ -79,6 +79,27 @@ STACK_SHAPES = [  # r, R, n, r2, R2
 
 
 @pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("pp", [(1, 1), (4, 4), (1, 4), (5, 6), (2, 7)])
+@pytest.mark.parametrize("shape", [(1, 3, 2), (5, 9, 1), (64, 64, 64), (33, 16, 70)])
+def test_rhs_stacks_small_and_general_rhs_ranks(dev, cplx, pp, shape):
+    """Right-hand-side stacks and micro right-hand sides (sle.py:222-247, :279-305, :393-430): rhs ranks <= 4 run the
+    one-kernel forms, larger ones the two-GEMM chains; both against the einsum restatement, and twice for bit-identity
+    (the left stack sums CTA partials in a fixed order)."""
+    r, n, r2 = shape
+    p, p2 = pp
+    rng = np.random.default_rng(11 + r + 7 * p + 13 * p2 + 101 * cplx)
+    x = rnd(rng, (r, n, r2), cplx)
+    bL, bR, b = rnd(rng, (p, r), cplx), rnd(rng, (p2, r2), cplx), rnd(rng, (p, n, p2), cplx)
+    dx, dbL, dbR, db = map(dev.to_device, (x, bL, bR, b))
+    tol = 2e-13
+    first = host(dev.stack_left_rhs(dbL, db, dx))
+    assert relerr(first, K.stack_left_rhs(bL, b, x)) < tol
+    assert np.array_equal(first, host(dev.stack_left_rhs(dbL, db, dx)))
+    assert relerr(host(dev.stack_right_rhs(dbR, db, dx)), K.stack_right_rhs(bR, b, x)) < tol
+    assert relerr(host(dev.micro_rhs_als(dbL, db, dbR)), K.micro_rhs_als(bL, b, bR)) < tol
+
+
+@pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("shape", STACK_SHAPES)
 def test_stacks_and_micro_systems(dev, cplx, shape):
     r, R, n, r2, R2 = shape
