@@ -101,26 +101,40 @@ _DEFER_MISSES = {}
 
 
 def _sweeps_als(st, repeats, solver, check=None):
-    """`check` (deferred micro solves only) is called at the end of every half sweep; a False ends the pass."""
+    """`check` (deferred micro solves only) is called at the end of every half sweep; a False ends the pass.
+
+    Warm starts of the matrix-free micro solves: the reference throws the triangular factor of every QR / RQ away
+    (sle.py:525, :541) because its direct solver needs no starting point.  Here that factor -- recovered as Q^H u resp.
+    u Q^H -- is pushed into the neighbouring core, which turns the current iterate of the sweep into the starting vector
+    of the next micro system (the same tensor, gauge moved by one core).  The micro systems and their solutions are
+    unchanged; CG merely starts from the sweep's current residual instead of from zero."""
     dev, d, x = st.dev, st.d, st.x
     for i in range(d - 1, -1, -1):                                        # sle.py:54-56
         st.right(i)
+    carry = None                                                          # gauge factor towards the next core to be solved
     for _ in range(repeats):                                              # sle.py:62
         for i in range(d):                                                # first half sweep, sle.py:65-77
             st.left(i)
             if i < d - 1:
-                u, (r, n, r2) = _micro_als(st, i, solver)
+                guess = _pushed(dev, carry, x[i], left=True)
+                u, (r, n, r2) = _micro_als(st, i, solver, guess)
+                u2 = u.reshape(r * n, r2)
                 with _local.phase(dev, 'qr'):
-                    q = dev.qr(u.reshape(r * n, r2))                      # sle.py:517-525
+                    q = dev.qr(u2)                                        # sle.py:517-525
+                    carry = dev.matmul(q, u2, opa='C') if _wants_guess(solver, u2.numel()) else None
                 x[i] = q.reshape(r, n, q.shape[1])
         if check is not None and not check():
             return False
         for i in range(d - 1, -1, -1):                                    # second half sweep, sle.py:80-90
             st.right(i)
-            u, (r, n, r2) = _micro_als(st, i, solver)
+            guess = _pushed(dev, carry, x[i], left=(i == d - 1))
+            u, (r, n, r2) = _micro_als(st, i, solver, guess)
+            carry = None
             if i > 0:
+                u2 = u.reshape(r, n * r2)
                 with _local.phase(dev, 'qr'):
-                    q = dev.rq(u.reshape(r, n * r2))                      # sle.py:533-541
+                    q = dev.rq(u2)                                        # sle.py:533-541
+                    carry = dev.matmul(u2, q, opb='C') if _wants_guess(solver, u2.numel()) else None
                 x[i] = q.reshape(q.shape[0], n, r2)
             else:
                 x[i] = u.reshape(r, n, r2)                                # sle.py:546
@@ -129,14 +143,35 @@ def _sweeps_als(st, repeats, solver, check=None):
     return True
 
 
-def _micro_als(st, i, solver):
+def _wants_guess(solver, N):
+    return solver in ('cg', 'gmres', 'krylov') or (solver in ('solve', 'lu') and N > _local.DENSE_LIMIT)
+
+
+def _pushed(dev, carry, core, left):
+    """Starting vector of the next micro system: the core as it stands with the gauge factor of the neighbour that was
+    just orthonormalised pushed into it (left: factor [k, r] times core [r, n, r2]; else core [r, n, r2] times factor
+    [r2, k]).  None when there is no factor -- the core itself is the starting vector then."""
+    if carry is None or core.dim() != 3:
+        return None
+    r, n, r2 = core.shape
+    if left:
+        if carry.shape[1] != r:
+            return None
+        return dev.matmul(carry, core.reshape(r, n * r2)).reshape(carry.shape[0], n, r2)
+    if carry.shape[0] != r2:
+        return None
+    return dev.matmul(core.reshape(r * n, r2), carry).reshape(r, n, carry.shape[1])
+
+
+def _micro_als(st, i, solver, guess=None):
     dev = st.dev
     L, R, A = st.Lop[i], st.Rop[i], st.A[i]
     with _local.phase(dev, 'micro_rhs'):
         f = dev.micro_rhs_als(st.Lrhs[i], st.b[i], st.Rrhs[i])            # sle.py:424-428
     r, n, r2 = L.shape[0], A.shape[2], R.shape[0]
     op = dev.local_op(L, A, R)
-    guess = st.x[i] if tuple(st.x[i].shape) == (r, n, r2) else None
+    if guess is None or tuple(guess.shape) != (r, n, r2):
+        guess = st.x[i] if tuple(st.x[i].shape) == (r, n, r2) else None
     with _local.phase(dev, 'solve'):
         u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_als(L, A, R), op, f, guess, st.cache)
     return u, (r, n, r2)
