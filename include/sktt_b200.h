@@ -235,6 +235,18 @@ int sktt_krylov_solve_refined(sktt_ctx* ctx, int dtype, const sktt_local_op* op,
 int sktt_krylov_solve_refined_async(sktt_ctx* ctx, int dtype, const sktt_local_op* op, const void* f, void* u,
                                     double tol, int max_cycles, void* work, double* result_dev);
 
+/* ------------------------------------------------------------------ gauge products ------------
+ * The triangular factor of the QR / RQ in sle.__update_core_als is discarded by the reference
+ * (scikit_tt/solvers/sle.py:525, :541); the matrix-free micro solves use it as a warm start (the sweep's current
+ * iterate expressed in the unknowns of the next micro system).  f64, one long index l < L, short extents <= 64, every
+ * operand addressed as base[l * s_long + i * s_short]:
+ *   factor: C(i, j)   = sum_l A(l, i) B(l, j)          (Q^H u, resp. u Q^H)
+ *   push  : out(l, i) = sum_b Rm(i, b) X(l, b)         (R x_next, resp. x_prev R')                                  */
+int sktt_gauge_factor(sktt_ctx* ctx, int dtype, int64_t L, int64_t ni, int64_t nj, const void* A, int64_t sla,
+                      int64_t sia, const void* B, int64_t slb, int64_t sjb, void* C, int64_t sci, int64_t scj);
+int sktt_gauge_push(sktt_ctx* ctx, int dtype, int64_t L, int64_t ni, int64_t nb, const void* Rm, int64_t sri,
+                    int64_t srb, const void* X, int64_t slx, int64_t sbx, void* out, int64_t slo, int64_t sio);
+
 /* ------------------------------------------------------------------ orthonormalisation -------
  * scipy.linalg.qr(mode='economic') in sle.__update_core_als (scikit_tt/solvers/sle.py:517-525):
  * Householder QR of the row-major m x n matrix A; Q (m x min(m,n), row-major) overwrites the

@@ -507,6 +507,40 @@ class Device:
         self.gemm2(M, N, K, A, am, ak, B, bk, bn, out, (big, 0, N), (big, 0, 1), conjA=int(opa == 'C'), conjB=int(opb == 'C'))
         return out
 
+    # ------------------------------------------------------------------ gauge products of the sweep (warm starts)
+    def gauge_factor(self, q, u, tall):
+        """Triangular factor the reference throws away (sle.py:525, :541), recovered from the orthonormal factor:
+        tall: q [L, k], u [L, r2] -> q^H u [k, r2];  else: q [k, L], u [r, L] -> u q^H [r, k]."""
+        if q.dtype != torch.float64 or max(q.shape[1 if tall else 0], u.shape[1 if tall else 0]) > 64:
+            return self.matmul(q, u, opa='C') if tall else self.matmul(u, q, opb='C')
+        if tall:
+            L, k = q.shape
+            r2 = u.shape[1]
+            out = self.empty((k, r2), q.dtype)
+            self._check(self.lib.sktt_gauge_factor(self.h, F64, L, k, r2, _ptr(q), k, 1, _ptr(u), r2, 1, _ptr(out), r2, 1))
+        else:
+            k, L = q.shape
+            r = u.shape[0]
+            out = self.empty((r, k), q.dtype)
+            self._check(self.lib.sktt_gauge_factor(self.h, F64, L, r, k, _ptr(u), 1, L, _ptr(q), 1, L, _ptr(out), k, 1))
+        return out
+
+    def gauge_push(self, carry, core, left):
+        """left: carry [k, r] @ core [r, L] -> [k, L];  else: core [L, r2] @ carry [r2, k] -> [L, k]."""
+        if core.dtype != torch.float64 or carry.dtype != torch.float64 or max(carry.shape) > 64:
+            return self.matmul(carry, core) if left else self.matmul(core, carry)
+        if left:
+            k, r = carry.shape
+            L = core.shape[1]
+            out = self.empty((k, L), core.dtype)
+            self._check(self.lib.sktt_gauge_push(self.h, F64, L, k, r, _ptr(carry), r, 1, _ptr(core), 1, L, _ptr(out), 1, L))
+        else:
+            r2, k = carry.shape
+            L = core.shape[0]
+            out = self.empty((L, k), core.dtype)
+            self._check(self.lib.sktt_gauge_push(self.h, F64, L, k, r2, _ptr(carry), 1, k, _ptr(core), r2, 1, _ptr(out), k, 1))
+        return out
+
     def widen(self, x):
         """float64 -> complex128 copy on the device."""
         if x.dtype == torch.complex128:

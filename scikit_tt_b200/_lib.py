@@ -67,6 +67,8 @@ SIGNATURES = {
     "sktt_krylov_work": (i64, [C.POINTER(LocalOp), i32, i32]),
     "sktt_krylov_solve": (i32, [vp, i32, C.POINTER(LocalOp), i32, i32, vp, vp, dbl, i32, vp, pint, pdbl]),
     "sktt_krylov_solve_refined": (i32, [vp, i32, C.POINTER(LocalOp), vp, vp, dbl, i32, i32, vp, pint, pdbl, pint]),
+    "sktt_gauge_factor": (i32, [vp, i32, i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64]),
+    "sktt_gauge_push": (i32, [vp, i32, i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64]),
     "sktt_krylov_solve_refined_async": (i32, [vp, i32, C.POINTER(LocalOp), vp, vp, dbl, i32, vp, vp]),
     "sktt_qr_work": (i64, [i64, i64]),
     "sktt_qr_left": (i32, [vp, i32, i64, i64, vp, vp, vp, vp]),

@@ -203,11 +203,18 @@ rhs_left_small_kernel(int p, int r, int m, int p2, int r2, const T* __restrict__
     __syncthreads();
     if (last) {
         __threadfence();
-        const int E = p2 * r2;
-        for (int e = tid; e < E; e += 256) {
+        // four threads per entry take every fourth partial (independent loads in flight), combined by two shuffles
+        const int E = p2 * r2, sub = tid & 3;
+        for (int e0 = 0; e0 < E; e0 += 64) {
+            const int e = e0 + (tid >> 2);
             T sacc = Num<T>::zero();
-            for (int g = 0; g < G; ++g) sacc = Num<T>::add(sacc, ld_cg<T>(part + (long long)g * E + e));
-            out[e] = sacc;
+            if (e < E) {
+#pragma unroll 8
+                for (int g = sub; g < G; g += 4) sacc = Num<T>::add(sacc, ld_cg<T>(part + (long long)g * E + e));
+            }
+            sacc = Num<T>::add(sacc, lane_bcast<T>(sacc, (tid & 31) ^ 1));
+            sacc = Num<T>::add(sacc, lane_bcast<T>(sacc, (tid & 31) ^ 2));
+            if (e < E && sub == 0) out[e] = sacc;
         }
         if (tid == 0) *counter = 0;
     }

@@ -121,7 +121,7 @@ def _sweeps_als(st, repeats, solver, check=None):
                 u2 = u.reshape(r * n, r2)
                 with _local.phase(dev, 'qr'):
                     q = dev.qr(u2)                                        # sle.py:517-525
-                    carry = dev.matmul(q, u2, opa='C') if _wants_guess(solver, u2.numel()) else None
+                    carry = dev.gauge_factor(q, u2, tall=True) if _wants_guess(solver, u2.numel()) else None
                 x[i] = q.reshape(r, n, q.shape[1])
         if check is not None and not check():
             return False
@@ -134,7 +134,7 @@ def _sweeps_als(st, repeats, solver, check=None):
                 u2 = u.reshape(r, n * r2)
                 with _local.phase(dev, 'qr'):
                     q = dev.rq(u2)                                        # sle.py:533-541
-                    carry = dev.matmul(u2, q, opb='C') if _wants_guess(solver, u2.numel()) else None
+                    carry = dev.gauge_factor(q, u2, tall=False) if _wants_guess(solver, u2.numel()) else None
                 x[i] = q.reshape(q.shape[0], n, r2)
             else:
                 x[i] = u.reshape(r, n, r2)                                # sle.py:546
@@ -157,10 +157,10 @@ def _pushed(dev, carry, core, left):
     if left:
         if carry.shape[1] != r:
             return None
-        return dev.matmul(carry, core.reshape(r, n * r2)).reshape(carry.shape[0], n, r2)
+        return dev.gauge_push(carry, core.reshape(r, n * r2), left=True).reshape(carry.shape[0], n, r2)
     if carry.shape[0] != r2:
         return None
-    return dev.matmul(core.reshape(r * n, r2), carry).reshape(r, n, carry.shape[1])
+    return dev.gauge_push(carry, core.reshape(r * n, r2), left=False).reshape(r, n, carry.shape[1])
 
 
 def _micro_als(st, i, solver, guess=None):

@@ -511,3 +511,24 @@ def test_c4_full_size_contractions(dev, r):
     assert relerr(host(dev.stack_left_op(dL, dx, dA)), K.stack_left_op(L, x, A)) < 1e-12
     assert relerr(host(dev.stack_right_op(dR, dx, dA)), K.stack_right_op(Rt, x, A)) < 1e-12
     assert relerr(host(dev.micro_matvec_als(dL, dA, dR, dx)), K.micro_matvec_als(L, A, Rt, x)) < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(4096, 64, 64), (4096, 64, 37), (100, 5, 3), (33, 1, 1), (20000, 64, 64)])
+def test_gauge_products(dev, shape):
+    """Q^H u / u Q^H and the push of that factor into the neighbouring core (warm starts of the matrix-free micro solves;
+    the factor the reference discards at sle.py:525, :541), both storage orders, against numpy; bit-identical reruns."""
+    L, k, r = shape
+    rng = np.random.default_rng(L + 7 * k + r)
+    q, u = rng.standard_normal((L, k)), rng.standard_normal((L, r))
+    dq, du = dev.to_device(q), dev.to_device(u)
+    R = host(dev.gauge_factor(dq, du, tall=True))
+    assert relerr(R, q.T @ u) < 1e-13
+    assert np.array_equal(R, host(dev.gauge_factor(dq, du, tall=True)))
+    dqt, dut = dev.to_device(np.ascontiguousarray(q.T)), dev.to_device(np.ascontiguousarray(u.T))
+    assert relerr(host(dev.gauge_factor(dqt, dut, tall=False)), u.T @ q) < 1e-13
+    carry = rng.standard_normal((k, r))
+    core = rng.standard_normal((r, L))
+    assert relerr(host(dev.gauge_push(dev.to_device(carry), dev.to_device(core), left=True)), carry @ core) < 1e-13
+    carry2 = rng.standard_normal((r, k))
+    core2 = rng.standard_normal((L, r))
+    assert relerr(host(dev.gauge_push(dev.to_device(carry2), dev.to_device(core2), left=False)), core2 @ carry2) < 1e-13
