@@ -181,8 +181,8 @@ def run_ours(args, cfg):
 
     d, n, r = cfg["d"], cfg["n"], cfg["r"]
     opc, rhsc, x0c = workload_cores(d, n, r)
-    op, rhs = TT(opc), TT(rhsc)
-    x0 = TT(x0c).ortho_right()                                # GPU ortho path (TT.ortho_right)
+    op, rhs = TT(opc).pin_memory(), TT(rhsc).pin_memory()     # inputs of the end-to-end leg lie in page-locked host memory
+    x0 = TT(x0c).ortho_right()                                # GPU ortho path (TT.ortho_right); its cores come back page-locked
     st = sle._State(op, x0, rhs)
     x0_dev = list(st.x)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

@@ -108,6 +108,13 @@ class Device:
             self._pin = buf
         return buf
 
+    def copy_stream(self):
+        """Second stream for device-to-host copies that overlap the sweep."""
+        s = getattr(self, "_copy_stream", None)
+        if s is None:
+            s = self._copy_stream = torch.cuda.Stream(device=self.device)
+        return s
+
     def _pool(self):
         pool = getattr(self, "_threads", None)
         if pool is None:
@@ -123,6 +130,22 @@ class Device:
             return None
         t = torch.from_numpy(a.reshape(-1))
         return t if t.is_pinned() else None
+
+    def pinned_copies(self, arrays):
+        """Copies of numpy arrays as views of ONE page-locked block (dtype kept: float64 / complex128 / anything numpy)."""
+        arrays = [np.ascontiguousarray(a) for a in arrays]
+        offs, total = [], 0
+        for a in arrays:
+            total = (total + 63) // 64 * 64
+            offs.append(total)
+            total += a.nbytes
+        block = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True).numpy()
+        out = []
+        for a, o in zip(arrays, offs):
+            v = block[o:o + a.nbytes].view(a.dtype).reshape(a.shape)
+            np.copyto(v, a)
+            out.append(v)
+        return out
 
     def upload_many(self, arrays, dtype):
         """List of numpy arrays -> list of contiguous device tensors of `dtype` (float64 / complex128)."""

@@ -31,6 +31,8 @@ class _State:
         self.one3 = _local.ones(dev, (1, 1, 1), self.dtype)
         self.one2 = _local.ones(dev, (1, 1), self.dtype)
         self.cache = {}                                  # per-call verdicts shared by the micro solves (see _local.solve_micro)
+        self.out = None                                  # streamed-out result cores (see stream_out)
+        self.stream_results = False                      # set by the public entry points: copy final cores out early
 
     # sle.py:194-247
     def left(self, i):
@@ -55,8 +57,52 @@ class _State:
     def reset(self, x_cores):
         """Restart from another set of device solution cores (bench: same problem, timed repeatedly)."""
         self.x[:] = list(x_cores)
+        self.out = None
+
+    # -- results leave the device while the sweep is still running: a core is final once the last backward half sweep
+    #    has passed it (sle.py:541, :546), so its device-to-host copy is queued on a second stream right there and
+    #    overlaps the remaining micro steps
+    def stream_out(self, i):
+        dev = self.dev
+        if not self.stream_results:
+            return
+        if self.out is None:
+            bound = [int(c.numel()) for c in self.x]               # ALS ranks never grow (sle.py:522, :538)
+            total = sum(bound)
+            if total * self.x[0].element_size() < dev.PIN_RESULT_MIN_BYTES:
+                self.out = False
+            else:
+                offs = np.concatenate([[0], np.cumsum(bound)]).tolist()
+                self.out = {'host': torch.empty(total, dtype=self.dtype, pin_memory=True), 'offs': offs, 'bound': bound,
+                            'done': {}, 'stream': dev.copy_stream()}
+        if self.out is False:
+            return
+        o = self.out
+        c = self.x[i]
+        n = int(c.numel())
+        if n > o['bound'][i]:
+            self.out = False                                         # cannot happen for ALS; fall back to the plain download
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(o['stream']):
+            o['stream'].wait_event(ev)
+            if n:
+                o['host'][o['offs'][i]:o['offs'][i] + n].copy_(c.reshape(-1), non_blocking=True)
+        o['done'][i] = (c, tuple(c.shape))                           # keeps the device core alive until the copy has run
 
     def result(self):
+        o = self.out
+        if isinstance(o, dict) and len(o['done']) == self.d and all(o['done'][i][0] is self.x[i] for i in range(self.d)):
+            o['stream'].synchronize()
+            hnp = o['host'].numpy()
+            cores = []
+            for i in range(self.d):
+                r, n, r2 = o['done'][i][1]
+                cores.append(hnp[o['offs'][i]:o['offs'][i] + r * n * r2].reshape(r, n, 1, r2))
+            self.out = None
+            return TT(cores)
+        self.out = None
         return TT(_local.download_vector_cores(self.x))
 
 
@@ -68,6 +114,7 @@ def als(operator, initial_guess, right_hand_side, repeats=1, solver='solve'):
     'gmres' force one.  Returns a new TT; inputs are not modified.
     """
     st = _State(operator, initial_guess, right_hand_side)
+    st.stream_results = True
     _run_als(st, repeats, solver)
     return st.result()
 
@@ -112,7 +159,8 @@ def _sweeps_als(st, repeats, solver, check=None):
     for i in range(d - 1, -1, -1):                                        # sle.py:54-56
         st.right(i)
     carry = None                                                          # gauge factor towards the next core to be solved
-    for _ in range(repeats):                                              # sle.py:62
+    st.out = None
+    for rep in range(repeats):                                            # sle.py:62
         for i in range(d):                                                # first half sweep, sle.py:65-77
             st.left(i)
             if i < d - 1:
@@ -138,6 +186,8 @@ def _sweeps_als(st, repeats, solver, check=None):
                 x[i] = q.reshape(q.shape[0], n, r2)
             else:
                 x[i] = u.reshape(r, n, r2)                                # sle.py:546
+            if rep == repeats - 1:
+                st.stream_out(i)
         if check is not None and not check():
             return False
     return True

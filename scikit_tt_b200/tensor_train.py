@@ -132,6 +132,15 @@ class TT(object):
     def isoperator(self):
         return not (all(m == 1 for m in self.row_dims) or all(n == 1 for n in self.col_dims))
 
+    def pin_memory(self):
+        """Move the cores into page-locked host memory (in place; returns self).  Not part of the reference surface:
+        a TT that is passed to the solvers repeatedly (the operator of a time stepper, a parameter sweep) is then DMA'd
+        from where it lies instead of being staged through a bounce buffer on every call.  The cores stay ordinary
+        numpy arrays (views of one page-locked block)."""
+        dev = _device.get_device()
+        self.cores = dev.pinned_copies(self.cores)
+        return self
+
     def copy(self):
         return TT([c.copy() for c in self.cores])
 

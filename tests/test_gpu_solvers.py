@@ -304,3 +304,36 @@ def test_trapezoidal_rule_and_adaptive_step_size(dev):
         assert len(times) == len(ref_times) and np.allclose(times, ref_times, rtol=1e-6, atol=0)
         assert rel_diff(sol[1].cores, cores(z, f"adapt/{method}/step1")) < SOL_TOL
         assert rel_diff(sol[-1].cores, cores(z, f"adapt/{method}/step{len(ref_times) - 1}")) < 1e-5
+
+
+def test_transfer_paths_and_deferred_redo(dev, monkeypatch):
+    """Host-side plumbing of sle.als at a size where it is active (results >= 1 MiB: streamed out of the last backward half
+    sweep into one page-locked block; page-locked inputs DMA'd in place; micro-solve outcomes inspected once per half
+    sweep): pageable and page-locked inputs give bit-identical cores, the result cores are ordinary writable numpy arrays
+    that can be fed back, the inputs are untouched, and a missed deferred outcome redoes the sweep synchronously with the
+    same result."""
+    import torch
+    import bench
+    opc, rhsc, x0c = bench.workload_cores(6, 64, 32)
+    op, rhs = TT(opc), TT(rhsc)
+    x0 = TT(ott.ortho_right(x0c))
+    before = [c.copy() for c in x0.cores]
+    a = sle.als(op, x0, rhs, repeats=2)
+    assert all(np.array_equal(c, b) for c, b in zip(x0.cores, before))
+    assert all(isinstance(c, np.ndarray) and c.flags.writeable and c.dtype == np.float64 for c in a.cores)
+    assert torch.from_numpy(a.cores[2].reshape(-1)).is_pinned()
+    opp, rhsp, x0p = TT(opc).pin_memory(), TT(rhsc).pin_memory(), TT([c.copy() for c in x0.cores]).pin_memory()
+    assert torch.from_numpy(x0p.cores[2].reshape(-1)).is_pinned()
+    b = sle.als(opp, x0p, rhsp, repeats=2)
+    assert all(np.array_equal(p, q) for p, q in zip(a.cores, b.cores))
+    c = sle.als(op, a, rhs, repeats=1)                        # a solver result fed back as the next guess
+    bnorm = np.prod([np.linalg.norm(v) for v in rhsc])
+    assert tt.residual_error(op, c, rhs) / bnorm <= 1.0001 * tt.residual_error(op, a, rhs) / bnorm + 1e-13
+    a.cores[0][...] = 0.0                                     # results own their memory as far as the caller can tell
+    assert np.any(b.cores[0] != 0.0)
+    # a deferred outcome that is judged bad: the sweeps are redone with a host decision after every solve
+    monkeypatch.setattr(_local.Deferred, "check", lambda self: False)
+    sle._DEFER_MISSES.clear()
+    redo = sle.als(op, x0, rhs, repeats=2)
+    sle._DEFER_MISSES.clear()
+    assert all(np.array_equal(p, q) for p, q in zip(redo.cores, b.cores))
