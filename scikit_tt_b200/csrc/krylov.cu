@@ -45,7 +45,9 @@ static int64_t local_dim(const sktt_local_op* op) {
 }
 // bound of the vector length in either layout
 static int64_t local_dim_bound(const sktt_local_op* op) {
-    return op->sites == 1 ? fused_rpad(op->r) * op->n * 68 : local_dim(op);
+    if (op->sites != 1) return local_dim(op);
+    const int64_t tiled = fused_rpad(op->r) * op->n * 68, natural = local_dim(op);   // tiled layout: r' <= 64 padded to 68
+    return tiled > natural ? tiled : natural;
 }
 static int64_t local_mv_work(const sktt_local_op* op) {
     if (op->sites == 1) {

@@ -132,7 +132,9 @@ def _run_als(st, repeats, solver):
         st.cache['defer'] = _local.Deferred(st.dev, 2 * st.d)
         try:
             ok = _sweeps_als(st, repeats, solver, check=st.cache['defer'].check)
-        except (_device.SkttError, np.linalg.LinAlgError):
+        except (_device.SkttError, np.linalg.LinAlgError) as exc:
+            if getattr(exc, 'status', 0) == 3:                            # SKTT_ERR_CUDA: a broken context cannot be redone
+                raise
             ok = False                                                    # let the host-driven pass raise what there is to raise
         finally:
             st.cache['defer'] = None

@@ -337,3 +337,23 @@ def test_transfer_paths_and_deferred_redo(dev, monkeypatch):
     redo = sle.als(op, x0, rhs, repeats=2)
     sle._DEFER_MISSES.clear()
     assert all(np.array_equal(p, q) for p, q in zip(redo.cores, b.cores))
+
+
+def test_krylov_workspace_right_rank_above_64(dev):
+    """Matrix-free micro systems whose right solution rank exceeds the 64 (+4) columns of the tiled vector layout (config 4:
+    r = 128 / 256): the Krylov workspace must be sized by the natural length r n r' -- regression for an undersized bound
+    that made the r = 256 sweep fault.  CG and GMRES solve the same micro systems, so their sweeps must agree."""
+    import bench
+    rng = np.random.default_rng(5)
+    d, n = 4, 16
+    opc = bench.laplace_cores(d, n)
+    ranks = [1, 16, 80, 16, 1]
+    rhs = TT([rng.standard_normal((1, n, 1, 1)) for _ in range(d)])
+    x0 = TT(ott.ortho_right([rng.standard_normal((ranks[i], n, 1, ranks[i + 1])) for i in range(d)]))
+    op = TT(opc)
+    a = sle.als(op, x0, rhs, repeats=1, solver='cg')
+    b = sle.als(op, x0, rhs, repeats=1, solver='gmres')
+    assert a.ranks == ranks
+    assert rel_diff(a.cores, b.cores) < SOL_TOL
+    bnorm = np.prod([np.linalg.norm(c) for c in rhs.cores])
+    assert tt.residual_error(op, a, rhs) / bnorm < 1e-2
