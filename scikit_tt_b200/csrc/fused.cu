@@ -1032,10 +1032,20 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
         }
         gsync();
         if (warp == 0) {
+            // all loads of a lane in flight at once (one L2 round trip instead of one per 32 CTAs), summed in a fixed order
             double t0 = 0.0, t1 = 0.0;
-            for (int g = lane; g < G; g += 32) {
-                t0 += __ldcg(part + 2 * g);
-                t1 += __ldcg(part + 2 * g + 1);
+            for (int g0 = 0; g0 < G; g0 += 256) {
+                double2 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int g = g0 + lane + 32 * k;
+                    v[k] = g < G ? __ldcg(reinterpret_cast<const double2*>(part) + g) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    t0 += v[k].x;
+                    t1 += v[k].y;
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -1157,16 +1167,34 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
             }
             const double alpha = gamma / denom;
             double acc = 0.0;
-            for (long long i = gtid; i < a.N; i += gstride) {
-                const double ri = a.rv[i];
-                const double pi = firstit ? ri : fma(beta, a.p[i], ri);
-                const double si = firstit ? a.w[i] : fma(beta, a.s[i], a.w[i]);
-                a.p[i] = pi;
-                a.s[i] = si;
-                a.u[i] = fma(alpha, pi, a.u[i]);
-                const double rn = fma(-alpha, si, ri);
-                a.rv[i] = rn;
-                acc = fma(rn, rn, acc);
+            // four elements per thread and pass, every load issued before the first store (the vectors may alias as far as
+            // the compiler knows, so the plain loop serialises one L2 round trip per element)
+            for (long long i0 = gtid; i0 < a.N; i0 += 4 * gstride) {
+                double ri[4], pi[4], si[4], wi[4], ui[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const long long i = i0 + k * gstride;
+                    const bool in = i < a.N;
+                    ri[k] = in ? __ldcg(a.rv + i) : 0.0;
+                    wi[k] = in ? __ldcg(a.w + i) : 0.0;
+                    ui[k] = in ? __ldcg(a.u + i) : 0.0;
+                    pi[k] = (in && !firstit) ? __ldcg(a.p + i) : 0.0;
+                    si[k] = (in && !firstit) ? __ldcg(a.s + i) : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const long long i = i0 + k * gstride;
+                    if (i < a.N) {
+                        const double pn = firstit ? ri[k] : fma(beta, pi[k], ri[k]);
+                        const double sn = firstit ? wi[k] : fma(beta, si[k], wi[k]);
+                        a.p[i] = pn;
+                        a.s[i] = sn;
+                        a.u[i] = fma(alpha, pn, ui[k]);
+                        const double rn = fma(-alpha, sn, ri[k]);
+                        a.rv[i] = rn;
+                        acc = fma(rn, rn, acc);
+                    }
+                }
             }
             grid_sum2(acc, 0.0, rr_rec, tmp);
             gamma_old = gamma;

@@ -560,6 +560,180 @@ __device__ __noinline__ void cq_house_r_panel(T* Y, const int LD, const int K, c
     }
 }
 
+// Team form of the same factorisation for f64 sketches of at most 128 rows (the bench shape: 128 x 64).  ncu's source page of
+// the panel routine above shows its one warp bound by instruction issue and fixed latencies -- 640 instructions per
+// reflector, two thirds of them the shuffle reduction of eight partial sums over the 32 row-owning lanes.  Here
+//  * a panel is factored by four warps (one per scheduler): sixteen threads own one COLUMN of the panel (eight rows
+//    each), so a reflector needs one partial sum per thread and four shuffle stages of a single value; the eight sums
+//    and the pivot row travel through 16 doubles of shared memory between two 128-thread named barriers;
+//  * the eight reflectors of the panel are applied to the remaining columns by all eight warps with lanes owning columns
+//    and warps owning 32-row blocks: no shuffles at all, the four block partials of a column meet in shared memory (one
+//    CTA barrier per reflector, double-buffered).
+// Same reflectors, same storage conventions (scaled v below the diagonal, R on and above it, tau in taus[]).
+__device__ __forceinline__ void cq_bar_team() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+#define CQ_TEAM_XCH 3200      // doubles of exchange space behind the sketch: 16 | Vs[8][128] | GV[8][8] | xr[4][8][64]
+
+template <int LD>
+__device__ __forceinline__ void cq_house_r_team(double* Y, const int K, const int n, double* taus, double* xch) {
+    constexpr int PW = 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* Vs = xch + 16;                                        // [8][128] reflectors of the panel: 1 on the diagonal, 0 above
+    double* GV = Vs + 8 * 128;                                    // [8][8]   v_k . v_l, l < k
+    double* xr = GV + 64;                                         // [4][8][64] v_k . y of the four 32-row blocks of a column
+    for (int j0 = 0; j0 < n; j0 += PW) {
+        const int pw = min(PW, n - j0);
+        if (warp < 4) {
+            const int cl = tid >> 4, sub = tid & 15;
+            const bool colok = cl < pw;
+            // rows of this thread: sub + 16 q; loads are unconditional (row index clamped), masks are selects
+            const double* ycol = Y + sub * LD;
+            double a[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int i = sub + 16 * q;
+                const double t = Y[min(i, K - 1) * LD + j0 + (colok ? cl : 0)];
+                a[q] = (colok && i < K) ? t : 0.0;
+            }
+#pragma unroll 1
+            for (int jj = 0; jj < pw; ++jj) {
+                const int j = j0 + jj, qs = j >> 4, ls = j & 15;
+                double yj[8], g0 = 0.0, g1 = 0.0, pr = a[0];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int i = sub + 16 * q;
+                    const double t = ycol[(K == 128 ? 16 * q : min(i, K - 1) - sub) * LD + j];
+                    yj[q] = i < K ? t : 0.0;
+                    const double m = i > j ? yj[q] : 0.0;
+                    if (q & 1) g1 = fma(m, a[q], g1);
+                    else g0 = fma(m, a[q], g0);
+                    pr = q == qs ? a[q] : pr;
+                }
+                double g = g0 + g1;
+                g += __shfl_xor_sync(0xffffffffu, g, 8);
+                g += __shfl_xor_sync(0xffffffffu, g, 4);
+                g += __shfl_xor_sync(0xffffffffu, g, 2);
+                g += __shfl_xor_sync(0xffffffffu, g, 1);
+                pr = __shfl_sync(0xffffffffu, pr, (lane & 16) | ls);
+                if (sub == 0) {
+                    xch[cl] = g;
+                    xch[8 + cl] = pr;
+                }
+                cq_bar_team();
+                const double sigma = xch[jj], alpha = xch[8 + jj];
+                double tau = 0.0, scl = 0.0, beta = alpha;
+                if (sigma != 0.0) {
+                    const double nrm = sqrt(fma(alpha, alpha, sigma));
+                    beta = alpha >= 0.0 ? -nrm : nrm;
+                    const double binv = 1.0 / beta;
+                    tau = (beta - alpha) * binv;
+                    scl = 1.0 / (alpha - beta);
+                }
+                const double w = tau * fma(scl, g, pr);
+                if (cl > jj) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int i = sub + 16 * q;
+                        const double v = i == j ? 1.0 : (i > j ? yj[q] * scl : 0.0);
+                        a[q] = fma(-v, w, a[q]);
+                    }
+                    if (cl == jj + 1 && colok) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int i = sub + 16 * q;
+                            if (i < K) Y[i * LD + j + 1] = a[q];
+                        }
+                    }
+                } else if (cl == jj) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int i = sub + 16 * q;
+                        const double v = i == j ? 1.0 : (i > j ? yj[q] * scl : 0.0);     // rows >= K: yj = 0
+                        Vs[jj * 128 + i] = v;
+                        if (i >= j && i < K) Y[i * LD + j] = i == j ? beta : v;
+                    }
+                }
+                if (tid == 0) taus[j] = tau;
+                cq_bar_team();
+            }
+        }
+        __syncthreads();
+        const int c0 = j0 + PW;
+        if (c0 < n) {
+            // the pw reflectors on the remaining columns, all at once: with d_k = v_k . y (on the column as it stands) and
+            // G = V^T V, the coefficients of the successive reflections follow from w_k = tau_k (d_k - sum_{l<k} G_kl w_l),
+            // and y -= sum_k v_k w_k.  Lanes own columns, warp pairs own 32-row blocks; three CTA barriers per panel.
+            const int part = warp >> 1, ci = 32 * (warp & 1) + lane, c = c0 + ci, ibase = 32 * part;
+            const bool cok = c < n, active = cok && ibase + 32 > j0 && ibase < K;
+            const int cc = cok ? c : c0;
+            if (warp < pw) {                                      // row `warp` of G
+                for (int l = 0; l < warp; ++l) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sacc = fma(Vs[warp * 128 + lane + 32 * q], Vs[l * 128 + lane + 32 * q], sacc);
+                    sacc = warp_sum<double>(sacc);
+                    if (lane == 0) GV[warp * 8 + l] = sacc;
+                }
+            }
+            double y[32], d[PW];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const double t = Y[min(ibase + k, K - 1) * LD + cc];
+                y[k] = (active && ibase + k < K) ? t : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < PW; ++k) d[k] = 0.0;
+            if (active) {
+                // sixteen independent accumulation chains (a dependent DFMA issues only every ~20 cycles)
+                double e1[PW];
+#pragma unroll
+                for (int k = 0; k < PW; ++k) e1[k] = 0.0;
+                const double2* vb = reinterpret_cast<const double2*>(Vs + ibase);
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+#pragma unroll
+                    for (int k = 0; k < PW; ++k) {
+                        const double2 vv = vb[k * 64 + t];          // rows of reflectors k >= pw are stale: masked below
+                        d[k] = fma(vv.x, y[2 * t], d[k]);
+                        e1[k] = fma(vv.y, y[2 * t + 1], e1[k]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < PW; ++k) d[k] = k < pw ? d[k] + e1[k] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < PW; ++k) xr[(part * 8 + k) * 64 + ci] = d[k];
+            __syncthreads();
+            if (active) {
+                double wk[PW];
+#pragma unroll
+                for (int k = 0; k < PW; ++k) {
+                    double dk = ((xr[k * 64 + ci] + xr[(8 + k) * 64 + ci]) + xr[(16 + k) * 64 + ci]) + xr[(24 + k) * 64 + ci];
+#pragma unroll
+                    for (int l = 0; l < k; ++l) dk = fma(-GV[k * 8 + l], wk[l], dk);
+                    wk[k] = k < pw ? taus[j0 + k] * dk : 0.0;
+                }
+                const double2* vb = reinterpret_cast<const double2*>(Vs + ibase);
+#pragma unroll
+                for (int k = 0; k < PW; ++k) {                    // wk[k] = 0 for k >= pw: stale rows of Vs do no harm unless NaN
+                    if (k < pw) {
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) {
+                            const double2 vv = vb[k * 64 + t];
+                            y[2 * t] = fma(-vv.x, wk[k], y[2 * t]);
+                            y[2 * t + 1] = fma(-vv.y, wk[k], y[2 * t + 1]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (ibase + k < K) Y[(ibase + k) * LD + c] = y[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __device__ __forceinline__ unsigned cq_hash(unsigned x) {
     x ^= x >> 16;
     x *= 0x7feb352du;
@@ -573,9 +747,9 @@ template <typename T, int NT>
 __global__ void __launch_bounds__(CQ_THREADS)
 cholqr_kernel(const T* __restrict__ src, QrView lv, int m, int n, int rows_per_cta, T* __restrict__ qdst, QrView qv,
               T* __restrict__ rdst, QrView rv, T* part, T* gfull, T* rstack, int* status, unsigned long long* dbg,
-              int sketch_k, T* ysk) {
+              int sketch_k, T* ysk, int use_team) {
     constexpr int NN = 16 * NT, LD = NN + 1, E = NN * NN;
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tile = (T*)smem_raw;                         // [rows_per_cta][LD]
     T* Gs = tile + (size_t)rows_per_cta * LD;       // [NN][LD]  Gram matrix -> Cholesky factor R (upper)
     T* Xs = Gs + (size_t)NN * LD;                   // [NN][LD]  second buffer of the R product (only when R is wanted)
@@ -691,7 +865,19 @@ cholqr_kernel(const T* __restrict__ src, QrView lv, int m, int n, int rows_per_c
         for (int e = tid; e < sketch_k * NN; e += CQ_THREADS) Ys[(e / NN) * LD + e % NN] = ld_cg<T>(ysk + e);
         __syncthreads();
         stamp();
-        if (sketch_k <= 128 && sketch_k >= n) cq_house_r_panel<T, 4>(Ys, LD, sketch_k, n, wv);
+        bool team_done = false;
+        if constexpr (!Num<T>::is_complex && NT <= 4) {
+            if (sketch_k <= 128 && sketch_k >= n && use_team) {
+                team_done = true;
+                // exchange space behind the sketch, 16-byte aligned by element arithmetic (keeps the pointers in the shared
+                // address space for the compiler: LDS / STS instead of generic loads)
+                double* xraw = (double*)Ys + (size_t)sketch_k * LD;
+                const size_t off = (size_t)(xraw - (double*)smem_raw);
+                cq_house_r_team<LD>((double*)Ys, sketch_k, n, (double*)wv, xraw + (off & 1));
+            }
+        }
+        if (team_done) {
+        } else if (sketch_k <= 128 && sketch_k >= n) cq_house_r_panel<T, 4>(Ys, LD, sketch_k, n, wv);
         else if (!Num<T>::is_complex && sketch_k <= 256 && sketch_k >= n) cq_house_r_panel<double, 8>((double*)Ys, LD, sketch_k, n, (double*)wv);
         else cq_house_r<T>(Ys, LD, sketch_k, n, red, wv, wpart);
         stamp();
@@ -936,7 +1122,8 @@ static int cholqr_launch_nt(sktt_ctx* ctx, int m, int n, const T* src, QrView lv
     int kb = (target + G - 1) / G;
     int sketch_k = plain ? 0 : G * kb;
     if (!plain && (kb > rows_per_cta || sketch_k > m / 2)) return 0;      // too few rows to sketch: Householder path
-    const size_t smem = ((size_t)rows_per_cta * LD + (size_t)(rdst ? 2 : 1) * NN * LD + (size_t)sketch_k * LD) * sizeof(T);
+    const size_t smem = ((size_t)rows_per_cta * LD + (size_t)(rdst ? 2 : 1) * NN * LD + (size_t)sketch_k * LD) * sizeof(T) +
+                        (sketch_k > 0 ? CQ_TEAM_XCH * sizeof(double) + 16 : 0);     // + exchange space of cq_house_r_team
     if (smem > budget) return 0;                                          // not for this kernel: Householder path
     // scratch: partial Gram matrices | reduced Gram matrix | R factors of the passes | sketch; sized for the fallback too
     const size_t mine = ((size_t)G * E + E + (size_t)(CQ_MAX_PASSES + 1) * E + (size_t)sketch_k * NN) * sizeof(T);
@@ -953,8 +1140,9 @@ static int cholqr_launch_nt(sktt_ctx* ctx, int m, int n, const T* src, QrView lv
         configured = true;
     }
     unsigned long long* dbg = (ctx->debug & 1) ? (unsigned long long*)((char*)ctx->scratch + CQ_DEBUG_OFF) : nullptr;
+    int use_team = (ctx->debug & 32) ? 0 : 1;                            // debug bit 32: the one-warp panel routine instead
     void* args[] = {&src, &lv, &m, &n, &rows_per_cta, &qdst, &qv, &rdst, &rv, &part, &gfull, &rstack, &status, &dbg,
-                    &sketch_k, &ysk};
+                    &sketch_k, &ysk, &use_team};
     SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)cholqr_kernel<T, NT>, dim3(G), dim3(CQ_THREADS), args, smem,
                                                ctx->stream));
     ctx->launches++;
