@@ -7,8 +7,8 @@ Workload (config.workload = "C3"): synthetic discretised-Laplacian TT operator d
 8d: SLIM layout, symmetric positive definite), right-hand side rank 1 (seed 0), initial guess with interior solution
 rank 64 (seed 1, right-orthonormalised).  One *step* = one `sle.als(op, x0, rhs, repeats=1)` = 2 half-sweeps
 (forward + backward) over the 32 cores: 64 interface-stack updates, 63 micro systems of 262 144 unknowns solved
-matrix-free (CG to a TRUE relative residual of 1e-14; the reference's dense micro matrix would be 512 GiB), 62 QR/RQ
-factorisations of 4096 x 64 unfoldings.
+matrix-free (CG to a TRUE relative residual of 1e-14, warm-started from the sweep's current iterate; the reference's dense
+micro matrix would be 512 GiB), 62 QR/RQ factorisations of 4096 x 64 unfoldings.
 
 `value`  : half-sweeps/s with operator, right-hand side and initial guess resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same call through the public API with host numpy TT cores in and out (H2D + D2H inside the timed region).
@@ -158,8 +158,8 @@ def run_reference(args, cfg):
 def cfg_public(cfg):
     return {"workload": "C3: sle.als on the rank-3 Laplacian-type TT operator", "d": cfg["d"], "n": cfg["n"],
             "operator_rank": 3, "solution_rank": cfg["r"], "repeats_per_step": 1, "half_sweeps_per_step": 2,
-            "micro_solver": "matrix-free CG (Chronopoulos-Gear form, reductions fused into the matvec), true relative "
-                            "residual 1e-14 (dense micro matrix impossible at this size)",
+            "micro_solver": "matrix-free CG (Chronopoulos-Gear form, reductions fused into the matvec, warm start from the "
+                            "sweep's current iterate), true relative residual 1e-14 (dense micro matrix impossible at this size)",
             "l2": "256 MiB buffer written between steps (inside the timed region)",
             "parallelism": "replicas" if cfg["gpus"] > 1 else "single GPU"}
 
@@ -315,7 +315,8 @@ def run_ours(args, cfg):
                              "traffic_note": "dram bytes per matvec of the two-kernel form (mv_stage1 2.35 MB + mv_stage23 9.41 MB, "
                                              "profiles/r01_ncu_final_full.txt, ncu flushes the caches per replay); inside the "
                                              "persistent kernel every operand is L2-resident: 3.1 MB of DRAM reads for 20 matvecs "
-                                             "(profiles/r01_ncu_persistent.txt); algorithmic bytes 4.72 MB",
+                                             "(profiles/r01_ncu_persistent.txt), 6.4 MB read + 1.2 MB written for one whole in-sweep "
+                                             "solve of about 19 matvecs (profiles/r01_ncu_pcg_final.txt); algorithmic bytes 4.72 MB",
                              "kernel": kernel_name,
                              "flops_per_matvec": F, "us_per_matvec": mv_ms * 1e3,
                              "executed_flops_per_matvec": F_exec,
