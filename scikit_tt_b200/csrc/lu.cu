@@ -138,15 +138,27 @@ lu_panel_kernel(T* __restrict__ A, int N, int j0, int nb, int* __restrict__ ipiv
         __syncthreads();
         // (f) scale the column and rank-1 update of the remaining panel columns
         if (!singular) {
-            for (int rr = warp; rr < nrows; rr += 8) {
-                int gr = row_begin + rr;
-                if (gr <= j) continue;
-                T l = Num<T>::div(chunk[rr * LU_LD + jj], pivot);
-                T cur = chunk[rr * LU_LD + lane];
-                if (lane == jj) cur = l;
-                else if (lane > jj) cur = Num<T>::sub(cur, Num<T>::mul(l, urow[lane]));
-                __syncwarp();
-                chunk[rr * LU_LD + lane] = cur;
+            // multipliers by the reciprocal of the pivot, as LAPACK's getf2 / getrf2 scale the column (one division per
+            // column instead of one per row); the row's entry of column jj reaches the other lanes by a shuffle, so four
+            // rows per warp are in flight without a hazard on shared memory
+            const T pinv = Num<T>::div(Num<T>::one(), pivot);
+            const T uj = urow[lane];
+            for (int rr0 = warp; rr0 < nrows; rr0 += 32) {
+                T cur[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int rr = rr0 + 8 * k;
+                    cur[k] = rr < nrows ? chunk[rr * LU_LD + lane] : Num<T>::zero();
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int rr = rr0 + 8 * k;
+                    const T l = Num<T>::mul(lane_bcast<T>(cur[k], jj), pinv);
+                    if (rr < nrows && row_begin + rr > j) {
+                        if (lane == jj) chunk[rr * LU_LD + lane] = l;
+                        else if (lane > jj) chunk[rr * LU_LD + lane] = Num<T>::sub(cur[k], Num<T>::mul(l, uj));
+                    }
+                }
             }
         }
         __syncthreads();
@@ -155,6 +167,143 @@ lu_panel_kernel(T* __restrict__ A, int N, int j0, int nb, int* __restrict__ ipiv
         int rr = e / LU_NB, cc = e % LU_NB;
         if (cc < nb) A[(size_t)(row_begin + rr) * N + j0 + cc] = chunk[rr * LU_LD + cc];
     }
+}
+
+// The same panel factorisation for panels of at most LU_CLUSTER_MAX CTAs (N - j0 <= 2048 rows: the portable cluster size), launched as ONE thread-block
+// cluster: every CTA pushes its pivot candidate (value, row, row contents) and -- if it owns it -- row j straight into the
+// shared memory of all CTAs of the cluster (distributed shared memory), one cluster barrier per column publishes them, and
+// the winner is picked from local shared memory.  No global-memory round trip and no grid-wide barrier in the column loop
+// (the cooperative kernel above pays ~5 us per column for them; a 1024 x 1024 factorisation spent 32 x 270 us there).
+#define LU_CLUSTER_MAX 8
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+lu_panel_cluster_kernel(T* __restrict__ A, int N, int j0, int nb, int* __restrict__ ipiv, int* __restrict__ perm, int* info) {
+    extern __shared__ unsigned char smem_raw[];
+    T* chunk = (T*)smem_raw;  // [LU_ROWS_PER_CTA][LU_LD]
+    __shared__ PanelCand<T> cands[2][LU_CLUSTER_MAX];
+    __shared__ T rowj_s[2][LU_NB];
+    __shared__ T urow[LU_NB];
+    __shared__ double red_val[8];
+    __shared__ int red_row[8];
+    __shared__ int s_piv;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int G = (int)cluster.num_blocks(), cta = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row_begin = j0 + cta * LU_ROWS_PER_CTA;
+    const int nrows = max(0, min(LU_ROWS_PER_CTA, N - row_begin));
+
+    for (int e = tid; e < nrows * LU_NB; e += 256) {
+        int rr = e / LU_NB, cc = e % LU_NB;
+        chunk[rr * LU_LD + cc] = cc < nb ? A[(size_t)(row_begin + rr) * N + j0 + cc] : Num<T>::zero();
+    }
+    cluster.sync();                                            // every CTA of the cluster is resident before the first push
+
+    for (int jj = 0; jj < nb; ++jj) {
+        const int j = j0 + jj, par = jj & 1;
+        // (a) local pivot candidate among rows >= j
+        double best = -1.0;
+        int brow = 0x7fffffff;
+        for (int rr = tid; rr < nrows; rr += 256) {
+            int gr = row_begin + rr;
+            if (gr >= j) {
+                double a = pivot_abs<T>(chunk[rr * LU_LD + jj]);
+                if (a > best) { best = a; brow = gr; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+            if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
+        }
+        if (lane == 0) { red_val[warp] = best; red_row[warp] = brow; }
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < 8 ? red_val[lane] : -1.0;
+            brow = lane < 8 ? red_row[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+                if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
+            }
+            best = __shfl_sync(0xffffffffu, best, 0);
+            brow = __shfl_sync(0xffffffffu, brow, 0);
+            // (b) push the candidate (and row j, if owned) into the shared memory of every CTA of the cluster
+            const T cval = best >= 0.0 ? chunk[(brow - row_begin) * LU_LD + lane] : Num<T>::zero();
+            const bool own_j = j >= row_begin && j < row_begin + nrows;
+            const T jval = own_j ? chunk[(j - row_begin) * LU_LD + lane] : Num<T>::zero();
+            for (int r = 0; r < G; ++r) {
+                PanelCand<T>* dst = cluster.map_shared_rank(&cands[par][cta], r);
+                if (lane == 0) { dst->absval = best; dst->row = brow; }
+                dst->vals[lane] = cval;
+                if (own_j) cluster.map_shared_rank(&rowj_s[par][0], r)[lane] = jval;
+            }
+        }
+        // (c) one cluster barrier per column (release / acquire: the pushes are visible behind it)
+        cluster.sync();
+        // (d) winner (ties -> smallest row index, deterministic), from local shared memory
+        if (warp == 0) {
+            double gb = -1.0;
+            int grow = 0x7fffffff, gc = 0;
+            if (lane < G) { gb = cands[par][lane].absval; grow = cands[par][lane].row; gc = lane; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ob = __shfl_xor_sync(0xffffffffu, gb, o);
+                int orow = __shfl_xor_sync(0xffffffffu, grow, o);
+                int oc = __shfl_xor_sync(0xffffffffu, gc, o);
+                if (ob > gb || (ob == gb && orow < grow)) { gb = ob; grow = orow; gc = oc; }
+            }
+            if (lane == 0) s_piv = grow;
+            urow[lane] = cands[par][gc].vals[lane];
+        }
+        __syncthreads();
+        const int piv = s_piv;
+        const T pivot = urow[jj];
+        const bool singular = (pivot_abs<T>(pivot) == 0.0);
+        // (e) interchange rows j <-> piv inside the panel
+        if (warp == 0) {
+            if (piv != j && piv >= row_begin && piv < row_begin + nrows) chunk[(piv - row_begin) * LU_LD + lane] = rowj_s[par][lane];
+            if (j >= row_begin && j < row_begin + nrows) chunk[(j - row_begin) * LU_LD + lane] = urow[lane];
+            if (cta == 0 && lane == 0) {
+                ipiv[j] = piv;
+                int t = perm[j];
+                perm[j] = perm[piv];
+                perm[piv] = t;
+                if (singular && *info == 0) *info = j + 1;
+            }
+        }
+        __syncthreads();
+        // (f) scale the column and rank-1 update of the remaining panel columns
+        if (!singular) {
+            const T pinv = Num<T>::div(Num<T>::one(), pivot);
+            const T uj = urow[lane];
+            for (int rr0 = warp; rr0 < nrows; rr0 += 32) {
+                T cur[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int rr = rr0 + 8 * k;
+                    cur[k] = rr < nrows ? chunk[rr * LU_LD + lane] : Num<T>::zero();
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int rr = rr0 + 8 * k;
+                    const T l = Num<T>::mul(lane_bcast<T>(cur[k], jj), pinv);
+                    if (rr < nrows && row_begin + rr > j) {
+                        if (lane == jj) chunk[rr * LU_LD + lane] = l;
+                        else if (lane > jj) chunk[rr * LU_LD + lane] = Num<T>::sub(cur[k], Num<T>::mul(l, uj));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < nrows * LU_NB; e += 256) {
+        int rr = e / LU_NB, cc = e % LU_NB;
+        if (cc < nb) A[(size_t)(row_begin + rr) * N + j0 + cc] = chunk[rr * LU_LD + cc];
+    }
+    cluster.sync();                                            // no CTA leaves while another may still push into it
 }
 
 // row interchanges outside the panel + U12 = L11^{-1} A12 (thread per column)
@@ -215,6 +364,8 @@ static int lu_factor_impl(sktt_ctx* ctx, int dtype, int N, T* A, int* ipiv, int*
     static bool configured = false;
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         configured = true;
     }
     for (int j0 = 0; j0 < N; j0 += LU_NB) {
@@ -222,7 +373,21 @@ static int lu_factor_impl(sktt_ctx* ctx, int dtype, int N, T* A, int* ipiv, int*
         int G = (N - j0 + LU_ROWS_PER_CTA - 1) / LU_ROWS_PER_CTA;
         int coop = G > 1 ? 1 : 0;
         void* args[] = {&A, &N, &j0, &nb, &ipiv, &perm, &cand, &rowj, &info_dev, &coop};
-        if (coop) {
+        if (G <= LU_CLUSTER_MAX && !(ctx->debug & 64)) {       // one thread-block cluster (debug bit 64: cooperative kernel)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(G);
+            cfg.blockDim = dim3(256);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = G;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            SKTT_CUDA(ctx, cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel<T>, A, N, j0, nb, ipiv, perm, info_dev));
+        } else if (coop) {
             SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)lu_panel_kernel<T>, dim3(G), dim3(256), args, smem,
                                                        ctx->stream));
         } else {
