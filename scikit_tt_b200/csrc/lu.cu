@@ -128,11 +128,8 @@ lu_panel_kernel(T* __restrict__ A, int N, int j0, int nb, int* __restrict__ ipiv
                 chunk[(piv - row_begin) * LU_LD + lane] = ld_cg<T>(&rowj[par * LU_NB + lane]);
             if (j >= row_begin && j < row_begin + nrows) chunk[(j - row_begin) * LU_LD + lane] = urow[lane];
             if (cta == 0 && lane == 0) {
-                ipiv[j] = piv;
-                int t = perm[j];
-                perm[j] = perm[piv];
-                perm[piv] = t;
-                if (singular && *info == 0) *info = j + 1;
+                ipiv[j] = piv;                                 // the accumulated permutation follows from ipiv afterwards
+                if (singular && *info == 0) *info = j + 1;     // (perm_from_ipiv_kernel): no dependent global loads here
             }
         }
         __syncthreads();
@@ -154,10 +151,9 @@ lu_panel_kernel(T* __restrict__ A, int N, int j0, int nb, int* __restrict__ ipiv
                 for (int k = 0; k < 4; ++k) {
                     const int rr = rr0 + 8 * k;
                     const T l = Num<T>::mul(lane_bcast<T>(cur[k], jj), pinv);
-                    if (rr < nrows && row_begin + rr > j) {
-                        if (lane == jj) chunk[rr * LU_LD + lane] = l;
-                        else if (lane > jj) chunk[rr * LU_LD + lane] = Num<T>::sub(cur[k], Num<T>::mul(l, uj));
-                    }
+                    const T upd = Num<T>::sub(cur[k], Num<T>::mul(l, uj));
+                    const T nv = lane == jj ? l : (lane > jj ? upd : cur[k]);       // selects: no divergence inside the warp
+                    if (rr < nrows && row_begin + rr > j) chunk[rr * LU_LD + lane] = nv;
                 }
             }
         }
@@ -267,11 +263,8 @@ lu_panel_cluster_kernel(T* __restrict__ A, int N, int j0, int nb, int* __restric
             if (piv != j && piv >= row_begin && piv < row_begin + nrows) chunk[(piv - row_begin) * LU_LD + lane] = rowj_s[par][lane];
             if (j >= row_begin && j < row_begin + nrows) chunk[(j - row_begin) * LU_LD + lane] = urow[lane];
             if (cta == 0 && lane == 0) {
-                ipiv[j] = piv;
-                int t = perm[j];
-                perm[j] = perm[piv];
-                perm[piv] = t;
-                if (singular && *info == 0) *info = j + 1;
+                ipiv[j] = piv;                                 // the accumulated permutation follows from ipiv afterwards
+                if (singular && *info == 0) *info = j + 1;     // (perm_from_ipiv_kernel): no dependent global loads here
             }
         }
         __syncthreads();
@@ -290,10 +283,9 @@ lu_panel_cluster_kernel(T* __restrict__ A, int N, int j0, int nb, int* __restric
                 for (int k = 0; k < 4; ++k) {
                     const int rr = rr0 + 8 * k;
                     const T l = Num<T>::mul(lane_bcast<T>(cur[k], jj), pinv);
-                    if (rr < nrows && row_begin + rr > j) {
-                        if (lane == jj) chunk[rr * LU_LD + lane] = l;
-                        else if (lane > jj) chunk[rr * LU_LD + lane] = Num<T>::sub(cur[k], Num<T>::mul(l, uj));
-                    }
+                    const T upd = Num<T>::sub(cur[k], Num<T>::mul(l, uj));
+                    const T nv = lane == jj ? l : (lane > jj ? upd : cur[k]);       // selects: no divergence inside the warp
+                    if (rr < nrows && row_begin + rr > j) chunk[rr * LU_LD + lane] = nv;
                 }
             }
         }
@@ -347,6 +339,28 @@ __global__ void iota_kernel(int n, int* p) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
 }
 
+// perm = the row permutation accumulated by the interchanges ipiv[0..N-1] (applied in order to the identity), built
+// once after the factorisation: in shared memory while N ints fit, in global memory otherwise; one thread, N swaps.
+__global__ void perm_from_ipiv_kernel(int N, const int* __restrict__ ipiv, int* __restrict__ perm, int in_smem) {
+    extern __shared__ int perm_s[];
+    int* pp = in_smem ? perm_s : perm;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) pp[i] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < N; ++j) {
+            const int piv = ipiv[j];
+            if (piv != j) {
+                const int t = pp[j];
+                pp[j] = pp[piv];
+                pp[piv] = t;
+            }
+        }
+    }
+    __syncthreads();
+    if (in_smem)
+        for (int i = threadIdx.x; i < N; i += blockDim.x) perm[i] = perm_s[i];
+}
+
 template <typename T>
 static int lu_factor_impl(sktt_ctx* ctx, int dtype, int N, T* A, int* ipiv, int* info_host) {
     int* perm = ipiv + N;
@@ -358,8 +372,6 @@ static int lu_factor_impl(sktt_ctx* ctx, int dtype, int N, T* A, int* ipiv, int*
     PanelCand<T>* cand = (PanelCand<T>*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
     T* rowj = (T*)((char*)cand + 2 * (size_t)G_max * sizeof(PanelCand<T>));
     SKTT_CUDA(ctx, cudaMemsetAsync(info_dev, 0, sizeof(int), ctx->stream));
-    iota_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(N, perm);
-    SKTT_LAUNCH_CHECK(ctx);
     const size_t smem = (size_t)LU_ROWS_PER_CTA * LU_LD * sizeof(T);
     static bool configured = false;
     if (!configured) {
@@ -408,6 +420,11 @@ static int lu_factor_impl(sktt_ctx* ctx, int dtype, int N, T* A, int* ipiv, int*
             g.beta[0] = 1.0;
             SKTT_TRY(sktt_gemm_run(ctx, dtype, g));
         }
+    }
+    {
+        const int in_smem = (size_t)N * sizeof(int) <= 40 * 1024 ? 1 : 0;
+        perm_from_ipiv_kernel<<<1, 256, in_smem ? (size_t)N * sizeof(int) : 0, ctx->stream>>>(N, ipiv, perm, in_smem);
+        SKTT_LAUNCH_CHECK(ctx);
     }
     if (info_host) {
         SKTT_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
