@@ -298,32 +298,61 @@ lu_panel_cluster_kernel(T* __restrict__ A, int N, int j0, int nb, int* __restric
     cluster.sync();                                            // no CTA leaves while another may still push into it
 }
 
-// row interchanges outside the panel + U12 = L11^{-1} A12 (thread per column)
+// row interchanges outside the panel + U12 = L11^{-1} A12 (thread per column).  The nb interchanges of the panel touch at
+// most 2 nb rows; their net effect is worked out once per CTA on an index array (cur[q] = which of those rows ends up at
+// position q), so a thread gathers its column's <= 2 nb entries with independent loads into shared memory and scatters them
+// once, instead of walking through nb dependent load-load-store-store swaps in global memory.
+#define LU_TRSM_THREADS 128
+
 template <typename T>
-__global__ void lu_swap_trsm_kernel(T* __restrict__ A, int N, int j0, int nb, const int* __restrict__ ipiv) {
+__global__ void __launch_bounds__(LU_TRSM_THREADS)
+lu_swap_trsm_kernel(T* __restrict__ A, int N, int j0, int nb, const int* __restrict__ ipiv) {
+    extern __shared__ unsigned char trsm_raw[];
+    T* vals = (T*)trsm_raw;                                    // [2 * LU_NB][LU_TRSM_THREADS]
     __shared__ T L11[LU_NB][LU_NB + 1];
-    __shared__ int piv[LU_NB];
-    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) L11[e / nb][e % nb] = A[(size_t)(j0 + e / nb) * N + j0 + e % nb];
-    if (threadIdx.x < nb) piv[threadIdx.x] = ipiv[j0 + threadIdx.x];
+    __shared__ int rows_s[2 * LU_NB], cur_s[2 * LU_NB], ns_s;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < nb * nb; e += blockDim.x) L11[e / nb][e % nb] = A[(size_t)(j0 + e / nb) * N + j0 + e % nb];
+    if (tid == 0) {
+        int ns = nb;
+        for (int k = 0; k < nb; ++k) {
+            rows_s[k] = j0 + k;
+            cur_s[k] = k;
+        }
+        for (int k = 0; k < nb; ++k) {
+            const int p = ipiv[j0 + k];
+            int q;
+            if (p < j0 + nb) q = p - j0;                       // pivots are rows >= j0 + k
+            else {
+                for (q = nb; q < ns; ++q)
+                    if (rows_s[q] == p) break;
+                if (q == ns) {
+                    rows_s[ns] = p;
+                    cur_s[ns] = ns;
+                    ++ns;
+                }
+            }
+            const int t = cur_s[k];
+            cur_s[k] = cur_s[q];
+            cur_s[q] = t;
+        }
+        ns_s = ns;
+    }
     __syncthreads();
+    const int ns = ns_s;
     const int j1 = j0 + nb;
     const int ncols = N - nb;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ncols; t += gridDim.x * blockDim.x) {
-        int c = t < j0 ? t : t + nb;
-        for (int k = 0; k < nb; ++k) {
-            int p = piv[k];
-            if (p != j0 + k) {
-                T a = A[(size_t)(j0 + k) * N + c], b = A[(size_t)p * N + c];
-                A[(size_t)(j0 + k) * N + c] = b;
-                A[(size_t)p * N + c] = a;
-            }
-        }
+    for (int t = blockIdx.x * blockDim.x + tid; t < ncols; t += gridDim.x * blockDim.x) {
+        const int c = t < j0 ? t : t + nb;
+        for (int q = 0; q < ns; ++q) vals[q * LU_TRSM_THREADS + tid] = A[(size_t)rows_s[q] * N + c];
+        for (int q = nb; q < ns; ++q)
+            if (cur_s[q] != q) A[(size_t)rows_s[q] * N + c] = vals[cur_s[q] * LU_TRSM_THREADS + tid];
         if (c >= j1) {
             T x[LU_NB];
 #pragma unroll
             for (int i = 0; i < LU_NB; ++i) {
                 if (i < nb) {
-                    T v = A[(size_t)(j0 + i) * N + c];
+                    T v = vals[cur_s[i] * LU_TRSM_THREADS + tid];
 #pragma unroll
                     for (int k = 0; k < LU_NB; ++k)
                         if (k < i) v = Num<T>::sub(v, Num<T>::mul(L11[i][k], x[k]));
@@ -331,6 +360,9 @@ __global__ void lu_swap_trsm_kernel(T* __restrict__ A, int N, int j0, int nb, co
                     A[(size_t)(j0 + i) * N + c] = v;
                 }
             }
+        } else {
+            for (int i = 0; i < nb; ++i)
+                if (cur_s[i] != i) A[(size_t)(j0 + i) * N + c] = vals[cur_s[i] * LU_TRSM_THREADS + tid];
         }
     }
 }
@@ -373,11 +405,13 @@ static int lu_factor_impl(sktt_ctx* ctx, int dtype, int N, T* A, int* ipiv, int*
     T* rowj = (T*)((char*)cand + 2 * (size_t)G_max * sizeof(PanelCand<T>));
     SKTT_CUDA(ctx, cudaMemsetAsync(info_dev, 0, sizeof(int), ctx->stream));
     const size_t smem = (size_t)LU_ROWS_PER_CTA * LU_LD * sizeof(T);
+    const size_t trsm_smem = (size_t)2 * LU_NB * LU_TRSM_THREADS * sizeof(T);
     static bool configured = false;
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_swap_trsm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem));
         configured = true;
     }
     for (int j0 = 0; j0 < N; j0 += LU_NB) {
@@ -407,8 +441,8 @@ static int lu_factor_impl(sktt_ctx* ctx, int dtype, int N, T* A, int* ipiv, int*
         }
         ctx->launches++;
         if (N - nb > 0) {
-            int blocks = (N - nb + 127) / 128;
-            lu_swap_trsm_kernel<T><<<blocks, 128, 0, ctx->stream>>>(A, N, j0, nb, ipiv);
+            int blocks = (N - nb + LU_TRSM_THREADS - 1) / LU_TRSM_THREADS;
+            lu_swap_trsm_kernel<T><<<blocks, LU_TRSM_THREADS, trsm_smem, ctx->stream>>>(A, N, j0, nb, ipiv);
             SKTT_LAUNCH_CHECK(ctx);
         }
         int j1 = j0 + nb;
