@@ -173,6 +173,8 @@ def run_ours(args, cfg):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # the version banner goes to stdout, next to the JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from scikit_tt_b200 import TT
     from scikit_tt_b200.solvers import sle
