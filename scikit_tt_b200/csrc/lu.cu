@@ -367,9 +367,6 @@ lu_swap_trsm_kernel(T* __restrict__ A, int N, int j0, int nb, const int* __restr
     }
 }
 
-__global__ void iota_kernel(int n, int* p) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
-}
 
 // perm = the row permutation accumulated by the interchanges ipiv[0..N-1] (applied in order to the identity), built
 // once after the factorisation: in shared memory while N ints fit, in global memory otherwise; one thread, N swaps.
