@@ -237,37 +237,52 @@ def mals(operator, initial_guess, right_hand_side, repeats=1, solver='solve', th
 
 
 def _run_mals(st, repeats, solver, threshold, max_rank):
+    """Warm starts as in _sweeps_als: the reference keeps only U (forward, sle.py:620) resp. V (backward, sle.py:645) of
+    the truncated SVD and drops diag(s) V resp. U diag(s); here that factor -- recovered as U^H u resp. u V^H -- stands in
+    for the neighbouring core when the starting vector of the next two-site system is formed, so the matrix-free solve
+    starts from the sweep's current (truncated) iterate.  The micro systems and their solutions are unchanged."""
     dev, d, x = st.dev, st.d, st.x
     for i in range(d - 1, 0, -1):                                         # sle.py:148-151
         st.right(i)
     for _ in range(repeats):
+        carry = None                                                      # diag(s) V of the last split, as core i + 1
         for i in range(d - 1):                                            # sle.py:160-172
             st.left(i)
             if i < d - 2:
-                u, (r, n, n2, r3) = _micro_mals(st, i, solver)
-                U, S, Vh, k = dev.svd(u.reshape(r * n, n2 * r3), threshold=threshold, max_rank=max_rank)   # sle.py:603-614
-                x[i] = U[:, :k].contiguous().reshape(r, n, k)             # sle.py:616-620
+                u, (r, n, n2, r3) = _micro_mals(st, i, solver, left=carry)
+                mat = u.reshape(r * n, n2 * r3)
+                U, S, Vh, k = dev.svd(mat, threshold=threshold, max_rank=max_rank)   # sle.py:603-614
+                uk = U[:, :k].contiguous()
+                x[i] = uk.reshape(r, n, k)                                # sle.py:616-620
+                carry = dev.matmul(uk, mat, opa='C').reshape(k, n2, r3) if mat.numel() > _local.DENSE_LIMIT else None
+        left, right = carry, None
         for i in range(d - 2, -1, -1):                                    # sle.py:175-186
             st.right(i + 1)
-            u, (r, n, n2, r3) = _micro_mals(st, i, solver)
+            u, (r, n, n2, r3) = _micro_mals(st, i, solver, left=left, right=right)
+            left = None
             mat = u.reshape(r * n, n2 * r3)
             U, S, Vh, k = dev.svd(mat, threshold=threshold, max_rank=max_rank)                             # sle.py:626-639
             vh = Vh[:k, :].contiguous()
             x[i + 1] = vh.reshape(k, n2, r3)                              # sle.py:645
+            right = None
             if i == 0:
                 x[i] = dev.matmul(mat, vh, opb='C').reshape(r, n, k)      # U diag(s), sle.py:647-650
+            elif mat.numel() > _local.DENSE_LIMIT:
+                right = dev.matmul(mat, vh, opb='C').reshape(r, n, k)     # U diag(s) as core i of the next two-site system
 
 
-def _micro_mals(st, i, solver):
+def _micro_mals(st, i, solver, left=None, right=None):
+    """`left` / `right` stand in for x[i] / x[i + 1] when the starting vector is formed (see _run_mals)."""
     dev = st.dev
     L, R, A1, A2 = st.Lop[i], st.Rop[i + 1], st.A[i], st.A[i + 1]
     f = dev.micro_rhs_mals(st.Lrhs[i], st.b[i], st.b[i + 1], st.Rrhs[i + 1])   # sle.py:464-470
     r, n, n2, r3 = L.shape[0], A1.shape[2], A2.shape[2], R.shape[0]
     op = dev.local_op(L, A1, R, A2=A2)
     guess = None
-    xi, xj = st.x[i], st.x[i + 1]
+    xi = left if left is not None else st.x[i]
+    xj = right if right is not None else st.x[i + 1]
     if xi.dim() == 3 and xj.dim() == 3 and xi.shape[0] == r and xj.shape[2] == r3 and xi.shape[2] == xj.shape[0] \
-            and r * n * n2 * r3 > _local.DENSE_LIMIT:
+            and tuple(xi.shape[1:2]) == (n,) and tuple(xj.shape[1:2]) == (n2,) and r * n * n2 * r3 > _local.DENSE_LIMIT:
         guess = dev.matmul(xi.reshape(r * n, xi.shape[2]), xj.reshape(xj.shape[0], n2 * r3))
     u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_mals(L, A1, A2, R), op, f.reshape(r, n, n2, r3), guess,
                            st.cache)
