@@ -125,7 +125,7 @@ extern "C" int sktt_gauge_factor(sktt_ctx* ctx, int dtype, int64_t L, int64_t ni
     if (!ctx || !A || !B || !C) return SKTT_ERR_ARG;
     if (dtype != SKTT_F64 || L < 1 || ni < 1 || nj < 1 || ni > 64 || nj > 64 || L > 0x7fffffff)
         return sktt_fail(ctx, SKTT_ERR_ARG, "gauge_factor: f64, short extents <= 64");
-    int chunk = 64;
+    int chunk = GAUGE_TL;                                      // one tile per CTA while the CTAs fit the SMs: shortest serial chain
     int G = (int)((L + chunk - 1) / chunk);
     if (G > ctx->sm_count) {
         chunk = (int)(((L + ctx->sm_count - 1) / ctx->sm_count + GAUGE_TL - 1) / GAUGE_TL * GAUGE_TL);

@@ -174,6 +174,7 @@ rhs_left_small_kernel(int p, int r, int m, int p2, int r2, const T* __restrict__
         T acc[RHS_PMAX];
 #pragma unroll
         for (int q2 = 0; q2 < RHS_PMAX; ++q2) acc[q2] = Num<T>::zero();
+#pragma unroll 2
         for (long long row = row0 + warp; row < row1; row += 8) {
             const int c = (int)(row / m), mm = (int)(row % m);
             const T xv = c2 < r2 ? Num<T>::conj(x[row * r2 + c2]) : Num<T>::zero();
@@ -232,6 +233,7 @@ rhs_right_small_kernel(int p, int r, int m, int p2, int r2, const T* __restrict_
     T acc[RHS_PMAX];
 #pragma unroll
     for (int q = 0; q < RHS_PMAX; ++q) acc[q] = Num<T>::zero();
+#pragma unroll 4
     for (long long e = tid; e < len; e += 256) {
         const int mm = (int)(e / r2), c2 = (int)(e % r2);
         const T xv = Num<T>::conj(xr[e]);
