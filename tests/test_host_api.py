@@ -95,3 +95,30 @@ def test_ortho_argument_validation():
             fn(start_index="a")
         with pytest.raises(TypeError):
             fn(end_index="b")
+
+
+def test_warm_start_plumbing_of_the_sweep():
+    """Host logic of the warm starts (solvers/sle.py): which solver settings want a starting vector, and how the gauge factor
+    of the neighbour that was just orthonormalised is pushed into the next core (left: factor @ core, right: core @ factor;
+    mismatching factors are ignored).  The device product is replaced by torch on the CPU here."""
+    import torch
+    from scikit_tt_b200.solvers import sle, _local
+
+    class FakeDev:
+        def gauge_push(self, carry, core, left):
+            return carry @ core if left else core @ carry
+
+    assert sle._wants_guess('cg', 10) and sle._wants_guess('gmres', 10)
+    assert not sle._wants_guess('dense', 10 ** 9)
+    assert sle._wants_guess('solve', _local.DENSE_LIMIT + 1) and not sle._wants_guess('solve', _local.DENSE_LIMIT)
+    g = torch.Generator().manual_seed(0)
+    core = torch.randn(5, 7, 3, dtype=torch.float64, generator=g)
+    R = torch.randn(4, 5, dtype=torch.float64, generator=g)                   # k x r: from the QR of the core to the left
+    out = sle._pushed(FakeDev(), R, core, left=True)
+    assert out.shape == (4, 7, 3) and torch.allclose(out, torch.einsum('ka,anb->knb', R, core))
+    Rp = torch.randn(3, 2, dtype=torch.float64, generator=g)                  # r2 x k: from the RQ of the core to the right
+    out = sle._pushed(FakeDev(), Rp, core, left=False)
+    assert out.shape == (5, 7, 2) and torch.allclose(out, torch.einsum('anb,bk->ank', core, Rp))
+    assert sle._pushed(FakeDev(), None, core, left=True) is None
+    assert sle._pushed(FakeDev(), torch.zeros(4, 6, dtype=torch.float64), core, left=True) is None     # rank changed
+    assert sle._pushed(FakeDev(), torch.zeros(4, 2, dtype=torch.float64), core, left=False) is None
