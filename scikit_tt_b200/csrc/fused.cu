@@ -1470,17 +1470,33 @@ __global__ void __launch_bounds__(THREADS) stack_persistent_kernel(StackParams a
         first2 = false;
     }
     gsync();
-    // out[e] = sum over tiles, in tile order; eight lanes share an entry (16 tiles each for 128 tiles), fixed shuffle tree
+    // out[e] = sum over the tile partials in a fixed order.  A CTA takes 32 consecutive entries at a time: lanes run along the
+    // entries (coalesced 256-byte rows of the partials -- one sector per 4 lanes instead of one per lane), sixteen warps
+    // split the tiles with all their loads in flight at once, warp 0 adds the sixteen sums in warp order.
     const int E = 64 * 3 * 64;
-    const long long gtid = (long long)cta * THREADS + tid, gthreads = (long long)G * THREADS;
-    const int sub = (int)(gtid & 7);
-    for (long long e = gtid >> 3; e < E + 3; e += gthreads >> 3) {         // + 3: keeps whole warps in the shuffles
-        double sacc = 0.0;
-        if (e < E)
-            for (int t = sub; t < tiles2; t += 8) sacc += __ldcg(a.part + (size_t)t * E + e);
+    __shared__ double red[16][32];
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int c = cta; c < E / 32; c += G) {
+        const int e = c * 32 + lane;
+        if (warp < 16) {
+            double v[8];
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-        if (e < E && sub == 0) a.out[e] = sacc;
+            for (int k = 0; k < 8; ++k) {
+                const int t = warp + 16 * k;
+                v[k] = t < tiles2 ? __ldcg(a.part + (size_t)t * E + e) : 0.0;
+            }
+            double sacc = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+            for (int t = warp + 128; t < tiles2; t += 16) sacc += __ldcg(a.part + (size_t)t * E + e);
+            red[warp][lane] = sacc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double sacc = red[0][lane];
+#pragma unroll
+            for (int w = 1; w < 16; ++w) sacc += red[w][lane];
+            a.out[e] = sacc;
+        }
+        __syncthreads();
     }
 }
 }  // namespace
