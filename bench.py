@@ -40,34 +40,7 @@ NCU_MATVEC_DRAM_BYTES = 2345472 + 9412352   # profiles/r01_ncu_final_full.txt, o
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def laplace_cores(d, n, c=1e-3):
-    S = 2 * np.eye(n) - np.eye(n, k=1) - np.eye(n, k=-1)
-    D = np.sqrt(c) * 0.5 * (np.eye(n, k=1) - np.eye(n, k=-1))
-    I, Z = np.eye(n), np.zeros((n, n))
-
-    def core(rows):
-        out = np.zeros((len(rows), n, n, len(rows[0])))
-        for i, row in enumerate(rows):
-            for j, blk in enumerate(row):
-                out[i, :, :, j] = blk
-        return out
-    first = core([[S, D, I]])
-    mid = core([[I, Z, Z], [D, Z, Z], [S, D, I]])
-    last = core([[I], [D], [S]])
-    return [first] + [mid.copy() for _ in range(d - 2)] + [last]
-
-
-def workload_cores(d, n, r):
-    op = laplace_cores(d, n)
-    rng0, rng1 = np.random.default_rng(0), np.random.default_rng(1)
-    rhs = [rng0.standard_normal((1, n, 1, 1)) for _ in range(d)]
-    ranks = [1] + [r] * (d - 1) + [1]
-    for i in range(1, d):                      # no rank may exceed what the unfoldings support
-        ranks[i] = min(ranks[i], ranks[i - 1] * n)
-    for i in range(d - 1, 0, -1):
-        ranks[i] = min(ranks[i], ranks[i + 1] * n)
-    x0 = [rng1.standard_normal((ranks[i], n, 1, ranks[i + 1])) for i in range(d)]
-    return op, rhs, x0
+from workloads import laplace_cores, workload_cores  # noqa: E402,F401  (the operator families live in workloads.py)
 
 
 def stack_flops(r, R, n, r2, R2):

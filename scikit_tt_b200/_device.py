@@ -26,6 +26,25 @@ def dtype_code(t):
     raise TypeError(f"scikit_tt_b200 supports float64 and complex128 only, got {t.dtype}")
 
 
+class _GuardedLib:
+    """Proxy of the ctypes library that makes the context's device current around every C-ABI call.  Only installed when
+    one process drives more than one GPU (get_device); the usual one-process-per-GPU layout calls the library directly."""
+
+    def __init__(self, lib, index):
+        self._lib, self._index = lib, index
+
+    def __getattr__(self, name):
+        fn, idx = getattr(self._lib, name), self._index
+
+        def call(*args):
+            if torch.cuda.current_device() != idx:
+                with torch.cuda.device(idx):
+                    return fn(*args)
+            return fn(*args)
+        setattr(self, name, call)
+        return call
+
+
 class Device:
     """Thin object wrapper over the C-ABI; methods mirror include/sktt_b200.h one to one."""
 
@@ -493,19 +512,33 @@ class Device:
         return W, V
 
     def eig_shift_invert(self, M, sigma, k, B=None, ncv=None, tol=1e-13, max_restarts=20):
-        """k eigenpairs of (M, B) closest to sigma; M is destroyed. Returns (lam[k], vecs[N,k]) complex128."""
+        """k eigenpairs of (M, B) closest to sigma; M is destroyed. Returns (lam[k], vecs[N,k]) complex128.
+
+        The reference's `lin.eig` always returns exact pairs and `splin.eigs` raises ArpackNoConvergence; here a run that
+        ends with fewer than k converged Ritz pairs (clustered spectrum near sigma, exhausted Krylov space) is repeated
+        once with the largest Krylov dimension and more restarts, and raises numpy.linalg.LinAlgError if that fails too --
+        unconverged pairs are never handed to the sweep."""
         N = M.shape[0]
         if ncv is None:
             ncv = min(N, max(2 * k + 1, 20))
         ncv = min(int(ncv), 64, N)
+        keep = (M.clone(), B) if ncv < N else None
         lam = self.empty((k,), torch.complex128)
         vecs = self.empty((N, k), torch.complex128)
-        w = self.work(self.lib.sktt_eig_si_work(N, k, ncv), torch.complex128, tag="eig")
         nconv = C.c_int(0)
-        self._check(self.lib.sktt_eig_shift_invert(self.h, dtype_code(M), N, _ptr(M), _ptr(B), float(sigma), k, ncv,
-                                                   float(tol), int(max_restarts), _ptr(lam), _ptr(vecs), _ptr(w),
-                                                   C.byref(nconv)))
+
+        def run(mat, ncv, max_restarts):
+            w = self.work(self.lib.sktt_eig_si_work(N, k, ncv), torch.complex128, tag="eig")
+            self._check(self.lib.sktt_eig_shift_invert(self.h, dtype_code(mat), N, _ptr(mat), _ptr(B), float(sigma), k, ncv,
+                                                       float(tol), int(max_restarts), _ptr(lam), _ptr(vecs), _ptr(w),
+                                                       C.byref(nconv)))
+        run(M, ncv, max_restarts)
+        if nconv.value < k and keep is not None:
+            run(keep[0], min(64, N), 5 * max_restarts)
         self.last_eig_nconv = nconv.value
+        if nconv.value < k:
+            raise np.linalg.LinAlgError(f"shift-invert Arnoldi: {nconv.value} of {k} eigenpairs near sigma = {sigma} converged "
+                                        f"(N = {N})")
         return lam, vecs
 
     # ------------------------------------------------------------------ misc
@@ -610,6 +643,10 @@ def get_device(index=None):
     if dev is None:
         dev = Device(idx)
         _contexts[idx] = dev
+        if len(_contexts) > 1:                                 # several GPUs in one process: guard every call
+            for other in _contexts.values():
+                if not isinstance(other.lib, _GuardedLib):
+                    other.lib = _GuardedLib(other.lib, other.index)
     else:
         # follow torch's current stream
         with torch.cuda.device(idx):

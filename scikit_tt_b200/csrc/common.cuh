@@ -48,6 +48,13 @@ static inline int sktt_fail(sktt_ctx* ctx, int code, const char* fmt, const char
         SKTT_CUDA(ctx, cudaGetLastError());                                                      \
     } while (0)
 
+// cudaFuncSetAttribute opt-ins (dynamic shared memory above 48 KB, cluster sizes) are per device: one flag per device
+// index, so that a second GPU driven from the same process gets its own opt-in (one context = one device)
+#define SKTT_MAX_DEVICES 64
+#define SKTT_ONCE_PER_DEVICE(ctx)                                                                \
+    static bool once_per_device_[SKTT_MAX_DEVICES] = {false};                                    \
+    bool& configured = once_per_device_[(ctx)->device & (SKTT_MAX_DEVICES - 1)]
+
 #define SKTT_TRY(expr)                                                                           \
     do {                                                                                         \
         int s__ = (expr);                                                                        \

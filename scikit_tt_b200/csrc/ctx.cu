@@ -9,7 +9,14 @@ extern "C" int sktt_ctx_create(int device, void* cuda_stream, sktt_ctx** out) {
     *out = nullptr;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return SKTT_ERR_CUDA;
+    int previous = -1;
+    cudaGetDevice(&previous);
     if (cudaSetDevice(device) != cudaSuccess) return SKTT_ERR_CUDA;
+    // the caller's current device is restored on every exit path (torch tracks it per thread)
+    struct Restore {
+        int dev;
+        ~Restore() { if (dev >= 0) cudaSetDevice(dev); }
+    } restore{previous};
     sktt_ctx* ctx = new sktt_ctx();
     ctx->device = device;
     ctx->stream = (cudaStream_t)cuda_stream;

@@ -173,7 +173,9 @@ __global__ void ritz_select_kernel(int m, int k, double sigma, const cplx* __res
         lam[s] = C::add(make_cplx(sigma, 0.0), C::div(C::one(), th));
         for (int r = 0; r < m; ++r) Ysel[r * k + s] = Y[r * m + best];
         double res = hn * cabs_(Y[(m - 1) * m + best]);
-        if (res <= tol * bv) conv++;
+        // a Ritz value of exactly zero is the footprint of an exhausted Krylov space (Arnoldi breakdown zeroes the next
+        // basis vector): lambda = sigma + 1/0 is not an eigenvalue, never count it as converged
+        if (bv > 0.0 && res <= tol * bv) conv++;
     }
     *nconv = conv;
 }
@@ -299,7 +301,7 @@ static int eig_si_impl(sktt_ctx* ctx, int dtype, long long N, T* Mat, const T* B
     SKTT_TRY(sktt_lu_factor(ctx, dtype, N, Mat, ipiv, &info));
     if (info != 0) return sktt_fail(ctx, SKTT_ERR_SINGULAR, "eig_shift_invert: (M - sigma B) is exactly singular");
 
-    static bool configured = false;
+    SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(hess_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;

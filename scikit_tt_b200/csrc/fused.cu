@@ -1339,7 +1339,7 @@ int sktt_fused_matvec_tiled_dots(sktt_ctx* ctx, long long r, long long R, long l
                                  double* dot_part, unsigned* counter, double* dots_out, const int* skip) {
     const int M1 = (int)(R * r), K1 = (int)r;
     const size_t smem1 = s1_smem_bytes(K1);
-    static bool configured = false;
+    SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(mv_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SKTT_CUDA(ctx, cudaFuncSetAttribute(mv_stage23_kernel<3, 64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1414,7 +1414,7 @@ int sktt_fused_pcg_persistent(sktt_ctx* ctx, long long r, long long R, long long
     a.part = part;
     a.out = out_dev;
     const size_t smem = pcg_phase_bytes((int)r) + pcg_rres_bytes() + 128;
-    static bool configured = false;
+    SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(pcg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         configured = true;
@@ -1519,7 +1519,7 @@ int sktt_fused_stack_update(sktt_ctx* ctx, long long r, long long R, long long m
     a.part = part;
     a.out = out;
     const size_t smem = pcg_phase_bytes((int)r) + 128;
-    static bool configured = false;
+    SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(stack_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;

@@ -368,7 +368,7 @@ template <int BM, int BN, int WM, int WN, int STAGES>
 static int launch_dmma(sktt_ctx* ctx, GemmParams& p) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr size_t smem = (size_t)STAGES * 16 * ((BM + 4) + (BN + 4)) * sizeof(double);
-    static bool configured = false;
+    SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WM, WN, STAGES>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -421,7 +421,7 @@ static int cg_tiled_precond_setup(sktt_ctx* ctx, const KOp& op, const CgTiledBuf
     const sktt_local_op& o = op.op;
     const int n = (int)o.n;
     const size_t smem = ((size_t)2 * n * (n + 1) + o.R + o.R2) * sizeof(double);
-    static bool configured = false;
+    SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(mode_precond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SKTT_CUDA(ctx, cudaFuncSetAttribute(mode_precond_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));

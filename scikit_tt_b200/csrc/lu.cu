@@ -403,7 +403,7 @@ static int lu_factor_impl(sktt_ctx* ctx, int dtype, int N, T* A, int* ipiv, int*
     SKTT_CUDA(ctx, cudaMemsetAsync(info_dev, 0, sizeof(int), ctx->stream));
     const size_t smem = (size_t)LU_ROWS_PER_CTA * LU_LD * sizeof(T);
     const size_t trsm_smem = (size_t)2 * LU_NB * LU_TRSM_THREADS * sizeof(T);
-    static bool configured = false;
+    SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1134,7 +1134,7 @@ static int cholqr_launch_nt(sktt_ctx* ctx, int m, int n, const T* src, QrView lv
     T* rstack = gfull + E;
     T* ysk = rstack + (size_t)(CQ_MAX_PASSES + 1) * E;
     int* status = (int*)((char*)ctx->scratch + CQ_STATUS_OFF);
-    static bool configured = false;
+    SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(cholqr_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         configured = true;

@@ -277,7 +277,7 @@ static int jacobi_run(sktt_ctx* ctx, T* X, int L, int mw, int n, int* sweeps_dev
     const double tol = 2.220446049250313e-16 * sqrt((double)(mw > 4 ? mw : 4));
     int* counters = (int*)((char*)ctx->scratch + SKTT_SCRATCH_COUNTER_OFF + 256);  // 64 ints
     SKTT_CUDA(ctx, cudaMemsetAsync(counters, 0, 64 * sizeof(int), ctx->stream));
-    static bool configured = false;
+    SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(jacobi_sweep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             200 * 1024));
@@ -337,7 +337,7 @@ static int svd_impl(sktt_ctx* ctx, int dtype, int m, int n, const T* A, T* U, do
     SKTT_TRY(jacobi_run<T>(ctx, X, L, mw, nb, sweeps_dev));
     if (nb > 4096) return sktt_fail(ctx, SKTT_ERR_ARG, "svd: min(m, n) > 4096 not supported");
     size_t post_smem = (size_t)nb * (sizeof(double) + sizeof(int)) + 16 + (size_t)mw * sizeof(T);
-    static bool configured = false;
+    SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(jacobi_post_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
@@ -444,7 +444,7 @@ static int eigh_impl(sktt_ctx* ctx, int N, T* Mat, double* W, T* V, int* sweeps_
     SKTT_LAUNCH_CHECK(ctx);
     SKTT_TRY(jacobi_run<T>(ctx, X, 2 * N, N, N, sweeps_dev));
     size_t post_smem = (size_t)N * (sizeof(double) + sizeof(int)) + 16 + (size_t)N * sizeof(T);
-    static bool configured = false;
+    SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(jacobi_post_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;

@@ -113,6 +113,7 @@ def als(operator, initial_guess, right_hand_side, repeats=1, solver='solve'):
     dense path while r*n*r' <= _local.DENSE_LIMIT and the matrix-free path above it; 'dense', 'cg',
     'gmres' force one.  Returns a new TT; inputs are not modified.
     """
+    _local.reset_stats()
     st = _State(operator, initial_guess, right_hand_side)
     st.stream_results = True
     _run_als(st, repeats, solver)
@@ -231,6 +232,7 @@ def _micro_als(st, i, solver, guess=None):
 
 def mals(operator, initial_guess, right_hand_side, repeats=1, solver='solve', threshold=1e-12, max_rank=np.inf):
     """MALS sweeps (two-site micro systems, truncated-SVD core splitting; sle.py:98-191)."""
+    _local.reset_stats()
     st = _State(operator, initial_guess, right_hand_side)
     _run_mals(st, repeats, solver, threshold, max_rank)
     return st.result()
@@ -287,3 +289,88 @@ def _micro_mals(st, i, solver, left=None, right=None):
     u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_mals(L, A1, A2, R), op, f.reshape(r, n, n2, r3), guess,
                            st.cache)
     return u, (r, n, n2, r3)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's private per-micro-step helpers under their own names and call conventions (sle.py:194-472; imported by
+# name by its TDVP integrators, ode.py:13): host numpy arrays in the stack lists and TT objects in, numpy out, the
+# arithmetic on the device through the same C-ABI entry points the sweeps use.  Stateless and therefore slower than the
+# resident sweep (one upload / download per call); they exist for drop-in callers and for parity tests that read like the
+# reference's.
+def _up(dev, a, dtype):
+    return dev.upload_many([np.asarray(a)], dtype)[0]
+
+
+def _helper_dtype(*arrays):
+    return torch.complex128 if any(np.iscomplexobj(a) for a in arrays) else torch.float64
+
+
+def __construct_stack_left_op(i, stack_left_op, operator, solution):
+    if i == 0:
+        stack_left_op[i] = np.array([1], ndmin=3)                        # sle.py:213
+        return
+    dev = _device.get_device()
+    x, A, L = solution.cores[i - 1][:, :, 0, :], operator.cores[i - 1], stack_left_op[i - 1]
+    dt = _helper_dtype(x, A, L)
+    stack_left_op[i] = dev.download(dev.stack_left_op(_up(dev, L, dt), _up(dev, x, dt), _up(dev, A, dt)))
+
+
+def __construct_stack_right_op(i, stack_right_op, operator, solution):
+    if i == operator.order - 1:
+        stack_right_op[i] = np.array([1], ndmin=3)                       # sle.py:269
+        return
+    dev = _device.get_device()
+    x, A, R = solution.cores[i + 1][:, :, 0, :], operator.cores[i + 1], stack_right_op[i + 1]
+    dt = _helper_dtype(x, A, R)
+    stack_right_op[i] = dev.download(dev.stack_right_op(_up(dev, R, dt), _up(dev, x, dt), _up(dev, A, dt)))
+
+
+def __construct_stack_left_rhs(i, stack_left_rhs, right_hand_side, solution):
+    if i == 0:
+        stack_left_rhs[i] = np.array([1], ndmin=2)                       # sle.py:241
+        return
+    dev = _device.get_device()
+    x, b, S = solution.cores[i - 1][:, :, 0, :], right_hand_side.cores[i - 1][:, :, 0, :], stack_left_rhs[i - 1]
+    dt = _helper_dtype(x, b, S)
+    stack_left_rhs[i] = dev.download(dev.stack_left_rhs(_up(dev, S, dt), _up(dev, b, dt), _up(dev, x, dt)))
+
+
+def __construct_stack_right_rhs(i, stack_right_rhs, right_hand_side, solution):
+    if i == right_hand_side.order - 1:
+        stack_right_rhs[i] = np.array([1], ndmin=2)                      # sle.py:298
+        return
+    dev = _device.get_device()
+    x, b, S = solution.cores[i + 1][:, :, 0, :], right_hand_side.cores[i + 1][:, :, 0, :], stack_right_rhs[i + 1]
+    dt = _helper_dtype(x, b, S)
+    stack_right_rhs[i] = dev.download(dev.stack_right_rhs(_up(dev, S, dt), _up(dev, b, dt), _up(dev, x, dt)))
+
+
+def __construct_micro_matrix_als(i, stack_left_op, stack_right_op, operator, solution):
+    dev = _device.get_device()
+    L, A, R = stack_left_op[i], operator.cores[i], stack_right_op[i]
+    dt = _helper_dtype(L, A, R)
+    return dev.download(dev.micro_matrix_als(_up(dev, L, dt), _up(dev, A, dt), _up(dev, R, dt)))
+
+
+def __construct_micro_matrix_mals(i, stack_left_op, stack_right_op, operator, solution):
+    dev = _device.get_device()
+    L, A1, A2, R = stack_left_op[i], operator.cores[i], operator.cores[i + 1], stack_right_op[i + 1]
+    dt = _helper_dtype(L, A1, A2, R)
+    return dev.download(dev.micro_matrix_mals(_up(dev, L, dt), _up(dev, A1, dt), _up(dev, A2, dt), _up(dev, R, dt)))
+
+
+def __construct_micro_rhs_als(i, stack_left_rhs, stack_right_rhs, right_hand_side, solution):
+    dev = _device.get_device()
+    bL, b, bR = stack_left_rhs[i], right_hand_side.cores[i][:, :, 0, :], stack_right_rhs[i]
+    dt = _helper_dtype(bL, b, bR)
+    f = dev.download(dev.micro_rhs_als(_up(dev, bL, dt), _up(dev, b, dt), _up(dev, bR, dt)))
+    return f.reshape(-1, 1)                                              # sle.py:428 (column vector)
+
+
+def __construct_micro_rhs_mals(i, stack_left_rhs, stack_right_rhs, right_hand_side, solution):
+    dev = _device.get_device()
+    bL, b1, b2, bR = (stack_left_rhs[i], right_hand_side.cores[i][:, :, 0, :], right_hand_side.cores[i + 1][:, :, 0, :],
+                      stack_right_rhs[i + 1])
+    dt = _helper_dtype(bL, b1, b2, bR)
+    f = dev.download(dev.micro_rhs_mals(_up(dev, bL, dt), _up(dev, b1, dt), _up(dev, b2, dt), _up(dev, bR, dt)))
+    return f.reshape(-1, 1)                                              # sle.py:470

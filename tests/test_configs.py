@@ -1,0 +1,252 @@
+"""Every BASELINE.json configuration as a parity test at the largest size the reference can still run (fixtures from the
+LIVE reference: tests/golden/make_config_golden.py), plus the size-independent properties at the named sizes.
+
+CPU part (no marker): the oracle is pinned to the new fixtures.  GPU part (@gpu): the CUDA path against fixtures / oracle.
+
+  C1  signaling_cascade(20), implicit Euler via sle.als, r = 4, FULL size (dense 1024^2 micro systems): per-step 1e-8.
+  C2  co_oxidation(20), evp.als 'eig', guesses of rank 16 / 24 / 32: the eigenvalues of the first micro steps (up to the
+      first full-size 768^2 / 1728^2 / 2592^2 micro matrix) against the reference's; later steps are chaotic in the
+      reference itself (tests/test_c2_noise.py and the recorded sequence in c2_first_step.npz, which wanders to |lambda| ~ 1e7).
+  C4  parity variant n = 16, R = 8 (SPD): sle.als at r = 32 (dense 16 384^2 micro systems) and sle.mals at r <= 8.
+  C5  mini batch of 8 CO pressures through the batch front end: identical to the one-at-a-time GPU path, first micro
+      steps equal to the oracle's, residual quality no worse than the oracle's.
+"""
+import numpy as np
+import pytest
+from threadpoolctl import threadpool_limits
+
+import workloads
+from oracle import sle as osle, evp as oevp, ode as oode, tt as ott
+from util import load, cores, rel_diff
+
+SOL_TOL = 1e-8
+VAL_TOL = 1e-10
+
+
+class _Stop(Exception):
+    pass
+
+
+def _oracle_first_lams(op, x0, limit):
+    seen = []
+    orig = oevp._local_eig
+
+    def spy(M, B, k, solver, sigma, real):
+        lam, vec = orig(M, B, k, solver, sigma, False)
+        seen.append((M.shape[0], complex(lam[0])))
+        if len(seen) >= limit:
+            raise _Stop()
+        return (np.real(lam) if real else lam), vec
+    oevp._local_eig = spy
+    try:
+        oevp.als(op, x0, repeats=1, conv_eps=0, solver='eig')
+    except _Stop:
+        pass
+    finally:
+        oevp._local_eig = orig
+    return seen
+
+
+# ------------------------------------------------------------------------------------------------ CPU: oracle pins
+def test_oracle_c1_full_first_step():
+    z = load("c1_full")
+    d = int(z["d"])
+    op, iv, guess = workloads.cascade_cores(d), workloads.cascade_initial_value(d), cores(z, "guess")
+    with threadpool_limits(limits=4):
+        sol = oode.implicit_euler(op, iv, guess, [1.0])
+    assert rel_diff(sol[1], cores(z, "step1")) < 1e-9
+
+
+def test_oracle_c2_first_steps_r16():
+    z, zc = load("c2_first_step"), load("c2_cooxidation20")
+    op = cores(zc, "op")
+    # from the fourth micro step on the reference is not reproducible against itself (fixture generated with 8 BLAS
+    # threads: 1.3503, one thread: 1.3902 -- the rank-16 guess is numerically rank 1 and LAPACK's null-space vectors enter)
+    with threadpool_limits(limits=1):
+        seen = _oracle_first_lams(op, cores(z, "r16/x0"), 3)
+    assert [s[0] for s in seen] == list(z["r16/N"][:3])
+    for (N, lam), ref in zip(seen, z["r16/lam"][:3]):
+        assert abs(lam - ref) <= 1e-6 * abs(ref), (N, lam, ref)
+
+
+def test_workload_families():
+    """Shapes and structural properties of the synthetic operator families (symmetry of C3 / C4-SPD, affine CO pressure)."""
+    op = workloads.laplace_cores(4, 8)
+    assert [c.shape for c in op] == [(1, 8, 8, 3), (3, 8, 8, 3), (3, 8, 8, 3), (3, 8, 8, 1)]
+    M = ott.matricize(op)
+    assert np.allclose(M, M.T) and np.linalg.eigvalsh(M).min() > 0
+    M = ott.matricize(workloads.c4_spd_cores(3, 4, 2))
+    assert np.allclose(M, M.T) and np.linalg.eigvalsh(M).min() > 0
+    a, b, c = (workloads.co_oxidation_cores(20, k) for k in (0.0, 1.0, 3.0))
+    assert [x.shape for x in a][:2] == [(1, 3, 3, 20), (20, 3, 3, 20)] and a[-1].shape == (20, 3, 3, 1)
+    assert all(np.allclose(x + 3.0 * (y - x), w) for x, y, w in zip(a, b, c))
+    # a CME generator: columns of the (small) full operator sum to zero
+    G = ott.matricize(workloads.co_oxidation_cores(3, 1e4))
+    assert np.abs(G.sum(axis=0)).max() < 1e-6 * np.abs(G).max()
+    full = workloads.add_identity(workloads.co_oxidation_cores(3, 1e4))
+    assert np.allclose(ott.matricize(full), np.eye(27) + G)
+    assert len(workloads.c5_pressures()) == 64 and workloads.capped_ranks(4, 3, 20) == [1, 3, 9, 3, 1]
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _T(c):
+    from scikit_tt_b200 import TT
+    return TT([np.array(x) for x in c])
+
+
+@pytest.mark.gpu
+def test_c1_full_size_per_step(dev):
+    """signaling_cascade(20), r = 4: each implicit Euler step from the reference's own previous state (one-repeat ALS on
+    this lossy problem amplifies rounding differences 3-50x per step) -- 1e-8 on the solution TT."""
+    from scikit_tt_b200.solvers import ode
+    z = load("c1_full")
+    d = int(z["d"])
+    op = _T(workloads.cascade_cores(d))
+    prev, g = _T(workloads.cascade_initial_value(d)), _T(cores(z, "guess"))
+    for k in range(1, 4):
+        nxt = ode.implicit_euler(op, prev, g, [1.0], progress=False)[1]
+        assert nxt.ranks == [1] + [4] * (d - 1) + [1]
+        assert rel_diff(nxt.cores, cores(z, f"step{k}")) < SOL_TOL, k
+        prev = g = _T(cores(z, f"step{k}"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("r", [16, 24, 32])
+def test_c2_first_micro_steps(dev, r):
+    """co_oxidation(20) at guess rank r.  (1) The eigenvalue each of the first three micro steps of the GPU sweep selects,
+    against the live reference's (from the fourth step on the reference is not reproducible against itself, see the CPU
+    test above).  (2) The full-size micro matrices (768^2 / 1728^2 / 2592^2): the oracle's own fourth micro matrix is handed
+    to the GPU eigen-solver, which must select the oracle's eigenvalue.  |M| ~ 1e9 and the wanted eigenvalue ~ 1, so values
+    are defined to ~ eps * |M| ~ 1e-7 absolute."""
+    from scikit_tt_b200.solvers import evp as gevp
+    z, zc = load("c2_first_step"), load("c2_cooxidation20")
+    op, x0 = cores(zc, "op"), cores(z, f"r{r}/x0")
+    eps = np.finfo(float).eps
+    seen = []
+    orig = gevp._local_eig
+
+    def spy(d, M, B, k, solver, sigma):
+        lam, vec = orig(d, M, B, k, solver, sigma)
+        seen.append((M.shape[0], complex(lam[0].item())))
+        if len(seen) >= 3:
+            raise _Stop()
+        return lam, vec
+    gevp._local_eig = spy
+    try:
+        gevp.als(_T(op), _T(x0), repeats=1, conv_eps=0, solver='eig')
+    except _Stop:
+        pass
+    finally:
+        gevp._local_eig = orig
+    assert [s[0] for s in seen] == list(z[f"r{r}/N"][:3])
+    for (N, lam), ref, amax in zip(seen, z[f"r{r}/lam"][:3], z[f"r{r}/absmax"][:3]):
+        assert abs(lam - ref) <= 50 * eps * amax, (N, lam, ref)
+    # the oracle's fourth micro matrix (first full-size one) through the GPU eigen-solver
+    mats = []
+    oorig = oevp._local_eig
+
+    def ospy(M, B, k, solver, sigma, real):
+        lam, vec = oorig(M, B, k, solver, sigma, False)
+        mats.append((M.copy(), complex(lam[0])))
+        if len(mats) >= 4:
+            raise _Stop()
+        return (np.real(lam) if real else lam), vec
+    oevp._local_eig = ospy
+    try:
+        oevp.als(op, x0, repeats=1, conv_eps=0, solver='eig')
+    except _Stop:
+        pass
+    finally:
+        oevp._local_eig = oorig
+    M, lam_o = mats[3]
+    assert M.shape[0] == int(z[f"r{r}/N"][3])
+    lam_g, vec = orig(dev, dev.to_device(M), None, 1, 'eig', 1)
+    assert abs(complex(lam_g[0].item()) - lam_o) <= 50 * eps * np.abs(M).max(), (lam_g, lam_o)
+    v = vec[:, 0].cpu().numpy()
+    assert np.linalg.norm(M @ v - complex(lam_g[0].item()) * v) <= 1e3 * eps * np.abs(M).max() * np.linalg.norm(v)
+
+
+@pytest.mark.gpu
+def test_c4_parity_als_r32(dev):
+    """n = 16, R = 8, r = 32: the reference's dense route (16 384^2 LU) and the matrix-free route against the live reference."""
+    from scikit_tt_b200.solvers import sle, _local
+    z = load("c4_parity")
+    d = int(z["als/d"])
+    op, rhs = _T(workloads.c4_spd_cores(d)), _T(workloads.rank1_rhs(d, 16))
+    x0 = _T(cores(z, "als/x0"))
+    ref = cores(z, "als/x")
+    for solver in ("cg", "solve"):
+        sol = sle.als(op, x0, rhs, repeats=1, solver=solver)
+        assert sol.ranks == ott.ranks_of(ref)
+        assert rel_diff(sol.cores, ref) < SOL_TOL, solver
+        res = osle.residual(op.cores, sol.cores, rhs.cores)
+        assert abs(res - float(z["als/residual"])) <= VAL_TOL * float(z["als/residual"]) + 1e-11, solver
+        if solver == "cg":
+            assert _local.stats["krylov_solves"] > 0 and _local.stats["worst_relres"] <= 1e-12
+
+
+@pytest.mark.gpu
+def test_c4_parity_mals_r8(dev):
+    from scikit_tt_b200.solvers import sle
+    z = load("c4_parity")
+    d = int(z["mals/d"])
+    op, rhs = _T(workloads.c4_spd_cores(d)), _T(workloads.rank1_rhs(d, 16))
+    x0 = _T(cores(z, "mals/x0"))
+    ref = cores(z, "mals/x")
+    for solver in ("cg", "solve"):
+        sol = sle.mals(op, x0, rhs, repeats=1, threshold=1e-12, max_rank=8, solver=solver)
+        assert sol.ranks == ott.ranks_of(ref)
+        assert rel_diff(sol.cores, ref) < SOL_TOL, solver
+
+
+@pytest.mark.gpu
+def test_c3_worst_accepted_krylov_residual(dev):
+    """C3 at full size: no reference exists, so the only guard against a drifting micro solve is the recorded worst
+    accepted true residual of the sweep -- it must stay at the 1e-12 the solution-level 1e-8 needs."""
+    from scikit_tt_b200 import TT
+    from scikit_tt_b200.solvers import sle, _local
+    opc, rhsc, x0c = workloads.workload_cores(32, 64, 64)
+    sle.als(TT(opc), TT(ott.ortho_right(x0c)), TT(rhsc), repeats=1)
+    assert _local.stats["krylov_solves"] >= 60
+    assert _local.stats["worst_relres"] <= 1e-12, _local.stats
+
+
+@pytest.mark.gpu
+def test_c5_mini_batch(dev):
+    """8 CO pressures of the config-5 sweep, rank-8 guess, through the batched front end."""
+    from scikit_tt_b200 import TT
+    import scikit_tt_b200.tensor_train as tt
+    from scikit_tt_b200.solvers import evp as gevp, multi
+    d = 20
+    ks = workloads.c5_pressures(64)[::8]
+    ops = []
+    for k in ks:
+        t = TT(workloads.co_oxidation_cores(d, k)).ortho_left().ortho_right()      # examples/co_oxidation.py:100
+        ops.append(tt.eye(t.row_dims) + t)
+    guess = tt.ones(ops[0].row_dims, [1] * d, ranks=8).ortho_left().ortho_right()
+    batch = multi.evp_als_batch(ops, guess, repeats=1, conv_eps=0, solver='eig')
+    assert len(batch) == len(ks)
+    for j in (0, 3, 7):
+        lam1, x1, it1 = gevp.als(ops[j], guess, repeats=1, conv_eps=0, solver='eig')
+        lamb, xb, itb = batch[j]
+        assert itb == it1 == 1 and xb.ranks == x1.ranks
+        assert abs(lamb - lam1) <= 1e-9 * max(abs(lam1), 1.0)                      # same arithmetic, batched or not
+        first = _oracle_first_lams(ops[j].cores, guess.cores, 3)
+        seen = []
+        orig = gevp._local_eig
+
+        def spy(dv, M, B, k, solver, sigma):
+            lam, vec = orig(dv, M, B, k, solver, sigma)
+            seen.append(complex(lam[0].item()))
+            if len(seen) >= 3:
+                raise _Stop()
+            return lam, vec
+        gevp._local_eig = spy
+        try:
+            gevp.als(ops[j], guess, repeats=1, conv_eps=0, solver='eig')
+        except _Stop:
+            pass
+        finally:
+            gevp._local_eig = orig
+        for (N, lo), lg in zip(first, seen):
+            assert abs(lg - lo) <= 1e-6 * max(abs(lo), 1.0), (j, N, lg, lo)
