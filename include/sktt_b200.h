@@ -290,6 +290,47 @@ int sktt_eig_shift_invert(sktt_ctx* ctx, int dtype, int64_t N, void* Mat, const 
                           double sigma, int64_t k, int64_t ncv, double tol, int max_restarts,
                           void* lam, void* vecs, void* work, int* nconv_host);
 
+/* ------------------------------------------------------------------ batched small systems ----
+ * a batch of independent systems with identical shapes (BASELINE config 5: the
+ * CO-pressure sweep of examples/co_oxidation.py:100-104 loops evp.als over the pressures; here the
+ * loop over the systems is the grid).  Every operand is contiguous with the batch index leading:
+ * Lst [batch, r, R, r], x [batch, r, n, r2], A [batch, R, m, n, R2], ...                        */
+
+/* sle.__construct_stack_left_op / evp.__construct_left_stacks (sle.py:194-219, evp.py:253-288) for
+ * `batch` systems; work: batch * (R r n r2 + r m r2 R2) elements.                               */
+int sktt_batch_stack_left_op(sktt_ctx* ctx, int dtype, int64_t batch, int64_t r, int64_t R, int64_t m,
+                             int64_t n, int64_t r2, int64_t R2, const void* Lst, const void* x,
+                             const void* A, void* out, void* work, int conj_mode);
+/* sle.__construct_stack_right_op / evp.__construct_right_stacks (sle.py:250-276, evp.py:295-330)  */
+int sktt_batch_stack_right_op(sktt_ctx* ctx, int dtype, int64_t batch, int64_t r, int64_t R, int64_t m,
+                              int64_t n, int64_t r2, int64_t R2, const void* Rst, const void* x,
+                              const void* A, void* out, void* work);
+/* evp.__construct_micro_matrices (evp.py:337-365) for `batch` systems: Mout [batch, N, N];
+ * work: batch * R m n r2 r2 elements.                                                            */
+int sktt_batch_micro_matrix_als(sktt_ctx* ctx, int dtype, int64_t batch, int64_t r, int64_t R, int64_t m,
+                                int64_t n, int64_t r2, int64_t R2, const void* Lst, const void* A,
+                                const void* Rst, void* Mout, void* work);
+/* evp.__update_core, local eigen-solve (evp.py:417-432) for `batch` dense N x N micro matrices
+ * (N <= 1024, k <= 8), ONE CTA per system, one launch for the batch: shift, LU with partial
+ * pivoting, shift-invert Arnoldi (CGS2), projected Hessenberg eigenproblem, Ritz selection,
+ * explicit restarts, Ritz vectors with LAPACK's phase convention.  lam [batch, k], vecs
+ * [batch, N, k] complex128; status_dev [batch][2] int32 ON THE DEVICE: converged pairs, info
+ * (bit 0 Hessenberg QR failed, bit 1 zero pivot).  Nothing is read back: the caller inspects
+ * status_dev at its next synchronisation.  work: sktt_batch_eig_work(...) complex128 elements.  */
+int64_t sktt_batch_eig_work(int64_t batch, int64_t N, int64_t k, int64_t ncv);
+int sktt_batch_eig_shift_invert(sktt_ctx* ctx, int dtype, int64_t batch, int64_t N, const void* Mat,
+                                double sigma, int64_t k, int64_t ncv, double tol, int max_restarts,
+                                void* lam, void* vecs, void* work, int32_t* status_dev,
+                                double* relres_dev /* [batch]: worst |h_{m+1,m} y_m| / |theta| of the returned pairs */);
+/* evp.__update_core, re-orthonormalisation (evp.py:452-464, :472-487): the first `keep` left
+ * singular vectors of `batch` small complex128 blocks F (P x Q), F(i, j) =
+ * op(in[sys * in_stride + fi(i) + fj(j)]) with two-level index maps, written as
+ * out[sys * out_stride + i * so_i + t * so_t] (optionally conjugated).  One-sided Jacobi in
+ * shared memory, ONE CTA per system; null columns are completed to an orthonormal set.          */
+int sktt_batch_svd_left(sktt_ctx* ctx, int64_t batch, int64_t P, int64_t Q, int64_t keep, const void* in,
+                        int64_t in_stride, sktt_idx2 fi, sktt_idx2 fj, int conj_in, void* out,
+                        int64_t out_stride, int64_t so_i, int64_t so_t, int conj_out);
+
 /* ------------------------------------------------------------------ small helpers ------------ */
 /* out[i] = alpha * x[i] (+ y[i] if y != NULL), n elements */
 int sktt_axpby(sktt_ctx* ctx, int dtype, int64_t n, const double* alpha, const void* x,

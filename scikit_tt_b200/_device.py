@@ -517,12 +517,13 @@ class Device:
         The reference's `lin.eig` always returns exact pairs and `splin.eigs` raises ArpackNoConvergence; here a run that
         ends with fewer than k converged Ritz pairs (clustered spectrum near sigma, exhausted Krylov space) is repeated
         once with the largest Krylov dimension and more restarts, and raises numpy.linalg.LinAlgError if that fails too --
-        unconverged pairs are never handed to the sweep."""
+        unconverged pairs are never handed to the sweep.  Up to EIG_EXACT_MAX_N unknowns the repeat is the exact one: a
+        Krylov space of full dimension."""
         N = M.shape[0]
         if ncv is None:
             ncv = min(N, max(2 * k + 1, 20))
         ncv = min(int(ncv), 64, N)
-        keep = (M.clone(), B) if ncv < N else None
+        keep = M.clone() if ncv < N else None
         lam = self.empty((k,), torch.complex128)
         vecs = self.empty((N, k), torch.complex128)
         nconv = C.c_int(0)
@@ -533,13 +534,81 @@ class Device:
                                                        float(tol), int(max_restarts), _ptr(lam), _ptr(vecs), _ptr(w),
                                                        C.byref(nconv)))
         run(M, ncv, max_restarts)
-        if nconv.value < k and keep is not None:
-            run(keep[0], min(64, N), 5 * max_restarts)
+        if nconv.value < k and keep is not None and N <= self.EIG_EXACT_MAX_N:
+            # Many eigenvalues at (nearly) the same distance from sigma -- restarted Arnoldi crawls.  The Krylov space of
+            # dimension N is the whole space: the projected Hessenberg matrix then carries the full spectrum, as lin.eig does
+            self.eig_exact_fallbacks = getattr(self, "eig_exact_fallbacks", 0) + 1
+            run(keep, N, 0)
+        elif nconv.value < k and keep is not None:
+            run(keep, min(64, N), 5 * max_restarts)
         self.last_eig_nconv = nconv.value
         if nconv.value < k:
             raise np.linalg.LinAlgError(f"shift-invert Arnoldi: {nconv.value} of {k} eigenpairs near sigma = {sigma} converged "
                                         f"(N = {N})")
         return lam, vecs
+
+    EIG_EXACT_MAX_N = 1024
+
+    # ------------------------------------------------------------------ batched small systems (leading batch dimension)
+    def batch_stack_left_op(self, Lst, x, A, conj_mode=CONJ_ROW):
+        """Lst [B, r, R, r], x [B, r, n, r2], A [B, R, m, n, R2] -> [B, r2, R2, r2]."""
+        B, r, n, r2 = x.shape
+        _, R, m, n_, R2 = A.shape
+        out = self.empty((B, r2, R2, r2), x.dtype)
+        w = self.work(B * (R * r * n * r2 + r * m * r2 * R2), x.dtype, tag="bstack")
+        self._check(self.lib.sktt_batch_stack_left_op(self.h, dtype_code(x), B, r, R, m, n_, r2, R2, _ptr(Lst), _ptr(x),
+                                                      _ptr(A), _ptr(out), _ptr(w), conj_mode))
+        return out
+
+    def batch_stack_right_op(self, Rst, x, A):
+        """Rst [B, r2, R2, r2], x [B, r, n, r2], A [B, R, m, n, R2] -> [B, r, R, r]."""
+        B, r, n, r2 = x.shape
+        _, R, m, n_, R2 = A.shape
+        out = self.empty((B, r, R, r), x.dtype)
+        w = self.work(B * (R * r * n * r2 + r * m * r2 * R2), x.dtype, tag="bstack")
+        self._check(self.lib.sktt_batch_stack_right_op(self.h, dtype_code(x), B, r, R, m, n_, r2, R2, _ptr(Rst), _ptr(x),
+                                                       _ptr(A), _ptr(out), _ptr(w)))
+        return out
+
+    def batch_micro_matrix_als(self, Lst, A, Rst):
+        """-> [B, r m r2, r n r2] dense micro matrices."""
+        B, r = Lst.shape[0], Lst.shape[1]
+        r2 = Rst.shape[1]
+        _, R, m, n, R2 = A.shape
+        out = self.empty((B, r * m * r2, r * n * r2), A.dtype)
+        w = self.work(B * R * m * n * r2 * r2, A.dtype, tag="bmicro")
+        self._check(self.lib.sktt_batch_micro_matrix_als(self.h, dtype_code(A), B, r, R, m, n, r2, R2, _ptr(Lst), _ptr(A),
+                                                         _ptr(Rst), _ptr(out), _ptr(w)))
+        return out
+
+    BATCH_EIG_MAX_N = 1024
+
+    def batch_eig_shift_invert(self, M, sigma, k, ncv=None, tol=1e-13, max_restarts=20):
+        """k eigenpairs closest to sigma of each M[b] ([B, N, N], float64 or complex128), one CTA per system, one launch.
+        Returns (lam [B, k], vecs [B, N, k], status [B, 3] float64: converged pairs, info, worst relative residual estimate)
+        -- all on the device, nothing is synchronised."""
+        B, N, _ = M.shape
+        if ncv is None:
+            ncv = min(N, max(2 * k + 1, 20))
+        ncv = min(int(ncv), 32, N)
+        lam = self.empty((B, k), torch.complex128)
+        vecs = self.empty((B, N, k), torch.complex128)
+        status = torch.empty((B, 2), dtype=torch.int32, device=self.device)
+        relres = torch.empty((B,), dtype=torch.float64, device=self.device)
+        w = self.work(self.lib.sktt_batch_eig_work(B, N, k, ncv), torch.complex128, tag="beig")
+        self._check(self.lib.sktt_batch_eig_shift_invert(self.h, dtype_code(M), B, N, _ptr(M), float(sigma), k, ncv,
+                                                         float(tol), int(max_restarts), _ptr(lam), _ptr(vecs), _ptr(w),
+                                                         _ptr(status), _ptr(relres)))
+        return lam, vecs, torch.cat([status.to(torch.float64), relres[:, None]], dim=1)
+
+    def batch_svd_left(self, src, P, Q, keep, fi, fj, conj_in, out, so_i, so_t, conj_out):
+        """First `keep` left singular vectors of the P x Q blocks F(i, j) = op(src[b].flat[fi(i) + fj(j)]), written to
+        out[b].flat[i * so_i + t * so_t]; src / out are [B, ...] contiguous complex128 tensors."""
+        B = src.shape[0]
+        mk = lambda t: Idx2(*t)
+        self._check(self.lib.sktt_batch_svd_left(self.h, B, P, Q, keep, _ptr(src), src[0].numel(), mk(fi), mk(fj),
+                                                 int(conj_in), _ptr(out), out[0].numel(), so_i, so_t, int(conj_out)))
+        return out
 
     # ------------------------------------------------------------------ misc
     def gemm2(self, M, N, K, A, am, ak, B, bk, bn, Cmat, cm, cn, conjA=0, conjB=0, alpha=(1.0, 0.0), beta=(0.0, 0.0)):
@@ -606,11 +675,12 @@ class Device:
         return out
 
     def axpby(self, alpha, x, beta, y, out=None):
-        """out = alpha * x + beta * y (elementwise, real scalars)."""
+        """out = alpha * x + beta * y (elementwise; complex scalars are allowed for complex128 operands)."""
         if out is None:
             out = torch.empty_like(x)
-        al = (C.c_double * 2)(float(alpha), 0.0)
-        be = (C.c_double * 2)(float(beta), 0.0)
+        alpha, beta = complex(alpha), complex(beta)
+        al = (C.c_double * 2)(alpha.real, alpha.imag)
+        be = (C.c_double * 2)(beta.real, beta.imag)
         self._check(self.lib.sktt_axpby(self.h, dtype_code(x), x.numel(), al, _ptr(x), be, _ptr(y), _ptr(out)))
         return out
 

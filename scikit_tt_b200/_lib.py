@@ -78,6 +78,12 @@ SIGNATURES = {
     "sktt_eigh_jacobi": (i32, [vp, i32, i64, vp, vp, vp, pint]),
     "sktt_eig_si_work": (i64, [i64, i64, i64]),
     "sktt_eig_shift_invert": (i32, [vp, i32, i64, vp, vp, dbl, i64, i64, dbl, i32, vp, vp, vp, pint]),
+    "sktt_batch_stack_left_op": (i32, [vp, i32] + [i64] * 7 + [vp] * 5 + [i32]),
+    "sktt_batch_stack_right_op": (i32, [vp, i32] + [i64] * 7 + [vp] * 5),
+    "sktt_batch_micro_matrix_als": (i32, [vp, i32] + [i64] * 7 + [vp] * 5),
+    "sktt_batch_eig_work": (i64, [i64] * 4),
+    "sktt_batch_eig_shift_invert": (i32, [vp, i32, i64, i64, vp, dbl, i64, i64, dbl, i32, vp, vp, vp, vp, vp]),
+    "sktt_batch_svd_left": (i32, [vp, i64, i64, i64, i64, vp, i64, Idx2, Idx2, i32, vp, i64, i64, i64, i32]),
     "sktt_axpby": (i32, [vp, i32, i64, pdbl, vp, pdbl, vp, vp]),
     "sktt_nrm2": (i32, [vp, i32, i64, vp, pdbl]),
     "sktt_dotc": (i32, [vp, i32, i64, vp, vp, pdbl]),

@@ -162,6 +162,10 @@ struct GemmDesc {
     double alpha[2];
     double beta[2];
     int conjC;  // store conj(result) (used to fold conjugations of the reference into epilogues)
+    long long batch;        // > 1: that many independent problems with identical extents and index maps ...
+    long long sA, sB, sC;   // ... whose operands lie sA / sB / sC elements apart
+    int npeer;              // > 0: the result is ALSO stored through these pointers (same offsets) -- peer-mapped copies of
+    void* Cpeer[7];         // C on other GPUs, written from the epilogue over NVLink (fused all-gather, peer.cu)
 };
 
 static inline GemmDesc gemm_desc(long long M, long long N, long long K, const void* A, Idx2 am, Idx2 ak,
@@ -174,6 +178,9 @@ static inline GemmDesc gemm_desc(long long M, long long N, long long K, const vo
     g.alpha[0] = 1.0; g.alpha[1] = 0.0;
     g.beta[0] = 0.0; g.beta[1] = 0.0;
     g.conjC = 0;
+    g.batch = 1; g.sA = g.sB = g.sC = 0;
+    g.npeer = 0;
+    for (int q = 0; q < 7; ++q) g.Cpeer[q] = nullptr;
     return g;
 }
 

@@ -7,147 +7,23 @@
 // eigen-solve runs on the host.
 #include "common.cuh"
 #include "blas1.cuh"
+#include "hess_eig.cuh"
 
-#define EIG_MAX_NCV 64
+#define EIG_MAX_NCV 1024   // ncv == N is the exact fallback (the Krylov space is the whole space) for small micro matrices
+#define EIG_SMEM_NCV 64    // up to here the projected eigenproblem is solved in shared memory
 
 // ------------------------------------------------------------------------------------------------
 // small complex Hessenberg eigen-solver (single warp).  Hin: m x m upper Hessenberg, row-major
 // complex.  Outputs: theta[m], Y[m][m] (column i = unit-norm eigenvector i of Hin).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double cabs_(cplx a) { return hypot(a.re, a.im); }
-
-__device__ __forceinline__ cplx csqrt_(cplx z) {
-    double r = hypot(z.re, z.im);
-    if (r == 0.0) return make_cplx(0.0, 0.0);
-    double sr = sqrt(0.5 * (r + fabs(z.re)));
-    double si = 0.5 * z.im / sr;
-    if (z.re >= 0.0) return make_cplx(sr, si);
-    return make_cplx(fabs(si), z.im >= 0.0 ? sr : -sr);
-}
-
 __global__ void __launch_bounds__(32)
-hess_eig_kernel(int m, const cplx* __restrict__ Hin, cplx* __restrict__ theta, cplx* __restrict__ Yout, int* info) {
+hess_eig_kernel(int m, const cplx* __restrict__ Hin, cplx* __restrict__ theta, cplx* __restrict__ Yout, int* info,
+                cplx* gwork /* 3 m^2 elements in global memory, or null: shared memory */) {
     extern __shared__ unsigned char smem_raw[];
-    cplx* H = (cplx*)smem_raw;          // [m][m]
-    cplx* Z = H + (size_t)m * m;        // [m][m]
-    cplx* X = Z + (size_t)m * m;        // [m][m]  eigenvectors of T (columns)
-    const int lane = threadIdx.x;
-    typedef Num<cplx> C;
-    for (int e = lane; e < m * m; e += 32) {
-        int r = e / m, c = e % m;
-        H[e] = (r <= c + 1) ? Hin[e] : C::zero();
-        Z[e] = (r == c) ? C::one() : C::zero();
-    }
-    __syncwarp();
-    double hnorm = 0.0;
-    for (int e = lane; e < m * m; e += 32) hnorm += C::abs2(H[e]);
-    hnorm = sqrt(warp_sum<double>(hnorm));
-    const double eps = 2.220446049250313e-16;
-    const double tiny = hnorm > 0.0 ? hnorm * eps : eps;
-    int hi = m - 1, iter = 0, total_iter = 0, fail = 0;
-    while (hi > 0) {
-        // deflation scan (uniform across lanes: every lane evaluates the same scalars)
-        int l = hi;
-        while (l > 0) {
-            double sub = cabs_(H[l * m + l - 1]);
-            double dsum = cabs_(H[(l - 1) * m + l - 1]) + cabs_(H[l * m + l]);
-            if (dsum == 0.0) dsum = hnorm;
-            if (sub <= eps * dsum || sub <= tiny * 1e-3) break;
-            --l;
-        }
-        if (l > 0 && lane == 0) H[l * m + l - 1] = C::zero();
-        __syncwarp();
-        if (l == hi) {
-            --hi;
-            iter = 0;
-            continue;
-        }
-        if (++total_iter > 60 * m) { fail = 1; break; }
-        ++iter;
-        // Wilkinson shift from the trailing 2x2 of the active block
-        cplx a = H[(hi - 1) * m + hi - 1], b = H[(hi - 1) * m + hi], c = H[hi * m + hi - 1], d = H[hi * m + hi];
-        cplx mu;
-        if (iter % 11 == 10) {
-            mu = C::add(d, make_cplx(cabs_(c) * 0.75, cabs_(c) * -0.4375));  // exceptional shift
-        } else {
-            cplx tr2 = C::scale(C::sub(a, d), 0.5);
-            cplx disc = csqrt_(C::add(C::mul(tr2, tr2), C::mul(b, c)));
-            cplx e1 = C::add(C::add(d, tr2), disc), e2 = C::sub(C::add(d, tr2), disc);
-            mu = cabs_(C::sub(e1, d)) <= cabs_(C::sub(e2, d)) ? e1 : e2;
-        }
-        cplx x = C::sub(H[l * m + l], mu), y = H[(l + 1) * m + l];
-        for (int k = l; k < hi; ++k) {
-            // G = [c s; -conj(s) c], G [x; y] = [rho; 0]
-            double nx = cabs_(x), ny = cabs_(y), nrm = hypot(nx, ny);
-            double cg;
-            cplx sg;
-            if (nrm == 0.0) {
-                cg = 1.0;
-                sg = C::zero();
-            } else if (nx == 0.0) {
-                cg = 0.0;
-                sg = C::scale(C::conj(y), 1.0 / ny);
-            } else {
-                cg = nx / nrm;
-                sg = C::scale(C::mul(C::scale(x, 1.0 / nx), C::conj(y)), 1.0 / nrm);
-            }
-            const cplx sgc = C::conj(sg);
-            // rows k, k+1 of H (columns from max(l, k-1) to m-1)
-            const int c0 = k > l ? k - 1 : l;
-            for (int cc = c0 + lane; cc < m; cc += 32) {
-                cplx h0 = H[k * m + cc], h1 = H[(k + 1) * m + cc];
-                H[k * m + cc] = C::add(C::scale(h0, cg), C::mul(sg, h1));
-                H[(k + 1) * m + cc] = C::sub(C::scale(h1, cg), C::mul(sgc, h0));
-            }
-            __syncwarp();
-            // columns k, k+1 of H (rows 0 .. min(k+2, hi)) times G^H
-            const int r1 = k + 2 < hi ? k + 2 : hi;
-            for (int rr = lane; rr <= r1; rr += 32) {
-                cplx h0 = H[rr * m + k], h1 = H[rr * m + k + 1];
-                H[rr * m + k] = C::add(C::scale(h0, cg), C::mul(sgc, h1));
-                H[rr * m + k + 1] = C::sub(C::scale(h1, cg), C::mul(sg, h0));
-            }
-            for (int rr = lane; rr < m; rr += 32) {
-                cplx z0 = Z[rr * m + k], z1 = Z[rr * m + k + 1];
-                Z[rr * m + k] = C::add(C::scale(z0, cg), C::mul(sgc, z1));
-                Z[rr * m + k + 1] = C::sub(C::scale(z1, cg), C::mul(sg, z0));
-            }
-            __syncwarp();
-            if (k < hi - 1) {
-                x = H[(k + 1) * m + k];
-                y = H[(k + 2) * m + k];
-            }
-        }
-    }
-    __syncwarp();
-    // eigenvectors of the triangular factor: lane i solves (T - t_ii I) x = 0 with x_i = 1
-    for (int i = lane; i < m; i += 32) {
-        cplx tii = H[i * m + i];
-        for (int r = m - 1; r > i; --r) X[r * m + i] = C::zero();
-        X[i * m + i] = C::one();
-        for (int r = i - 1; r >= 0; --r) {
-            cplx s = C::zero();
-            for (int c = r + 1; c <= i; ++c) C::fma(s, H[r * m + c], X[c * m + i]);
-            cplx den = C::sub(H[r * m + r], tii);
-            if (cabs_(den) < tiny) den = make_cplx(tiny, 0.0);
-            X[r * m + i] = C::neg(C::div(s, den));
-        }
-        theta[i] = tii;
-    }
-    __syncwarp();
-    // Y = Z X, unit-norm columns
-    for (int i = lane; i < m; i += 32) {
-        double nrm2 = 0.0;
-        for (int r = 0; r < m; ++r) {
-            cplx s = C::zero();
-            for (int c = 0; c <= i; ++c) C::fma(s, Z[r * m + c], X[c * m + i]);
-            Yout[r * m + i] = s;
-            nrm2 += C::abs2(s);
-        }
-        double inv = nrm2 > 0.0 ? 1.0 / sqrt(nrm2) : 0.0;
-        for (int r = 0; r < m; ++r) Yout[r * m + i] = C::scale(Yout[r * m + i], inv);
-    }
-    if (lane == 0 && info) *info = fail;
+    cplx* H = gwork ? gwork : (cplx*)smem_raw;   // [m][m]
+    cplx* Z = H + (size_t)m * m;                 // [m][m]
+    cplx* X = Z + (size_t)m * m;                 // [m][m]  eigenvectors of T (columns)
+    hess_eig_warp(m, Hin, theta, Yout, info, H, Z, X);
 }
 
 // order Ritz values by |theta| descending, keep k; out: sel[k] indices, lam[k] = sigma + 1/theta,
@@ -159,16 +35,18 @@ __global__ void ritz_select_kernel(int m, int k, double sigma, const cplx* __res
     typedef Num<cplx> C;
     int conv = 0;
     const double hn = hnext2 ? sqrt(hnext2[0] > 0.0 ? hnext2[0] : 0.0) : 0.0;
-    unsigned long long used_lo = 0ull;  // m <= 64
+    int taken[64];                      // k <= 64 (k <= ncv, and only a handful of pairs is ever asked for)
     for (int s = 0; s < k; ++s) {
         int best = -1;
         double bv = -1.0;
         for (int i = 0; i < m; ++i) {
-            if ((used_lo >> i) & 1ull) continue;
+            bool used = false;
+            for (int t = 0; t < s; ++t) used |= (taken[t] == i);
+            if (used) continue;
             double v = cabs_(theta[i]);
             if (v > bv) { bv = v; best = i; }
         }
-        used_lo |= 1ull << best;
+        taken[s] = best;
         cplx th = theta[best];
         lam[s] = C::add(make_cplx(sigma, 0.0), C::div(C::one(), th));
         for (int r = 0; r < m; ++r) Ysel[r * k + s] = Y[r * m + best];
@@ -252,7 +130,7 @@ __global__ void scale_unit_kernel(long long n, const T* __restrict__ w, const do
 template <typename T>
 __global__ void hess_store_kernel(int j, int m, const T* __restrict__ h1, const T* __restrict__ h2, const double* nrm2,
                                   cplx* __restrict__ H) {
-    int i = threadIdx.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= j) {
         T v = Num<T>::add(h1[i], h2[i]);
         H[i * m + j] = make_cplx(Num<T>::real(v), Num<T>::imag(v));
@@ -263,7 +141,7 @@ __global__ void hess_store_kernel(int j, int m, const T* __restrict__ h1, const 
 extern "C" int64_t sktt_eig_si_work(int64_t N, int64_t k, int64_t ncv) {
     if (ncv > EIG_MAX_NCV) ncv = EIG_MAX_NCV;
     // V [(ncv+1) N] + w [N] + t [N] (in units of complex128 elements, generous for real T)
-    return (ncv + 3) * N + 4 * ncv * ncv + 4 * ncv + ncv * k + 2 * N + 256;
+    return (ncv + 3) * N + 8 * ncv * ncv + 4 * ncv + ncv * k + 2 * N + 512;
 }
 
 template <typename T>
@@ -287,6 +165,7 @@ static int eig_si_impl(sktt_ctx* ctx, int dtype, long long N, T* Mat, const T* B
     // pivots + permutation live after Ysel
     ipiv = (int*)(Ysel + (size_t)m * k);
     int* flags = ipiv + 2 * N;                  // [0] nconv, [1] hess info
+    cplx* hwork = (cplx*)((((uintptr_t)(flags + 8)) + 15) & ~(uintptr_t)15);   // [3][m][m], used when m > EIG_SMEM_NCV
     double* slots = (double*)ctx->scratch;      // [0..1] nrm2
     const int nbk = (int)((N + 255) / 256 < 4LL * ctx->sm_count ? (N + 255) / 256 : 4LL * ctx->sm_count);
 
@@ -339,14 +218,18 @@ static int eig_si_impl(sktt_ctx* ctx, int dtype, long long N, T* Mat, const T* B
                 SKTT_TRY(sktt_gemm_run(ctx, dtype, g2));
             }
             SKTT_TRY(blas1_dot(ctx, dtype, N, w, w, slots));
-            hess_store_kernel<T><<<1, 128, 0, ctx->stream>>>(j, m, h1, h2, slots, H);
+            hess_store_kernel<T><<<(j + 2 + 127) / 128, 128, 0, ctx->stream>>>(j, m, h1, h2, slots, H);
             SKTT_LAUNCH_CHECK(ctx);
             scale_unit_kernel<T><<<nbk, 256, 0, ctx->stream>>>(N, w, slots, V + (size_t)(j + 1) * N);
             SKTT_LAUNCH_CHECK(ctx);
         }
         // projected eigenproblem, selection, convergence
-        size_t hsmem = (size_t)3 * m * m * sizeof(cplx);
-        hess_eig_kernel<<<1, 32, hsmem, ctx->stream>>>(m, H, theta, Y, flags + 1);
+        if (m <= EIG_SMEM_NCV) {
+            size_t hsmem = (size_t)3 * m * m * sizeof(cplx);
+            hess_eig_kernel<<<1, 32, hsmem, ctx->stream>>>(m, H, theta, Y, flags + 1, (cplx*)nullptr);
+        } else {
+            hess_eig_kernel<<<1, 32, 0, ctx->stream>>>(m, H, theta, Y, flags + 1, hwork);
+        }
         SKTT_LAUNCH_CHECK(ctx);
         ritz_select_kernel<<<1, 32, 0, ctx->stream>>>(m, k, sigma, theta, Y, m < N ? slots : (const double*)nullptr, tol,
                                                       lam, Ysel, flags);

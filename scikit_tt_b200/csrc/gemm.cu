@@ -26,9 +26,13 @@ struct GemmParams {
     Idx2 am, ak, bk, bn, cm, cn;
     int conjA, conjB, conjC;
     double alpha_re, alpha_im, beta_re, beta_im;
-    int splits;      // grid.z
+    int splits;      // grid.z = batch * splits
     int k_chunk;     // K range handled per split (multiple of BK)
-    void* partial;   // [splits][M][N] when splits > 1
+    void* partial;   // [batch][splits][M][N] when splits > 1
+    int batch;       // independent problems with the same extents and index maps
+    long long sA, sB, sC;   // element strides between consecutive problems of the batch
+    int npeer;       // additional destinations of the result (peer GPUs), same offsets as C
+    void* Cpeer[7];
 };
 
 template <typename T>
@@ -54,11 +58,12 @@ gemm_simt_kernel(GemmParams p) {
     constexpr int NT = (BM / TM) * (BN / TN);
     __shared__ T As[BK][BM + 1];
     __shared__ T Bs[BK][BN + 1];
-    const T* __restrict__ A = (const T*)p.A;
-    const T* __restrict__ B = (const T*)p.B;
+    const int bz = blockIdx.z / p.splits, sz = blockIdx.z % p.splits;
+    const T* __restrict__ A = (const T*)p.A + (long long)bz * p.sA;
+    const T* __restrict__ B = (const T*)p.B + (long long)bz * p.sB;
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kbeg = blockIdx.z * p.k_chunk;
+    const int kbeg = sz * p.k_chunk;
     const int kend = min(p.K, kbeg + p.k_chunk);
     const int tx = tid % (BN / TN), ty = tid / (BN / TN);
 
@@ -105,7 +110,7 @@ gemm_simt_kernel(GemmParams p) {
     }
 
     if (p.splits > 1) {
-        T* P = (T*)p.partial + (size_t)blockIdx.z * p.M * p.N;
+        T* P = (T*)p.partial + (size_t)blockIdx.z * p.M * p.N;      // blockIdx.z = bz * splits + sz
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
             int m = m0 + ty * TM + i;
@@ -118,7 +123,7 @@ gemm_simt_kernel(GemmParams p) {
         }
         return;
     }
-    T* C = (T*)p.C;
+    T* C = (T*)p.C + (long long)bz * p.sC;
     const bool use_beta = (p.beta_re != 0.0 || p.beta_im != 0.0);
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
@@ -134,6 +139,7 @@ gemm_simt_kernel(GemmParams p) {
             T r = alpha_beta<T>(acc[i][j], cold, p.alpha_re, p.alpha_im, p.beta_re, p.beta_im, use_beta);
             if (p.conjC) r = Num<T>::conj(r);
             C[o] = r;
+            for (int q = 0; q < p.npeer; ++q) ((T*)p.Cpeer[q] + (long long)bz * p.sC)[o] = r;
         }
     }
 }
@@ -141,8 +147,8 @@ gemm_simt_kernel(GemmParams p) {
 template <typename T>
 __global__ void splitk_reduce_kernel(GemmParams p) {
     long long total = (long long)p.M * p.N;
-    const T* P = (const T*)p.partial;
-    T* C = (T*)p.C;
+    const T* P = (const T*)p.partial + (size_t)blockIdx.y * p.splits * total;
+    T* C = (T*)p.C + (long long)blockIdx.y * p.sC;                  // grid.y = batch
     const bool use_beta = (p.beta_re != 0.0 || p.beta_im != 0.0);
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
@@ -154,6 +160,7 @@ __global__ void splitk_reduce_kernel(GemmParams p) {
         T r = alpha_beta<T>(s, cold, p.alpha_re, p.alpha_im, p.beta_re, p.beta_im, use_beta);
         if (p.conjC) r = Num<T>::conj(r);
         C[o] = r;
+        for (int q = 0; q < p.npeer; ++q) ((T*)p.Cpeer[q] + (long long)blockIdx.y * p.sC)[o] = r;
     }
 }
 
@@ -210,11 +217,12 @@ gemm_dmma_kernel(GemmParams p) {
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
 
-    const double* __restrict__ A = (const double*)p.A;
-    const double* __restrict__ B = (const double*)p.B;
+    const int bz = blockIdx.z / p.splits, sz = blockIdx.z % p.splits;
+    const double* __restrict__ A = (const double*)p.A + (long long)bz * p.sA;
+    const double* __restrict__ B = (const double*)p.B + (long long)bz * p.sB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kbeg = blockIdx.z * p.k_chunk;
+    const int kbeg = sz * p.k_chunk;
     const int kend = min(p.K, kbeg + p.k_chunk);
     const int ntiles = (kend - kbeg + BK - 1) / BK;
 
@@ -311,7 +319,7 @@ gemm_dmma_kernel(GemmParams p) {
         }
         return;
     }
-    double* C = (double*)p.C;
+    double* C = (double*)p.C + (long long)bz * p.sC;
     const bool use_beta = (p.beta_re != 0.0);
     long long cno[NI][2];
 #pragma unroll
@@ -334,6 +342,7 @@ gemm_dmma_kernel(GemmParams p) {
                 double r = p.alpha_re * acc[i][j][h];
                 if (use_beta) r = fma(p.beta_re, C[o], r);
                 C[o] = r;
+                for (int q = 0; q < p.npeer; ++q) ((double*)p.Cpeer[q] + (long long)bz * p.sC)[o] = r;
             }
         }
     }
@@ -374,7 +383,7 @@ static int launch_dmma(sktt_ctx* ctx, GemmParams& p) {
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits * p.batch);
     gemm_dmma_kernel<BM, BN, WM, WN, STAGES><<<grid, NT, smem, ctx->stream>>>(p);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
@@ -382,7 +391,7 @@ static int launch_dmma(sktt_ctx* ctx, GemmParams& p) {
 
 template <typename T, int BM, int BN, int BK, int TM, int TN>
 static int launch_simt(sktt_ctx* ctx, GemmParams& p) {
-    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits * p.batch);
     gemm_simt_kernel<T, BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, ctx->stream>>>(p);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
@@ -404,6 +413,11 @@ int sktt_gemm_run(sktt_ctx* ctx, int dtype, const GemmDesc& g) {
     p.splits = 1;
     p.k_chunk = p.K > 0 ? p.K : 1;
     p.partial = nullptr;
+    p.batch = g.batch > 1 ? (int)g.batch : 1;
+    p.sA = g.sA; p.sB = g.sB; p.sC = g.sC;
+    p.npeer = g.npeer < 0 ? 0 : (g.npeer > 7 ? 7 : g.npeer);
+    for (int q = 0; q < 7; ++q) p.Cpeer[q] = g.Cpeer[q];
+    if ((long long)p.batch > 65535) return sktt_fail(ctx, SKTT_ERR_ARG, "gemm batch exceeds 65535");
 
     const bool is_f64 = dtype == SKTT_F64;
     const int sms = ctx->sm_count;
@@ -416,8 +430,8 @@ int sktt_gemm_run(sktt_ctx* ctx, int dtype, const GemmDesc& g) {
     if (dmma_ok) {
         long long t128 = cdiv(g.M, 128) * cdiv(g.N, 128);
         long long t64 = cdiv(g.M, 64) * cdiv(g.N, 64);
-        bool big = t128 >= (long long)(sms * 3) / 4;
-        long long tiles = big ? t128 : t64;
+        bool big = t128 * p.batch >= (long long)(sms * 3) / 4;
+        long long tiles = (big ? t128 : t64) * p.batch;
         // split-K when the tile grid cannot fill the machine and K is long
         if (tiles < sms && g.K >= 512) {
             long long want = cdiv(2LL * sms, tiles);
@@ -429,7 +443,7 @@ int sktt_gemm_run(sktt_ctx* ctx, int dtype, const GemmDesc& g) {
             }
         }
         if (p.splits > 1) {
-            SKTT_TRY(sktt_scratch_reserve(ctx, (size_t)p.splits * g.M * g.N * sizeof(double) + SKTT_SCRATCH_BULK_OFF));
+            SKTT_TRY(sktt_scratch_reserve(ctx, (size_t)p.batch * p.splits * g.M * g.N * sizeof(double) + SKTT_SCRATCH_BULK_OFF));
             p.partial = (char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF;
         }
         if (big) SKTT_TRY((launch_dmma<128, 128, 64, 32, 3>(ctx, p)));
@@ -437,7 +451,7 @@ int sktt_gemm_run(sktt_ctx* ctx, int dtype, const GemmDesc& g) {
         if (p.splits > 1) {
             long long total = g.M * g.N;
             int blocks = (int)(cdiv(total, 256) < 4LL * sms ? cdiv(total, 256) : 4LL * sms);
-            splitk_reduce_kernel<double><<<blocks, 256, 0, ctx->stream>>>(p);
+            splitk_reduce_kernel<double><<<dim3(blocks, p.batch), 256, 0, ctx->stream>>>(p);
             SKTT_LAUNCH_CHECK(ctx);
         }
         return 0;
@@ -445,7 +459,7 @@ int sktt_gemm_run(sktt_ctx* ctx, int dtype, const GemmDesc& g) {
 
     // SIMT path
     bool small = (g.M <= 16 || g.N <= 16);
-    long long tiles = small ? cdiv(g.M, 16) * cdiv(g.N, 16) : cdiv(g.M, 64) * cdiv(g.N, 64);
+    long long tiles = (small ? cdiv(g.M, 16) * cdiv(g.N, 16) : cdiv(g.M, 64) * cdiv(g.N, 64)) * p.batch;
     if (tiles < sms && g.K >= 256) {
         long long want = cdiv(2LL * sms, tiles);
         long long maxs = g.K / 64;
@@ -456,7 +470,7 @@ int sktt_gemm_run(sktt_ctx* ctx, int dtype, const GemmDesc& g) {
         }
     }
     if (p.splits > 1) {
-        SKTT_TRY(sktt_scratch_reserve(ctx, (size_t)p.splits * g.M * g.N * dtype_size(dtype) + SKTT_SCRATCH_BULK_OFF));
+        SKTT_TRY(sktt_scratch_reserve(ctx, (size_t)p.batch * p.splits * g.M * g.N * dtype_size(dtype) + SKTT_SCRATCH_BULK_OFF));
         p.partial = (char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF;
     }
     if (is_f64) {
@@ -469,8 +483,8 @@ int sktt_gemm_run(sktt_ctx* ctx, int dtype, const GemmDesc& g) {
     if (p.splits > 1) {
         long long total = g.M * g.N;
         int blocks = (int)(cdiv(total, 256) < 4LL * sms ? cdiv(total, 256) : 4LL * sms);
-        if (is_f64) splitk_reduce_kernel<double><<<blocks, 256, 0, ctx->stream>>>(p);
-        else splitk_reduce_kernel<cplx><<<blocks, 256, 0, ctx->stream>>>(p);
+        if (is_f64) splitk_reduce_kernel<double><<<dim3(blocks, p.batch), 256, 0, ctx->stream>>>(p);
+        else splitk_reduce_kernel<cplx><<<dim3(blocks, p.batch), 256, 0, ctx->stream>>>(p);
         SKTT_LAUNCH_CHECK(ctx);
     }
     return 0;

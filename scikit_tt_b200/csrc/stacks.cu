@@ -67,21 +67,50 @@ static int fused_stack(sktt_ctx* ctx, long long rin, long long Rin, long long m,
     return sktt_fused_stack_update(ctx, rp, Rin, m, n, image, xt, (double*)out, T1p, part);
 }
 
+// Batched forms ("batched variants taking a leading batch dimension"): `batch` independent systems with
+// identical shapes, every operand contiguous with the batch index leading; the contraction engine takes the batch as a
+// grid dimension.
+static inline void set_batch(GemmDesc& g, long long batch, long long sA, long long sB, long long sC) {
+    g.batch = batch;
+    g.sA = sA;
+    g.sB = sB;
+    g.sC = sC;
+}
+
 // T1[(b,c),(n,a2)] = sum_a L[a,(b,c)] X[a,(n,a2)]            (first tensordot of sle.py:217)
 static int left_step1(sktt_ctx* ctx, int dtype, long long r, long long R, long long ncols, const void* Lst,
-                      const void* X, int conjX, void* T1) {
+                      const void* X, int conjX, void* T1, long long batch = 1) {
     GemmDesc g = gemm_desc(R * r, ncols, r, Lst, lin_idx(1), lin_idx(R * r), X, lin_idx(ncols), lin_idx(1), T1,
                            lin_idx(ncols), lin_idx(1));
     g.conjB = conjX;
+    set_batch(g, batch, r * R * r, r * ncols, R * r * ncols);
     return sktt_gemm_run(ctx, dtype, g);
 }
 
 // T2[c,m,a2,b2] = sum_{b,n} T1[b,c,n,a2] A[b,m,n,b2]           (second tensordot of sle.py:218)
 static int left_step2(sktt_ctx* ctx, int dtype, long long r, long long R, long long m, long long n, long long r2,
-                      long long R2, const void* T1, const void* A, void* T2) {
+                      long long R2, const void* T1, const void* A, void* T2, long long batch = 1) {
     GemmDesc g = gemm_desc(r * r2, m * R2, R * n, T1, two(r2, n * r2, 1), two(n, r * n * r2, r2), A,
                            two(n, m * n * R2, R2), two(R2, n * R2, 1), T2, two(r2, m * r2 * R2, R2),
                            two(R2, r2 * R2, 1));
+    set_batch(g, batch, R * r * n * r2, R * m * n * R2, r * m * r2 * R2);
+    return sktt_gemm_run(ctx, dtype, g);
+}
+
+static int stack_left_chain(sktt_ctx* ctx, int dtype, long long batch, int64_t r, int64_t R, int64_t m, int64_t n,
+                            int64_t r2, int64_t R2, const void* Lst, const void* x, const void* A, void* out, void* work,
+                            int conj_mode) {
+    size_t es = dtype_size(dtype);
+    char* T1 = (char*)work;
+    char* T2 = T1 + (size_t)(batch * R * r * n * r2) * es;
+    const int conj_col = (conj_mode == SKTT_CONJ_COL), conj_row = !conj_col;
+    SKTT_TRY(left_step1(ctx, dtype, r, R, n * r2, Lst, x, conj_col, T1, batch));
+    SKTT_TRY(left_step2(ctx, dtype, r, R, m, n, r2, R2, T1, A, T2, batch));
+    // out[(a2,b2),c2] = sum_{(c,m)} T2[(c,m),(a2,b2)] X2[(c,m),c2]     (third tensordot, sle.py:219)
+    GemmDesc g = gemm_desc(r2 * R2, r2, r * m, T2, lin_idx(1), lin_idx(r2 * R2), x, lin_idx(r2), lin_idx(1), out,
+                           lin_idx(r2), lin_idx(1));
+    g.conjB = conj_row;
+    set_batch(g, batch, r * m * r2 * R2, r * m * r2, r2 * R2 * r2);
     return sktt_gemm_run(ctx, dtype, g);
 }
 
@@ -91,20 +120,35 @@ extern "C" int sktt_stack_left_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t R
     if (!ctx) return SKTT_ERR_ARG;
     SKTT_TRY(check_dtype(ctx, dtype));
     if (m != n) return sktt_fail(ctx, SKTT_ERR_ARG, "stack_left_op: row and column mode sizes must agree");
-    size_t es = dtype_size(dtype);
-    char* T1 = (char*)work;
-    char* T2 = T1 + (size_t)(R * r * n * r2) * es;
-    const int conj_col = (conj_mode == SKTT_CONJ_COL), conj_row = !conj_col;
     if (!(ctx->debug & 32) && r2 == 64 && R2 == 3 &&
         sktt_fused_supported(ctx, dtype, r, R, m, n, r2, R2))              // real: conjugation is the identity
         return fused_stack(ctx, r, R, m, n, Lst, x, A, out, work, 0);
-    SKTT_TRY(left_step1(ctx, dtype, r, R, n * r2, Lst, x, conj_col, T1));
-    SKTT_TRY(left_step2(ctx, dtype, r, R, m, n, r2, R2, T1, A, T2));
-    // out[(a2,b2),c2] = sum_{(c,m)} T2[(c,m),(a2,b2)] X2[(c,m),c2]     (third tensordot, sle.py:219)
-    GemmDesc g = gemm_desc(r2 * R2, r2, r * m, T2, lin_idx(1), lin_idx(r2 * R2), x, lin_idx(r2), lin_idx(1), out,
-                           lin_idx(r2), lin_idx(1));
-    g.conjB = conj_row;
-    return sktt_gemm_run(ctx, dtype, g);
+    return stack_left_chain(ctx, dtype, 1, r, R, m, n, r2, R2, Lst, x, A, out, work, conj_mode);
+}
+
+static int stack_right_chain(sktt_ctx* ctx, int dtype, long long batch, int64_t r, int64_t R, int64_t m, int64_t n,
+                             int64_t r2, int64_t R2, const void* Rst, const void* x, const void* A, void* out,
+                             void* work) {
+    size_t es = dtype_size(dtype);
+    char* U1 = (char*)work;                                  // [c, m, a2, b2]
+    char* U2 = U1 + (size_t)(batch * r * m * r2 * R2) * es;  // [n, a2, b, c]
+    // U1[(c,m),(a2,b2)] = sum_c2 conj(x)[(c,m),c2] Rst[(a2,b2),c2]          (sle.py:274)
+    GemmDesc g1 = gemm_desc(r * m, r2 * R2, r2, x, lin_idx(r2), lin_idx(1), Rst, lin_idx(1), lin_idx(r2), U1,
+                            lin_idx(r2 * R2), lin_idx(1));
+    g1.conjA = 1;
+    set_batch(g1, batch, r * m * r2, r2 * R2 * r2, r * m * r2 * R2);
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g1));
+    // U2[n,a2,b,c] = sum_{m,b2} A[b,m,n,b2] U1[c,m,a2,b2]                   (sle.py:275)
+    GemmDesc g2 = gemm_desc(R * n, r * r2, m * R2, A, two(n, m * n * R2, R2), two(R2, n * R2, 1), U1,
+                            two(R2, r2 * R2, 1), two(r2, m * r2 * R2, R2), U2, two(n, r, r2 * R * r),
+                            two(r2, 1, R * r));
+    set_batch(g2, batch, R * m * n * R2, r * m * r2 * R2, n * r2 * R * r);
+    SKTT_TRY(sktt_gemm_run(ctx, dtype, g2));
+    // out[a,(b,c)] = sum_{(n,a2)} x[a,(n,a2)] U2[(n,a2),(b,c)]              (sle.py:276)
+    GemmDesc g3 = gemm_desc(r, R * r, n * r2, x, lin_idx(n * r2), lin_idx(1), U2, lin_idx(R * r), lin_idx(1), out,
+                            lin_idx(R * r), lin_idx(1));
+    set_batch(g3, batch, r * n * r2, n * r2 * R * r, r * R * r);
+    return sktt_gemm_run(ctx, dtype, g3);
 }
 
 extern "C" int sktt_stack_right_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n, int64_t r2,
@@ -112,25 +156,28 @@ extern "C" int sktt_stack_right_op(sktt_ctx* ctx, int dtype, int64_t r, int64_t 
     if (!ctx) return SKTT_ERR_ARG;
     SKTT_TRY(check_dtype(ctx, dtype));
     if (m != n) return sktt_fail(ctx, SKTT_ERR_ARG, "stack_right_op: row and column mode sizes must agree");
-    size_t es = dtype_size(dtype);
     if (!(ctx->debug & 32) && r == 64 && R == 3 && sktt_fused_supported(ctx, dtype, r2, R2, m, n, r, R))
         return fused_stack(ctx, r2, R2, m, n, Rst, x, A, out, work, 1);
-    char* U1 = (char*)work;                                  // [c, m, a2, b2]
-    char* U2 = U1 + (size_t)(r * m * r2 * R2) * es;          // [n, a2, b, c]
-    // U1[(c,m),(a2,b2)] = sum_c2 conj(x)[(c,m),c2] Rst[(a2,b2),c2]          (sle.py:274)
-    GemmDesc g1 = gemm_desc(r * m, r2 * R2, r2, x, lin_idx(r2), lin_idx(1), Rst, lin_idx(1), lin_idx(r2), U1,
-                            lin_idx(r2 * R2), lin_idx(1));
-    g1.conjA = 1;
-    SKTT_TRY(sktt_gemm_run(ctx, dtype, g1));
-    // U2[n,a2,b,c] = sum_{m,b2} A[b,m,n,b2] U1[c,m,a2,b2]                   (sle.py:275)
-    GemmDesc g2 = gemm_desc(R * n, r * r2, m * R2, A, two(n, m * n * R2, R2), two(R2, n * R2, 1), U1,
-                            two(R2, r2 * R2, 1), two(r2, m * r2 * R2, R2), U2, two(n, r, r2 * R * r),
-                            two(r2, 1, R * r));
-    SKTT_TRY(sktt_gemm_run(ctx, dtype, g2));
-    // out[a,(b,c)] = sum_{(n,a2)} x[a,(n,a2)] U2[(n,a2),(b,c)]              (sle.py:276)
-    GemmDesc g3 = gemm_desc(r, R * r, n * r2, x, lin_idx(n * r2), lin_idx(1), U2, lin_idx(R * r), lin_idx(1), out,
-                            lin_idx(R * r), lin_idx(1));
-    return sktt_gemm_run(ctx, dtype, g3);
+    return stack_right_chain(ctx, dtype, 1, r, R, m, n, r2, R2, Rst, x, A, out, work);
+}
+
+// Batched interface-stack updates: operands [batch, ...] contiguous, work >= batch * (R r n r2 + r m r2 R2) elements.
+extern "C" int sktt_batch_stack_left_op(sktt_ctx* ctx, int dtype, int64_t batch, int64_t r, int64_t R, int64_t m, int64_t n,
+                                        int64_t r2, int64_t R2, const void* Lst, const void* x, const void* A, void* out,
+                                        void* work, int conj_mode) {
+    if (!ctx || batch < 1) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    if (m != n) return sktt_fail(ctx, SKTT_ERR_ARG, "batch_stack_left_op: row and column mode sizes must agree");
+    return stack_left_chain(ctx, dtype, batch, r, R, m, n, r2, R2, Lst, x, A, out, work, conj_mode);
+}
+
+extern "C" int sktt_batch_stack_right_op(sktt_ctx* ctx, int dtype, int64_t batch, int64_t r, int64_t R, int64_t m,
+                                         int64_t n, int64_t r2, int64_t R2, const void* Rst, const void* x, const void* A,
+                                         void* out, void* work) {
+    if (!ctx || batch < 1) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    if (m != n) return sktt_fail(ctx, SKTT_ERR_ARG, "batch_stack_right_op: row and column mode sizes must agree");
+    return stack_right_chain(ctx, dtype, batch, r, R, m, n, r2, R2, Rst, x, A, out, work);
 }
 
 // ---------------------------------------------------------------------- small rhs ranks: one kernel per chain --
@@ -432,31 +479,41 @@ extern "C" int sktt_micro_matvec_mals(sktt_ctx* ctx, int dtype, int64_t r, int64
 // Mout[(c,mu,c3),(a,nu,a3)] = sum_b L[a,b,c] W[b,mu,nu,a3,c3]; mu = (m,m2), nu = (n,n2) composite mode
 // indices; W is addressed as W[b, m, n, m2, n2, a3, c3] (m2 = n2 = 1 for ALS).
 template <typename T>
-__global__ void micro_expand_kernel(int r, int R, int m, int n, int m2, int n2, int r3, const T* __restrict__ Lst,
-                                    const T* __restrict__ W, T* __restrict__ Mout) {
-    // one CTA per (mu, nu); threads sweep (c, c3, a, a3) with a3 fastest (contiguous in Mout)
+__global__ void micro_expand_kernel(int r, int R, int m, int n, int m2, int n2, int r3, int cc, int chunks,
+                                    const T* __restrict__ Lst, const T* __restrict__ W, T* __restrict__ Mout) {
+    // one CTA per (mu, nu, chunk of c3); threads sweep (c, c3, a, a3) with a3 fastest (contiguous in Mout).  The chunking
+    // of c3 (cc values per CTA) bounds the shared-memory tile R * r3 * cc for large operator / solution ranks (co_oxidation
+    // at r = 32: R = 21, r3 = 32)
     const int mu = blockIdx.y, nu = blockIdx.x;
+    const int bz = blockIdx.z / chunks;                       // system of the batch (operands contiguous per system)
+    const int c3lo = (blockIdx.z % chunks) * cc, c3n = min(cc, r3 - c3lo);
     const int mi = mu / m2, m2i = mu % m2, ni = nu / n2, n2i = nu % n2;
     const long long ncolmode = (long long)n * n2, nrowmode = (long long)m * m2;
     const long long Ncol = (long long)r * ncolmode * r3;
     const long long wstride_b = (long long)m * n * m2 * n2 * r3 * r3;
+    Lst += (long long)bz * r * R * r;
+    W += (long long)bz * R * wstride_b;
+    Mout += (long long)bz * ((long long)r * nrowmode * r3) * Ncol;
     const long long wbase = ((((long long)mi * n + ni) * m2 + m2i) * n2 + n2i) * r3 * r3;
     extern __shared__ unsigned char smem_raw[];
-    T* Ws = (T*)smem_raw;  // [R][r3*r3] (a3, c3)
-    const int rr3 = r3 * r3;
-    for (int e = threadIdx.x; e < R * rr3; e += blockDim.x) Ws[e] = W[wbase + (long long)(e / rr3) * wstride_b + e % rr3];
+    T* Ws = (T*)smem_raw;  // [R][r3 (a3)][cc (c3 - c3lo)]
+    const int tile = r3 * cc;
+    for (int e = threadIdx.x; e < R * r3 * c3n; e += blockDim.x) {
+        int cl = e % c3n, a3 = (e / c3n) % r3, b = e / (c3n * r3);
+        Ws[b * tile + a3 * cc + cl] = W[wbase + (long long)b * wstride_b + a3 * r3 + c3lo + cl];
+    }
     __syncthreads();
-    const long long total = (long long)r * r * rr3;
+    const long long total = (long long)r * r * r3 * c3n;
     for (long long e = threadIdx.x; e < total; e += blockDim.x) {
         int a3 = (int)(e % r3);
         long long t = e / r3;
         int a = (int)(t % r);
         t /= r;
-        int c3 = (int)(t % r3);
-        int c = (int)(t / r3);
+        int cl = (int)(t % c3n);
+        int c = (int)(t / c3n);
         T s = Num<T>::zero();
-        for (int b = 0; b < R; ++b) Num<T>::fma(s, Lst[((long long)a * R + b) * r + c], Ws[b * rr3 + a3 * r3 + c3]);
-        long long row = ((long long)c * nrowmode + mu) * r3 + c3;
+        for (int b = 0; b < R; ++b) Num<T>::fma(s, Lst[((long long)a * R + b) * r + c], Ws[b * tile + a3 * cc + cl]);
+        long long row = ((long long)c * nrowmode + mu) * r3 + c3lo + cl;
         long long col = ((long long)a * ncolmode + nu) * r3 + a3;
         Mout[row * Ncol + col] = s;
     }
@@ -464,30 +521,48 @@ __global__ void micro_expand_kernel(int r, int R, int m, int n, int m2, int n2, 
 
 template <typename T>
 static int launch_expand(sktt_ctx* ctx, int r, int R, int m, int n, int m2, int n2, int r3, const void* Lst,
-                         const void* W, void* Mout) {
-    size_t smem = (size_t)R * r3 * r3 * sizeof(T);
-    if (smem > 200 * 1024) return sktt_fail(ctx, SKTT_ERR_ARG, "micro_matrix: R*r2^2 tile exceeds shared memory");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+                         const void* W, void* Mout, int batch = 1) {
+    const size_t budget = 160 * 1024;
+    int cc = r3;
+    while (cc > 1 && (size_t)R * r3 * cc * sizeof(T) > budget) cc = (cc + 1) / 2;
+    size_t smem = (size_t)R * r3 * cc * sizeof(T);
+    if (smem > 200 * 1024) return sktt_fail(ctx, SKTT_ERR_ARG, "micro_matrix: R*r2 tile exceeds shared memory");
+    SKTT_ONCE_PER_DEVICE(ctx);
+    if (smem > 48 * 1024 && !configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(micro_expand_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(200 * 1024)));
-        configured = 200 * 1024;
+        configured = true;
     }
-    dim3 grid(n * n2, m * m2);
-    long long per = (long long)r * r * r3 * r3;
+    const int chunks = (r3 + cc - 1) / cc;
+    dim3 grid(n * n2, m * m2, chunks * batch);
+    long long per = (long long)r * r * r3 * cc;
     int threads = per >= 1024 ? 1024 : (per >= 256 ? 256 : 64);
-    micro_expand_kernel<T><<<grid, threads, smem, ctx->stream>>>(r, R, m, n, m2, n2, r3, (const T*)Lst, (const T*)W,
-                                                                  (T*)Mout);
+    micro_expand_kernel<T><<<grid, threads, smem, ctx->stream>>>(r, R, m, n, m2, n2, r3, cc, chunks, (const T*)Lst,
+                                                                  (const T*)W, (T*)Mout);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
 }
 
 // W[b,m,n,a2,c2] = sum_b2 A[(b,m,n),b2] Rst[a2,b2,c2]
 static int right_fold(sktt_ctx* ctx, int dtype, long long rows, long long R2, long long r2, const void* A,
-                      const void* Rst, void* W) {
+                      const void* Rst, void* W, long long batch = 1) {
     GemmDesc g = gemm_desc(rows, r2 * r2, R2, A, lin_idx(R2), lin_idx(1), Rst, lin_idx(r2), two(r2, R2 * r2, 1), W,
                            lin_idx(r2 * r2), lin_idx(1));
+    set_batch(g, batch, rows * R2, r2 * R2 * r2, rows * r2 * r2);
     return sktt_gemm_run(ctx, dtype, g);
+}
+
+// Batched dense micro matrices: Lst [batch, r, R, r], A [batch, R, m, n, R2], Rst [batch, r2, R2, r2] ->
+// Mout [batch, r m r2, r n r2]; work >= batch * R m n r2 r2 elements.
+extern "C" int sktt_batch_micro_matrix_als(sktt_ctx* ctx, int dtype, int64_t batch, int64_t r, int64_t R, int64_t m,
+                                           int64_t n, int64_t r2, int64_t R2, const void* Lst, const void* A,
+                                           const void* Rst, void* Mout, void* work) {
+    if (!ctx || batch < 1 || batch > 4096) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    SKTT_TRY(right_fold(ctx, dtype, R * m * n, R2, r2, A, Rst, work, batch));
+    if (dtype == SKTT_F64)
+        return launch_expand<double>(ctx, (int)r, (int)R, (int)m, (int)n, 1, 1, (int)r2, Lst, work, Mout, (int)batch);
+    return launch_expand<cplx>(ctx, (int)r, (int)R, (int)m, (int)n, 1, 1, (int)r2, Lst, work, Mout, (int)batch);
 }
 
 extern "C" int sktt_micro_matrix_als(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n, int64_t r2,

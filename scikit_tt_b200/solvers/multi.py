@@ -65,17 +65,26 @@ def _pack(t):
 
 
 def evp_als_batch(operators, initial_guesses, group=None, **kwargs):
-    """evp.als on a list of independent operators, one block of the list per GPU.  `initial_guesses` is one TT (shared)
-    or a list.  Returns a list of (eigenvalue(s), eigentensor(s), iterations) in input order on every rank."""
+    """evp.als on a list of independent operators: one contiguous block of the list per GPU (no data-path collective),
+    and inside each GPU the block runs through the batched kernels of evp.als_batch (the systems are a grid dimension).
+    `initial_guesses` is one TT (shared) or a list.  Returns a list of (eigenvalue(s), eigentensor(s), iterations) in
+    input order on every rank; one host-side gather of the results at the end."""
     from . import evp
     guesses = initial_guesses if isinstance(initial_guesses, (list, tuple)) else [initial_guesses] * len(operators)
-
-    def one(i):
-        lam, vec, it = evp.als(operators[i], guesses[i], **kwargs)
-        vec = [_pack(v) for v in vec] if isinstance(vec, list) else _pack(vec)
-        return lam, vec, it
-
-    res = map_sharded(one, list(range(len(operators))), group=group)
+    world, rank = _world(group)
+    lo, hi = shard_bounds(len(operators), world, rank)
+    mine = []
+    if hi > lo:
+        for j, (lam, vec, it) in enumerate(evp.als_batch(operators[lo:hi], guesses[lo:hi], **kwargs)):
+            vec = [_pack(v) for v in vec] if isinstance(vec, list) else _pack(vec)
+            mine.append((lo + j, (lam, vec, it)))
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine, group=group)
+        mine = [item for part in parts for item in part]
+    res = [None] * len(operators)
+    for i, r in mine:
+        res[i] = r
     out = []
     for lam, vec, it in res:
         tens = [TT(v) for v in vec] if vec and isinstance(vec[0], list) else TT(vec)
