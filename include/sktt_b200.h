@@ -331,6 +331,41 @@ int sktt_batch_svd_left(sktt_ctx* ctx, int64_t batch, int64_t P, int64_t Q, int6
                         int64_t in_stride, sktt_idx2 fi, sktt_idx2 fj, int conj_in, void* out,
                         int64_t out_stride, int64_t so_i, int64_t so_t, int conj_out);
 
+/* ------------------------------------------------------------------ rank-sharded micro-matvec -
+ * SURVEY.md 8e (BASELINE config 4): the one exchange step of the path.  y = M v of the one-site
+ * local operator (sle.py:339-345 applied matrix-free) with the OUTPUT solution-rank index sharded
+ * over the GPUs of one NVSwitch domain, one process per GPU.  sktt_sharded_matvec computes the
+ * rows [lo, hi) and its last contraction stores them into y_local and, from the same epilogue,
+ * into the peer-mapped y buffers of the other ranks (fused all-gather over NVLink);
+ * sktt_peer_barrier (flag exchange in peer memory) orders those stores before the readers of y.
+ * Buffers written by peers come from sktt_peer_alloc and travel as 64-byte CUDA IPC handles
+ * (sktt_peer_export / sktt_peer_open); the cross-device entry points take the peer pointers where
+ * an MPI-style library would take a communicator.                                               */
+int sktt_peer_alloc(sktt_ctx* ctx, int64_t bytes, void** out);
+int sktt_peer_free(sktt_ctx* ctx, void* ptr);
+int sktt_peer_export(sktt_ctx* ctx, void* ptr, uint8_t* handle_out /* 64 bytes */);
+int sktt_peer_open(sktt_ctx* ctx, const uint8_t* handle /* 64 bytes */, void** out);
+int sktt_peer_close(sktt_ctx* ctx, void* ptr);
+/* flags[g]: rank g's array of `world` uint64 slots (peer-mapped for g != rank); every rank calls
+ * with the same increasing epoch.  timeout_flag_dev is set to 1 if a peer did not arrive.        */
+int sktt_peer_barrier(sktt_ctx* ctx, int world, int rank, uint64_t epoch, void* const* flags,
+                      int32_t* timeout_flag_dev);
+int64_t sktt_sharded_matvec_work(int64_t r, int64_t R, int64_t m, int64_t n, int64_t r2, int64_t R2,
+                                 int64_t rows);
+int sktt_sharded_matvec(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t m, int64_t n,
+                        int64_t r2, int64_t R2, const void* Lst, const void* A, const void* Rst,
+                        const void* v, int64_t lo, int64_t hi, void* y_local, int npeer,
+                        void* const* y_peers, void* work);
+
+/* ------------------------------------------------------------------ exponential integrators --
+ * ode.__update_core_tdvp / __update_core_tdvp2site (scikit_tt/solvers/ode.py:1398-1614) apply
+ * exp(-i h M) to a core through scipy's expm_multiply or the fixed-dimension local_krylov
+ * (ode.py:1689-1757).  Here the action is a Krylov projection on the device (matvecs and
+ * orthogonalisation through the contraction engine) and this entry point exponentiates the small
+ * projected matrix: E = exp((c_re + i c_im) H), H and E complex128 row-major, m <= 96, one CTA,
+ * scaling and squaring around a degree-18 Taylor polynomial.                                     */
+int sktt_expm_small(sktt_ctx* ctx, int64_t m, const void* H, double c_re, double c_im, void* E);
+
 /* ------------------------------------------------------------------ small helpers ------------ */
 /* out[i] = alpha * x[i] (+ y[i] if y != NULL), n elements */
 int sktt_axpby(sktt_ctx* ctx, int dtype, int64_t n, const double* alpha, const void* x,

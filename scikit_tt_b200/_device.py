@@ -401,6 +401,9 @@ class Device:
 
     def prepare_local_op(self, op):
         """Build the TMA tile images of a one-site local operator (no-op for shapes the fused matvec does not cover)."""
+        if getattr(op, "_prepared", False):
+            return op
+        op._prepared = True
         dt = op._keep[0].dtype
         n = self.lib.sktt_local_op_image_size(self.h, dtype_code(op._keep[0]), C.byref(op))
         if n > 0:
@@ -583,7 +586,7 @@ class Device:
 
     BATCH_EIG_MAX_N = 1024
 
-    def batch_eig_shift_invert(self, M, sigma, k, ncv=None, tol=1e-13, max_restarts=20):
+    def batch_eig_shift_invert(self, M, sigma, k, ncv=None, tol=1e-12, max_restarts=5):
         """k eigenpairs closest to sigma of each M[b] ([B, N, N], float64 or complex128), one CTA per system, one launch.
         Returns (lam [B, k], vecs [B, N, k], status [B, 3] float64: converged pairs, info, worst relative residual estimate)
         -- all on the device, nothing is synchronised."""
@@ -609,6 +612,15 @@ class Device:
         self._check(self.lib.sktt_batch_svd_left(self.h, B, P, Q, keep, _ptr(src), src[0].numel(), mk(fi), mk(fj),
                                                  int(conj_in), _ptr(out), out[0].numel(), so_i, so_t, int(conj_out)))
         return out
+
+    def expm_small(self, H, c):
+        """exp(c * H) of a small dense complex128 matrix (m <= 96) on the device."""
+        m = H.shape[0]
+        H = H.contiguous() if H.dtype == torch.complex128 else self.widen(H.contiguous())
+        E = self.empty((m, m), torch.complex128)
+        c = complex(c)
+        self._check(self.lib.sktt_expm_small(self.h, m, _ptr(H), c.real, c.imag, _ptr(E)))
+        return E
 
     # ------------------------------------------------------------------ misc
     def gemm2(self, M, N, K, A, am, ak, B, bk, bn, Cmat, cm, cn, conjA=0, conjB=0, alpha=(1.0, 0.0), beta=(0.0, 0.0)):

@@ -84,6 +84,15 @@ SIGNATURES = {
     "sktt_batch_eig_work": (i64, [i64] * 4),
     "sktt_batch_eig_shift_invert": (i32, [vp, i32, i64, i64, vp, dbl, i64, i64, dbl, i32, vp, vp, vp, vp, vp]),
     "sktt_batch_svd_left": (i32, [vp, i64, i64, i64, i64, vp, i64, Idx2, Idx2, i32, vp, i64, i64, i64, i32]),
+    "sktt_peer_alloc": (i32, [vp, i64, C.POINTER(vp)]),
+    "sktt_peer_free": (i32, [vp, vp]),
+    "sktt_peer_export": (i32, [vp, vp, C.c_char_p]),
+    "sktt_peer_open": (i32, [vp, C.c_char_p, C.POINTER(vp)]),
+    "sktt_peer_close": (i32, [vp, vp]),
+    "sktt_peer_barrier": (i32, [vp, i32, i32, C.c_uint64, C.POINTER(vp), vp]),
+    "sktt_sharded_matvec_work": (i64, [i64] * 7),
+    "sktt_sharded_matvec": (i32, [vp, i32] + [i64] * 6 + [vp] * 4 + [i64, i64, vp, i32, C.POINTER(vp), vp]),
+    "sktt_expm_small": (i32, [vp, i64, vp, dbl, dbl, vp]),
     "sktt_axpby": (i32, [vp, i32, i64, pdbl, vp, pdbl, vp, vp]),
     "sktt_nrm2": (i32, [vp, i32, i64, vp, pdbl]),
     "sktt_dotc": (i32, [vp, i32, i64, vp, vp, pdbl]),

@@ -17,6 +17,7 @@
 #define BE_MAX_NCV 32
 #define BE_MAX_K 8
 #define BE_MAX_N 1024
+#define BE_DBUF 2          // diagonal-block buffers (17 KB each): that many blocks are inverted concurrently
 
 typedef Num<cplx> CX;
 
@@ -31,6 +32,7 @@ struct BeigArgs {
     cplx* V;           // [batch][m + 1][N]
     cplx* lam;         // [batch][k]
     cplx* vecs;        // [batch][N][k]
+    int v_in_smem;     // the Krylov basis fits into shared memory next to everything else
     int* status;       // [batch][2]: converged Ritz pairs, info (bit 0: Hessenberg QR failed, bit 1: zero pivot)
     double* relres;    // [batch]: largest residual estimate |h_{m+1,m} y_m| / |theta| among the k returned pairs
 };
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(BE_THREADS) beig_kernel(BeigArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = BE_THREADS / 32;
     const long long sys = blockIdx.x;
     cplx* S = a.S + sys * (long long)N * N;
-    cplx* V = a.V + sys * (long long)(m + 1) * N;
+    cplx* V = a.V + sys * (long long)(m + 1) * N;            // Krylov basis: global memory (L2) unless it fits below
     // shared-memory carve-up
     cplx* ws = (cplx*)smem_raw;                    // [N] current vector
     cplx* H = ws + N;                              // [(m + 1)][m]
@@ -53,14 +55,17 @@ __global__ void __launch_bounds__(BE_THREADS) beig_kernel(BeigArgs a) {
     cplx* Ysel = theta + m;                        // [m][k]
     cplx* h1 = Ysel + m * k;                       // [m + 1]
     cplx* hs = h1 + (m + 1);                       // [m + 1]
-    cplx* D = hs + (m + 1);                        // [32][33] diagonal block of the triangular solves
-    cplx* tmp = D + 32 * 33;                       // [32]
+    cplx* D = hs + (m + 1);                        // [BE_DBUF][32][33] diagonal blocks (inversion: one per warp; solves: the first)
+    cplx* tmp = D + BE_DBUF * 32 * 33;             // [32]
     cplx* red = tmp + 32;                          // [32]
     double* dred = (double*)(red + 32);            // [32]
     int* ired = (int*)(dred + 32);                 // [32]
     int* perm = ired + 32;                         // [N]
     int* sflag = perm + N;                         // [4]: pivot row, nconv, hess info, lu info
     cplx* invd = (cplx*)(((uintptr_t)(sflag + 4) + 15) & ~(uintptr_t)15);   // [N] reciprocals of the pivots (diagonal of U)
+    cplx* urow = invd + N;                         // [N] pivot row of the current LU column
+    cplx* lcol = urow + N;                         // [N] multipliers of the current LU column
+    if (a.v_in_smem) V = lcol + N;                 // [(m + 1)][N] Krylov basis in shared memory
 
     // ---- S = M - sigma I
     {
@@ -75,12 +80,18 @@ __global__ void __launch_bounds__(BE_THREADS) beig_kernel(BeigArgs a) {
     }
     __syncthreads();
 
-    // ---- P S = L U, right-looking, partial pivoting on |re| + |im| (LAPACK izamax)
-    for (int j = 0; j < N; ++j) {
+    // ---- P S = L U, right-looking, partial pivoting on |re| + |im| (LAPACK izamax).  Three CTA barriers per column:
+    //   1. row interchange j <-> p; the pivot row (columns > j) is staged in shared memory on the way
+    //   2. multipliers l_i = S[i,j] / pivot: written back and staged in shared memory
+    //   3. rank-1 update of the trailing block from the two staged vectors; the threads that produce column j + 1 also
+    //      vote for the next pivot (atomicMax on a key made of the truncated magnitude and the row index)
+    unsigned long long* pkey = reinterpret_cast<unsigned long long*>(dred);        // [0]: next pivot key (dred is free here)
+    {
+        // pivot of column 0
         double best = -1.0;
-        int bi = j;
-        for (int i = j + tid; i < N; i += BE_THREADS) {
-            cplx v = S[(long long)i * N + j];
+        int bi = 0;
+        for (int i = tid; i < N; i += BE_THREADS) {
+            cplx v = S[(long long)i * N];
             double c1 = fabs(v.re) + fabs(v.im);
             if (c1 > best) { best = c1; bi = i; }
         }
@@ -90,47 +101,159 @@ __global__ void __launch_bounds__(BE_THREADS) beig_kernel(BeigArgs a) {
             int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
         }
-        if (lane == 0) { dred[warp] = best; ired[warp] = bi; }
+        if (lane == 0) { tmp[warp].re = best; ired[warp] = bi; }
         __syncthreads();
         if (tid == 0) {
             for (int w = 1; w < nwarps; ++w)
-                if (dred[w] > best || (dred[w] == best && ired[w] < bi)) { best = dred[w]; bi = ired[w]; }
+                if (tmp[w].re > best || (tmp[w].re == best && ired[w] < bi)) { best = tmp[w].re; bi = ired[w]; }
             sflag[0] = bi;
-            if (!(best > 0.0)) sflag[3] |= 2;
-            int t = perm[j];
-            perm[j] = perm[bi];
-            perm[bi] = t;
-        }
-        __syncthreads();
-        const int p = sflag[0];
-        if (p != j)
-            for (int c = tid; c < N; c += BE_THREADS) {
-                cplx t = S[(long long)j * N + c];
-                S[(long long)j * N + c] = S[(long long)p * N + c];
-                S[(long long)p * N + c] = t;
-            }
-        __syncthreads();
-        const cplx piv = S[(long long)j * N + j];
-        const bool okp = (fabs(piv.re) + fabs(piv.im)) > 0.0;
-        const cplx inv = okp ? CX::div(CX::one(), piv) : CX::zero();
-        for (int i = j + 1 + tid; i < N; i += BE_THREADS) S[(long long)i * N + j] = CX::mul(S[(long long)i * N + j], inv);
-        if (tid == 0) invd[j] = inv;
-        __syncthreads();
-        const int cnt = N - j - 1;
-        for (int e = tid; e < cnt * cnt; e += BE_THREADS) {
-            int i = j + 1 + e / cnt, c = j + 1 + e % cnt;
-            cplx l = S[(long long)i * N + j], u = S[(long long)j * N + c], v = S[(long long)i * N + c];
-            v.re = fma(-l.re, u.re, v.re);
-            v.re = fma(l.im, u.im, v.re);
-            v.im = fma(-l.re, u.im, v.im);
-            v.im = fma(-l.im, u.re, v.im);
-            S[(long long)i * N + c] = v;
         }
         __syncthreads();
     }
+    for (int j = 0; j < N; ++j) {
+        const int p = sflag[0];
+        cplx* rowj = S + (long long)j * N;
+        cplx* rowp = S + (long long)p * N;
+        for (int c = tid; c < N; c += BE_THREADS) {                 // (1)
+            cplx aj = rowj[c], ap = rowp[c];
+            if (p != j) {
+                rowj[c] = ap;
+                rowp[c] = aj;
+            }
+            if (c >= j) urow[c] = ap;
+        }
+        if (tid == 0) {
+            int t = perm[j];
+            perm[j] = perm[p];
+            perm[p] = t;
+            pkey[0] = 0ull;
+        }
+        __syncthreads();
+        const cplx piv = urow[j];
+        const bool okp = (fabs(piv.re) + fabs(piv.im)) > 0.0;
+        const cplx inv = okp ? CX::div(CX::one(), piv) : CX::zero();
+        for (int i = j + 1 + tid; i < N; i += BE_THREADS) {         // (2)
+            cplx l = CX::mul(S[(long long)i * N + j], inv);
+            S[(long long)i * N + j] = l;
+            lcol[i] = l;
+        }
+        if (tid == 0) {
+            invd[j] = inv;
+            if (!okp) sflag[3] |= 2;
+        }
+        __syncthreads();
+        // (3): a warp per row, lanes along the row (coalesced), four independent 16-byte loads in flight per thread -- the
+        // trailing block lives in L2, so the update is bound by how many loads a CTA keeps outstanding
+        for (int i = j + 1 + 2 * warp; i < N; i += 2 * nwarps) {
+            const bool two = i + 1 < N;
+            const cplx l0 = lcol[i], l1 = two ? lcol[i + 1] : CX::zero();
+            cplx* row0 = S + (long long)i * N;
+            cplx* row1 = row0 + N;
+            for (int c0 = j + 1 + lane; c0 < N; c0 += 32 * 4) {
+                cplx v0[4], v1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = c0 + 32 * u;
+                    if (c < N) {
+                        v0[u] = row0[c];
+                        if (two) v1[u] = row1[c];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = c0 + 32 * u;
+                    if (c < N) {
+                        const cplx uu = urow[c];
+                        cplx w = v0[u];
+                        w.re = fma(-l0.re, uu.re, w.re);
+                        w.re = fma(l0.im, uu.im, w.re);
+                        w.im = fma(-l0.re, uu.im, w.im);
+                        w.im = fma(-l0.im, uu.re, w.im);
+                        row0[c] = w;
+                        cplx w1 = v1[u];
+                        if (two) {
+                            w1.re = fma(-l1.re, uu.re, w1.re);
+                            w1.re = fma(l1.im, uu.im, w1.re);
+                            w1.im = fma(-l1.re, uu.im, w1.im);
+                            w1.im = fma(-l1.im, uu.re, w1.im);
+                            row1[c] = w1;
+                        }
+                        if (c == j + 1) {
+                            // key: magnitude with its 10 lowest mantissa bits replaced by (1023 - row): the largest |.|
+                            // wins, ties (to 2^-42 relative) go to the smaller row; positive doubles order like their bits
+                            const double c1 = fabs(w.re) + fabs(w.im);
+                            atomicMax(pkey, ((unsigned long long)__double_as_longlong(c1) & ~0x3FFull) | (unsigned long long)(1023 - i));
+                            if (two) {
+                                const double c2 = fabs(w1.re) + fabs(w1.im);
+                                atomicMax(pkey, ((unsigned long long)__double_as_longlong(c2) & ~0x3FFull) |
+                                                    (unsigned long long)(1023 - (i + 1)));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && j + 1 < N) sflag[0] = 1023 - (int)(pkey[0] & 0x3FFull);
+        __syncthreads();
+    }
+    // ---- the 32 x 32 diagonal blocks of L and U are replaced by their inverses (in place: strictly lower part L_kk^-1,
+    // upper part U_kk^-1), so that the triangular solves below apply them as small dense products instead of walking a
+    // dependent chain of 32 substitution steps
+    {
+        const int nblk = (N + 31) / 32;
+        for (int k0 = 0; k0 < nblk; k0 += BE_DBUF) {
+            const int kb = warp < BE_DBUF ? k0 + warp : nblk;       // warp w < BE_DBUF inverts block k0 + w in its own buffer
+            cplx* Dw = D + (size_t)(warp < BE_DBUF ? warp : 0) * (32 * 33);
+            if (kb < nblk) {
+                const int i0 = kb * 32, nb = min(32, N - i0);
+                for (int e = lane; e < nb * nb; e += 32) Dw[(e / nb) * 33 + e % nb] = S[(long long)(i0 + e / nb) * N + i0 + e % nb];
+                __syncwarp();
+                if (lane < nb) {
+                    const int c = lane;                             // this lane produces column c of both inverses
+                    {
+                        // L^-1 (unit lower): x_c = 1, x_i = - sum_{t=c}^{i-1} L[i][t] x_t
+                        cplx x[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) x[i] = CX::zero();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (i == c) x[i] = CX::one();
+                            else if (i > c && i < nb) {
+                                cplx acc = CX::zero();
+#pragma unroll
+                                for (int t = 0; t < 32; ++t)
+                                    if (t >= c && t < i) CX::fma(acc, Dw[i * 33 + t], x[t]);
+                                x[i] = CX::neg(acc);
+                                S[(long long)(i0 + i) * N + i0 + c] = x[i];      // Dw is a copy: the block in S is free to take it
+                            }
+                        }
+                    }
+                    {
+                        // U^-1 (upper): y_c = 1 / U[c][c], y_i = - (sum_{t=i+1}^{c} U[i][t] y_t) / U[i][i]
+                        cplx y[32];
+#pragma unroll
+                        for (int i = 31; i >= 0; --i) {
+                            y[i] = CX::zero();
+                            if (i == c) y[i] = invd[i0 + c];
+                            else if (i < c) {
+                                cplx acc = CX::zero();
+#pragma unroll
+                                for (int t = 0; t < 32; ++t)
+                                    if (t > i && t <= c) CX::fma(acc, Dw[i * 33 + t], y[t]);
+                                y[i] = CX::neg(CX::mul(acc, invd[i0 + i]));
+                            }
+                            if (i <= c) S[(long long)(i0 + i) * N + i0 + c] = y[i];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
 
     // ws <- S^-1 (P applied by the caller): forward substitution with unit-lower L, backward with U, 32 rows at a time:
-    // all warps form the block's dot products with the part already solved, warp 0 solves the 32 x 32 triangle
+    // all warps form the block's dot products with the part already solved, warp 0 applies the inverted diagonal block
     auto solve = [&]() {
         const int nblk = (N + 31) / 32;
         for (int I = 0; I < nblk; ++I) {
@@ -138,6 +261,7 @@ __global__ void __launch_bounds__(BE_THREADS) beig_kernel(BeigArgs a) {
             for (int row = warp; row < nb; row += nwarps) {
                 const cplx* Li = S + (long long)(i0 + row) * N;
                 cplx acc = CX::zero();
+#pragma unroll 8
                 for (int c = lane; c < i0; c += 32) CX::fma(acc, Li[c], ws[c]);
                 acc = warp_sum<cplx>(acc);
                 if (lane == 0) tmp[row] = acc;
@@ -145,10 +269,11 @@ __global__ void __launch_bounds__(BE_THREADS) beig_kernel(BeigArgs a) {
             for (int e = tid; e < nb * nb; e += BE_THREADS) D[(e / nb) * 33 + e % nb] = S[(long long)(i0 + e / nb) * N + i0 + e % nb];
             __syncthreads();
             if (warp == 0) {
-                cplx val = lane < nb ? CX::sub(ws[i0 + lane], tmp[lane]) : CX::zero();
+                const cplx t = lane < nb ? CX::sub(ws[i0 + lane], tmp[lane]) : CX::zero();
+                cplx val = t;                                       // unit diagonal
                 for (int c = 0; c < nb; ++c) {
-                    cplx wc = lane_bcast<cplx>(val, c);
-                    if (lane > c && lane < nb) val = CX::sub(val, CX::mul(D[lane * 33 + c], wc));
+                    const cplx tc = lane_bcast<cplx>(t, c);
+                    if (lane > c && lane < nb) CX::fma(val, D[lane * 33 + c], tc);
                 }
                 if (lane < nb) ws[i0 + lane] = val;
             }
@@ -159,6 +284,7 @@ __global__ void __launch_bounds__(BE_THREADS) beig_kernel(BeigArgs a) {
             for (int row = warp; row < nb; row += nwarps) {
                 const cplx* Ui = S + (long long)(i0 + row) * N;
                 cplx acc = CX::zero();
+#pragma unroll 8
                 for (int c = i0 + nb + lane; c < N; c += 32) CX::fma(acc, Ui[c], ws[c]);
                 acc = warp_sum<cplx>(acc);
                 if (lane == 0) tmp[row] = acc;
@@ -166,11 +292,11 @@ __global__ void __launch_bounds__(BE_THREADS) beig_kernel(BeigArgs a) {
             for (int e = tid; e < nb * nb; e += BE_THREADS) D[(e / nb) * 33 + e % nb] = S[(long long)(i0 + e / nb) * N + i0 + e % nb];
             __syncthreads();
             if (warp == 0) {
-                cplx val = lane < nb ? CX::sub(ws[i0 + lane], tmp[lane]) : CX::zero();
-                for (int c = nb - 1; c >= 0; --c) {
-                    if (lane == c) val = CX::mul(val, invd[i0 + c]);
-                    cplx wc = lane_bcast<cplx>(val, c);
-                    if (lane < c) val = CX::sub(val, CX::mul(D[lane * 33 + c], wc));
+                const cplx t = lane < nb ? CX::sub(ws[i0 + lane], tmp[lane]) : CX::zero();
+                cplx val = CX::zero();
+                for (int c = 0; c < nb; ++c) {
+                    const cplx tc = lane_bcast<cplx>(t, c);
+                    if (lane <= c && lane < nb) CX::fma(val, D[lane * 33 + c], tc);
                 }
                 if (lane < nb) ws[i0 + lane] = val;
             }
@@ -260,9 +386,9 @@ __global__ void __launch_bounds__(BE_THREADS) beig_kernel(BeigArgs a) {
         nconv = sflag[1];
         const double prev_rel = worst_rel;
         worst_rel = dred[0];
-        // a cycle that does not gain a factor of four on the residual estimate will not reach the tolerance in any
+        // a cycle that does not gain a factor of ten on the residual estimate will not reach the tolerance in any
         // reasonable number of restarts (eigenvalues at nearly equal distance from sigma): stop, report unconverged
-        const bool stagnated = restart >= 1 && worst_rel > 0.25 * prev_rel;
+        const bool stagnated = restart >= 1 && worst_rel > 0.1 * prev_rel;
         __syncthreads();
         cplx* vecs = a.vecs + sys * (long long)N * k;
         for (int e = tid; e < N * k; e += BE_THREADS) {
@@ -320,10 +446,10 @@ __global__ void __launch_bounds__(BE_THREADS) beig_kernel(BeigArgs a) {
 }
 
 static size_t beig_smem(int N, int m, int k) {
-    size_t c = (size_t)N + (size_t)(m + 1) * m + 3 * (size_t)m * m + (size_t)m * m + m + (size_t)m * k + 2 * (m + 1) + 32 * 33 +
-               32 + 32;
+    size_t c = (size_t)N + (size_t)(m + 1) * m + 3 * (size_t)m * m + (size_t)m * m + m + (size_t)m * k + 2 * (m + 1) +
+               (size_t)BE_DBUF * 32 * 33 + 32 + 32;
     return c * sizeof(cplx) + 32 * sizeof(double) + 32 * sizeof(int) + (size_t)N * sizeof(int) + 4 * sizeof(int) + 64 +
-           (size_t)N * sizeof(cplx);
+           3 * (size_t)N * sizeof(cplx);
 }
 
 extern "C" int64_t sktt_batch_eig_work(int64_t batch, int64_t N, int64_t k, int64_t ncv) {
@@ -356,8 +482,11 @@ extern "C" int sktt_batch_eig_shift_invert(sktt_ctx* ctx, int dtype, int64_t bat
     a.vecs = (cplx*)vecs;
     a.status = status_dev;
     a.relres = relres_dev;
-    const size_t smem = beig_smem((int)N, m, (int)k);
+    size_t smem = beig_smem((int)N, m, (int)k);
     if (smem > 200 * 1024) return sktt_fail(ctx, SKTT_ERR_ARG, "batch_eig_shift_invert: shared memory budget exceeded");
+    const size_t vbytes = (size_t)(m + 1) * N * sizeof(cplx);
+    a.v_in_smem = smem + vbytes <= 200 * 1024 ? 1 : 0;
+    if (a.v_in_smem) smem += vbytes;
     SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(beig_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -571,6 +700,91 @@ extern "C" int sktt_batch_svd_left(sktt_ctx* ctx, int64_t batch, int64_t P, int6
     a.out = (cplx*)out; a.out_stride = out_stride; a.so_i = so_i; a.so_t = so_t;
     a.sweeps = nullptr;
     bsvd_kernel<<<(unsigned)batch, BS_THREADS, smem, ctx->stream>>>(a);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// E = exp(c * H) for one small dense complex matrix (m <= 96), one CTA: scaling and squaring around a Taylor polynomial of
+// degree 18 on ||c H||_1 / 2^s <= 1/2 (truncation error ~ 0.5^19 / 19! relative, far below fp64 rounding).  The projected
+// problems of the exponential integrators (ode.tdvp*: scipy.sparse.linalg.expm_multiply of the micro matrix, ode.py:1437-1508;
+// local_krylov, ode.py:1689-1757) are of this size.
+#define EX_THREADS 256
+__global__ void __launch_bounds__(EX_THREADS) expm_small_kernel(int m, const cplx* __restrict__ H, cplx cc, cplx* __restrict__ E) {
+    extern __shared__ unsigned char smem_raw[];
+    cplx* A = (cplx*)smem_raw;        // [m][m]  c H / 2^s
+    cplx* T = A + m * m;              // current Taylor term
+    cplx* X = T + m * m;              // accumulated sum / squaring result
+    cplx* W = X + m * m;              // product scratch
+    __shared__ double colsum[96];
+    __shared__ int s_scale;
+    const int tid = threadIdx.x, mm = m * m;
+    for (int e = tid; e < mm; e += EX_THREADS) A[e] = CX::mul(cc, H[e]);
+    __syncthreads();
+    for (int j = tid; j < m; j += EX_THREADS) {
+        double a = 0.0;
+        for (int i = 0; i < m; ++i) a += sqrt(CX::abs2(A[i * m + j]));
+        colsum[j] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double nrm = 0.0;
+        for (int j = 0; j < m; ++j) nrm = colsum[j] > nrm ? colsum[j] : nrm;
+        int s = 0;
+        while (nrm > 0.5 && s < 60) { nrm *= 0.5; ++s; }
+        s_scale = s;
+    }
+    __syncthreads();
+    const int s = s_scale;
+    const double sc = ldexp(1.0, -s);
+    for (int e = tid; e < mm; e += EX_THREADS) {
+        A[e] = CX::scale(A[e], sc);
+        const cplx id = (e / m == e % m) ? CX::one() : CX::zero();
+        T[e] = id;
+        X[e] = id;
+    }
+    __syncthreads();
+    for (int k = 1; k <= 18; ++k) {
+        const double invk = 1.0 / k;
+        for (int e = tid; e < mm; e += EX_THREADS) {          // W = T A / k
+            const int i = e / m, j = e % m;
+            cplx acc = CX::zero();
+            for (int t = 0; t < m; ++t) CX::fma(acc, T[i * m + t], A[t * m + j]);
+            W[e] = CX::scale(acc, invk);
+        }
+        __syncthreads();
+        for (int e = tid; e < mm; e += EX_THREADS) {
+            T[e] = W[e];
+            X[e] = CX::add(X[e], W[e]);
+        }
+        __syncthreads();
+    }
+    for (int q = 0; q < s; ++q) {
+        for (int e = tid; e < mm; e += EX_THREADS) {
+            const int i = e / m, j = e % m;
+            cplx acc = CX::zero();
+            for (int t = 0; t < m; ++t) CX::fma(acc, X[i * m + t], X[t * m + j]);
+            W[e] = acc;
+        }
+        __syncthreads();
+        for (int e = tid; e < mm; e += EX_THREADS) X[e] = W[e];
+        __syncthreads();
+    }
+    for (int e = tid; e < mm; e += EX_THREADS) E[e] = X[e];
+}
+
+// E (m x m complex128, row-major) = exp((c_re + i c_im) * H), H complex128 row-major, m <= 96.
+extern "C" int sktt_expm_small(sktt_ctx* ctx, int64_t m, const void* H, double c_re, double c_im, void* E) {
+    if (!ctx || !H || !E) return SKTT_ERR_ARG;
+    if (m < 1 || m > 96) return sktt_fail(ctx, SKTT_ERR_ARG, "expm_small: m out of range (1..96)");
+    const size_t smem = (size_t)4 * m * m * sizeof(cplx);
+    SKTT_ONCE_PER_DEVICE(ctx);
+    if (!configured) {
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(expm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    if (smem > 200 * 1024) return sktt_fail(ctx, SKTT_ERR_ARG, "expm_small: shared memory budget exceeded");
+    expm_small_kernel<<<1, EX_THREADS, smem, ctx->stream>>>((int)m, (const cplx*)H, make_cplx(c_re, c_im), (cplx*)E);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
 }

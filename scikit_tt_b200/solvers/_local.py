@@ -21,6 +21,10 @@ from .. import _device
 # falls back to the dense LU while the matrix still fits (DENSE_FALLBACK_LIMIT), and raises only beyond that.
 # 'dense' / 'cg' / 'gmres' as `solver` force one route.
 DENSE_LIMIT = 16384
+SMALL_DENSE_LIMIT = 2048    # up to here dense LU is also the FASTEST route; between SMALL_DENSE_LIMIT and DENSE_LIMIT a micro
+                            # system that the persistent fused CG kernel covers (fp64, Hermitian, bench-type shapes: the edge
+                            # cores of C3 have 4096 unknowns) goes matrix-free FIRST -- same answer to 1e-12 or the dense LU
+                            # takes over -- everything else is factorised as the reference does
 DENSE_FALLBACK_LIMIT = 32768
 KRYLOV_TOL = 1e-14          # target TRUE relative residual of the matrix-free micro solves
 KRYLOV_ACCEPT = 1e-12       # a solve that stagnates above this is redone by dense LU where that fits
@@ -188,6 +192,10 @@ def solve_micro(dev, solver, dense_builder, op, f, guess, cache=None):
     mode = solver
     if solver in ('solve', 'lu'):
         mode = 'dense' if N <= DENSE_LIMIT else 'krylov'
+        if SMALL_DENSE_LIMIT < N <= DENSE_LIMIT and f.dtype == torch.float64 and op is not None and op.sites == 1:
+            dev.prepare_local_op(op)
+            if dev.tiled_len(op) > 0 and (cache is None or cache.get('hermitian') is not False):
+                mode = 'krylov'
     if mode == 'dense':
         M = dense_builder()
         if _TRACE:
@@ -205,6 +213,8 @@ def solve_micro(dev, solver, dense_builder, op, f, guess, cache=None):
                 herm = is_hermitian_local(dev, op, tuple(f.shape), f.dtype)
             if cache is not None:
                 cache['hermitian'] = herm
+        if not herm and solver in ('solve', 'lu') and N <= DENSE_LIMIT:
+            return dev.solve(dense_builder(), f)              # not the fused CG's business: factorise as the reference does
         method = 'cg' if herm else 'gmres'
     if _TRACE:
         print(f"  [micro] N={N} {method}", flush=True)
@@ -260,7 +270,8 @@ def download_vector_cores(cores):
 # strided-GEMM micro-matvec, the contraction engine for the (re)orthogonalisation against the Krylov basis (classical
 # Gram-Schmidt, twice), cyclic Jacobi for the projected matrix.
 EIGH_DENSE_LIMIT = 4096     # Jacobi eigh of the dense micro matrix up to here (sktt_eigh_jacobi), Lanczos above
-LANCZOS_TOL = 1e-12         # residual ||M v - theta v|| <= tol * max |theta| for the k wanted pairs
+LANCZOS_TOL = 1e-14         # residual ||M v - theta v|| <= tol * max |theta| for the k wanted pairs ...
+LANCZOS_FLOOR = 1e-11       # ... or, once restarts stop improving it (rounding floor eps * cond), at most this
 LANCZOS_MAX_RESTARTS = 200
 lanczos_stats = {"solves": 0, "matvecs": 0, "restarts": 0, "worst_residual": 0.0}
 
@@ -287,6 +298,7 @@ def eigh_matrix_free(dev, matvec, shape, dtype, k, v0=None, tol=LANCZOS_TOL, ncv
     q = 0                                        # number of locked-in Ritz vectors at the head of V
     keep = min(m - 1, k + max(4, k))             # thick restart: the wanted pairs plus a few neighbours
     matvecs = 0
+    prev_worst = np.inf
     for restart in range(max_restarts + 1):
         beta = 0.0
         for j in range(q, m):
@@ -316,7 +328,10 @@ def eigh_matrix_free(dev, matvec, shape, dtype, k, v0=None, tol=LANCZOS_TOL, ncv
         last = Y[m - 1, :].cpu().numpy()
         scale = max(np.abs(Wh).max(), 1e-300)
         res = np.abs(beta * last[m - k:])        # residual norms of the k largest Ritz pairs
-        done = bool(np.all(res <= tol * scale)) or m >= N or beta == 0.0
+        worst = float(res.max() / scale)
+        stalled = restart >= 2 and worst > 0.5 * prev_worst and worst <= LANCZOS_FLOOR
+        prev_worst = worst
+        done = bool(np.all(res <= tol * scale)) or m >= N or beta == 0.0 or stalled
         sel = slice(m - k, m) if done else slice(m - keep, m)
         Ys = Y[:, sel].contiguous()
         cnt = Ys.shape[1]

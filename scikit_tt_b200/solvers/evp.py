@@ -159,7 +159,8 @@ def als_batch(operators, initial_guesses, previous=[], shift=0, operator_gevp=No
     'eigh', micro matrices above 1024 unknowns, ragged shapes).
 
     on_unconverged: what happens to a system one of whose local eigen-solves ended without reaching the Arnoldi tolerance
-    inside the batched kernel (restarted Arnoldi, Krylov dimension 20, 20 restarts): 'redo' runs that system again through
+    inside the batched kernel (restarted Arnoldi, Krylov dimension 20, relative residual 1e-12, at most 5 restarts, leaving as
+    soon as a restart cycle gains less than a factor of ten): 'redo' runs that system again through
     the host-driven path, whose last resort is the exact full-space solve (what `lin.eig` delivers) -- the default for
     solver='eig'; 'accept' keeps the best Ritz pair and reports it (batch_stats, one RuntimeWarning per call) -- the default
     for the iterative solver='eigs', where the reference's ARPACK is restarted Arnoldi too.  Zero pivots and failures of the

@@ -190,3 +190,173 @@ def cg_sharded(L, A, Rt, f, u0=None, tol=1e-13, max_iters=2000, group=None, dev=
         rr = rr_new
         it += 1
     return u.reshape(f.shape), it, float(np.sqrt(rr / f2)) if f2 > 0 else 0.0
+
+
+# ------------------------------------------------------------------------------------------------ partition 2, fused form
+class _RawCuda:
+    """Zero-copy torch view of device memory that was not allocated by torch (peer-exchange buffers come from cudaMalloc
+    through the C-ABI so that they can be exported as CUDA IPC handles)."""
+
+    def __init__(self, ptr, nelem, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(nelem),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """The y buffers of the rank-sharded micro-matvec, mapped into every process of `group` (one process per GPU of one
+    NVSwitch domain): two alternating buffers of `nelem` elements per rank plus one slot array for the flag barrier.  The
+    last contraction of the matvec stores its rows of y into all of them from its epilogue (csrc/peer.cu); the barrier
+    kernel orders those remote stores before the readers.  Two buffers: a rank may already be writing matvec t + 1 into a
+    peer that is still reading y of matvec t; matvec t + 2 reuses the first buffer only after the barrier of t + 1, which a
+    rank passes after it has finished reading y of matvec t (stream order)."""
+
+    def __init__(self, dev, nelem, dtype, group=None):
+        import ctypes as C
+        self.dev, self.group, self.dtype = dev, group, dtype
+        self.world, self.rank = _world(group)
+        self.nelem = int(nelem)
+        item = 16 if dtype == torch.complex128 else 8
+        self._C = C
+        self.local = []                                    # raw pointers: y0, y1, flags
+        for nbytes in (self.nelem * item, self.nelem * item, 64 * 8):
+            p = C.c_void_p()
+            dev._check(dev.lib.sktt_peer_alloc(dev.h, int(nbytes), C.byref(p)))
+            self.local.append(p.value)
+        handles = []
+        for p in self.local:
+            buf = C.create_string_buffer(64)
+            dev._check(dev.lib.sktt_peer_export(dev.h, C.c_void_p(p), buf))
+            handles.append(buf.raw)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles, group=group)
+        self.opened = []
+        self.ptrs = []                                     # ptrs[g] = [y0, y1, flags] of rank g as seen from this process
+        for g in range(self.world):
+            if g == self.rank:
+                self.ptrs.append(list(self.local))
+                continue
+            mine = []
+            for h in gathered[g]:
+                p = C.c_void_p()
+                dev._check(dev.lib.sktt_peer_open(dev.h, h, C.byref(p)))
+                mine.append(p.value)
+                self.opened.append(p.value)
+            self.ptrs.append(mine)
+        typestr = "<c16" if dtype == torch.complex128 else "<f8"
+        self.y = [torch.as_tensor(_RawCuda(self.local[k], self.nelem, typestr), device=dev.device) for k in (0, 1)]
+        self.timeout = torch.zeros(1, dtype=torch.int32, device=dev.device)
+        self.epoch = 0
+        self.turn = 0
+        dist.barrier(group=group)                          # every mapping exists before the first remote store
+
+    def barrier(self):
+        C = self._C
+        self.epoch += 1
+        arr = (C.c_void_p * self.world)(*[self.ptrs[g][2] for g in range(self.world)])
+        self.dev._check(self.dev.lib.sktt_peer_barrier(self.dev.h, self.world, self.rank, self.epoch, arr,
+                                                       C.c_void_p(self.timeout.data_ptr())))
+
+    def matvec(self, L, A, Rt, v):
+        """y = M v, rows sharded over the ranks, all-gather fused into the last contraction.  Returns a view of the local
+        exchange buffer shaped like v (valid until the matvec after the next one)."""
+        C = self._C
+        dev = self.dev
+        r, R = L.shape[0], L.shape[1]
+        _, m, n, R2 = A.shape
+        r2 = Rt.shape[0]
+        N = r * m * r2
+        if N > self.nelem:
+            raise ValueError("PeerExchange buffer too small for this micro system")
+        lo, hi = shard_bounds(r, self.world, self.rank)
+        k = self.turn
+        self.turn ^= 1
+        peers = [self.ptrs[g][k] for g in range(self.world) if g != self.rank]
+        arr = (C.c_void_p * max(len(peers), 1))(*peers)
+        w = dev.work(dev.lib.sktt_sharded_matvec_work(r, R, m, n, r2, R2, max(hi - lo, 1)), v.dtype, tag="shard")
+        code = 1 if v.dtype == torch.complex128 else 0
+        dev._check(dev.lib.sktt_sharded_matvec(dev.h, code, r, R, m, n, r2, R2, C.c_void_p(L.data_ptr()),
+                                               C.c_void_p(A.data_ptr()), C.c_void_p(Rt.data_ptr()),
+                                               C.c_void_p(v.data_ptr()), lo, hi, C.c_void_p(self.local[k]), len(peers), arr,
+                                               C.c_void_p(w.data_ptr())))
+        self.barrier()
+        return self.y[k][:N].view(r, m, r2)
+
+    def check(self):
+        if int(self.timeout.item()) != 0:
+            raise RuntimeError("peer barrier timed out: a rank of the group did not reach the exchange step")
+
+    def close(self):
+        dev = self.dev
+        if getattr(self, "local", None) is None:
+            return
+        dev.sync()
+        try:
+            dist.barrier(group=self.group)                 # nobody unmaps while a peer may still store
+        except Exception:
+            pass
+        self.y = None
+        for p in self.opened:
+            dev.lib.sktt_peer_close(dev.h, self._C.c_void_p(p))
+        for p in self.local:
+            dev.lib.sktt_peer_free(dev.h, self._C.c_void_p(p))
+        self.local = None
+
+
+SHARDED_TOL = 1e-14
+SHARDED_ACCEPT = 1e-12
+SHARDED_MAX_ITERS = 5000
+SHARDED_MAX_CYCLES = 5
+sharded_stats = {"solves": 0, "matvecs": 0, "worst_relres": 0.0}
+
+
+def solve_sharded(dev, matvec, f, guess=None, tol=SHARDED_TOL, max_iters=SHARDED_MAX_ITERS):
+    """CG on the Hermitian positive definite micro system with a matvec that is sharded over the ranks (`matvec(v)` returns
+    the assembled y on every rank, bit-identical everywhere, so every rank runs the same scalar recurrences and takes the
+    same decisions: the exchange inside the matvec is the only communication).  Residual replacement as the one-GPU path:
+    after every CG run the TRUE residual f - M u is recomputed and the correction equation solved again until it is below
+    `tol` or stops improving.  Returns the flat solution; raises numpy.linalg.LinAlgError above SHARDED_ACCEPT."""
+    shape = tuple(f.shape)
+    fv = f.reshape(-1)
+    real = f.dtype == torch.float64
+    dot = (lambda a, b: dev.dotc(a, b)) if real else (lambda a, b: dev.dotc(a, b).real)
+    fnorm = np.sqrt(dot(fv, fv))
+    u = guess.reshape(-1).clone() if guess is not None and guess.numel() == fv.numel() else torch.zeros_like(fv)
+    if fnorm == 0.0:
+        return u.zero_()
+    mv = lambda x: matvec(x.reshape(shape)).reshape(-1)
+    prev, relres, used = np.inf, None, 0
+    for cycle in range(SHARDED_MAX_CYCLES):
+        res = dev.axpby(-1.0, mv(u), 1.0, fv)
+        used += 1
+        rr = dot(res, res)
+        relres = np.sqrt(rr) / fnorm
+        if cycle == 0 and not relres < 1.0:                      # a warm start worse than zero is dropped
+            u.zero_()
+            res, relres, rr = fv.clone(), 1.0, fnorm * fnorm
+        if relres <= tol or relres > 0.5 * prev:
+            break
+        prev = relres
+        target2 = (0.5 * tol * fnorm) ** 2
+        e = torch.zeros_like(fv)
+        p = res.clone()
+        r_ = res
+        for _ in range(max_iters):
+            if rr <= target2:
+                break
+            Ap = mv(p)
+            used += 1
+            pAp = dot(p, Ap)
+            if not pAp > 0.0:
+                raise np.linalg.LinAlgError("sharded CG: the micro operator is not Hermitian positive definite")
+            alpha = rr / pAp
+            dev.axpby(alpha, p, 1.0, e, out=e)
+            r_ = dev.axpby(-alpha, Ap, 1.0, r_)
+            rr_new = dot(r_, r_)
+            dev.axpby(rr_new / rr, p, 1.0, r_, out=p)
+            rr = rr_new
+        dev.axpby(1.0, e, 1.0, u, out=u)
+    sharded_stats["solves"] += 1
+    sharded_stats["matvecs"] += used
+    sharded_stats["worst_relres"] = max(sharded_stats["worst_relres"], float(relres))
+    if not relres <= SHARDED_ACCEPT:
+        raise np.linalg.LinAlgError(f"sharded CG micro solve did not converge (true relative residual {relres:.2e})")
+    return u

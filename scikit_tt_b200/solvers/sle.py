@@ -33,6 +33,8 @@ class _State:
         self.cache = {}                                  # per-call verdicts shared by the micro solves (see _local.solve_micro)
         self.out = None                                  # streamed-out result cores (see stream_out)
         self.stream_results = False                      # set by the public entry points: copy final cores out early
+        self.group = None                                # process group of a rank-sharded call (als(..., group=))
+        self.px = None                                   # its peer-mapped exchange buffers (multi.PeerExchange)
 
     # sle.py:194-247
     def left(self, i):
@@ -106,15 +108,32 @@ class _State:
         return TT(_local.download_vector_cores(self.x))
 
 
-def als(operator, initial_guess, right_hand_side, repeats=1, solver='solve'):
+def als(operator, initial_guess, right_hand_side, repeats=1, solver='solve', group=None):
     """ALS sweeps for operator @ x = right_hand_side (sle.py:10-95).
 
     solver: 'solve' / 'lu' (reference values; both an LU with partial pivoting here as there) pick the
     dense path while r*n*r' <= _local.DENSE_LIMIT and the matrix-free path above it; 'dense', 'cg',
     'gmres' force one.  Returns a new TT; inputs are not modified.
+
+    group (not in the reference): a torch.distributed process group, one process per GPU of one NVSwitch domain, every
+    rank calling with the same arguments (BASELINE config 4: one system at very large rank).  The matrix-free micro-matvec
+    is then sharded over the output solution-rank index across the ranks, its all-gather fused into the last contraction's
+    epilogue over peer memory (solvers/multi.py, csrc/peer.cu); everything else of the sweep is replicated, and every
+    rank returns the same TT.
     """
     _local.reset_stats()
     st = _State(operator, initial_guess, right_hand_side)
+    st.group = group
+    if st.group is not None:
+        try:
+            _sweeps_als(st, repeats, solver)
+            if st.px is not None:
+                st.px.check()
+        finally:
+            if st.px is not None:
+                st.px.close()
+                st.px = None
+        return st.result()
     st.stream_results = True
     _run_als(st, repeats, solver)
     return st.result()
@@ -197,7 +216,7 @@ def _sweeps_als(st, repeats, solver, check=None):
 
 
 def _wants_guess(solver, N):
-    return solver in ('cg', 'gmres', 'krylov') or (solver in ('solve', 'lu') and N > _local.DENSE_LIMIT)
+    return solver in ('cg', 'gmres', 'krylov') or (solver in ('solve', 'lu') and N > _local.SMALL_DENSE_LIMIT)
 
 
 def _pushed(dev, carry, core, left):
@@ -222,12 +241,30 @@ def _micro_als(st, i, solver, guess=None):
     with _local.phase(dev, 'micro_rhs'):
         f = dev.micro_rhs_als(st.Lrhs[i], st.b[i], st.Rrhs[i])            # sle.py:424-428
     r, n, r2 = L.shape[0], A.shape[2], R.shape[0]
-    op = dev.local_op(L, A, R)
     if guess is None or tuple(guess.shape) != (r, n, r2):
         guess = st.x[i] if tuple(st.x[i].shape) == (r, n, r2) else None
+    if st.group is not None and _wants_guess(solver, r * n * r2) and solver != 'gmres' and r >= 2 * _group_size(st.group):
+        return _solve_sharded(st, L, A, R, f, guess), (r, n, r2)
+    op = dev.local_op(L, A, R)
     with _local.phase(dev, 'solve'):
         u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_als(L, A, R), op, f, guess, st.cache)
     return u, (r, n, r2)
+
+
+def _group_size(group):
+    import torch.distributed as dist
+    return dist.get_world_size(group)
+
+
+def _solve_sharded(st, L, A, R, f, guess):
+    """One micro solve with the matvec sharded over the ranks of st.group (multi.solve_sharded); the exchange buffers are
+    created on first use, sized for the largest micro system of the call, and closed by `als`."""
+    from . import multi
+    dev = st.dev
+    if st.px is None:
+        nmax = max(int(st.x[i].shape[0] * st.A[i].shape[1] * st.x[i].shape[2]) for i in range(st.d))
+        st.px = multi.PeerExchange(dev, nmax, st.dtype, st.group)
+    return multi.solve_sharded(dev, lambda v: st.px.matvec(L, A, R, v), f, guess)
 
 
 def mals(operator, initial_guess, right_hand_side, repeats=1, solver='solve', threshold=1e-12, max_rank=np.inf):
@@ -256,7 +293,7 @@ def _run_mals(st, repeats, solver, threshold, max_rank):
                 U, S, Vh, k = dev.svd(mat, threshold=threshold, max_rank=max_rank)   # sle.py:603-614
                 uk = U[:, :k].contiguous()
                 x[i] = uk.reshape(r, n, k)                                # sle.py:616-620
-                carry = dev.matmul(uk, mat, opa='C').reshape(k, n2, r3) if mat.numel() > _local.DENSE_LIMIT else None
+                carry = dev.matmul(uk, mat, opa='C').reshape(k, n2, r3) if mat.numel() > _local.SMALL_DENSE_LIMIT else None
         left, right = carry, None
         for i in range(d - 2, -1, -1):                                    # sle.py:175-186
             st.right(i + 1)
@@ -269,7 +306,7 @@ def _run_mals(st, repeats, solver, threshold, max_rank):
             right = None
             if i == 0:
                 x[i] = dev.matmul(mat, vh, opb='C').reshape(r, n, k)      # U diag(s), sle.py:647-650
-            elif mat.numel() > _local.DENSE_LIMIT:
+            elif mat.numel() > _local.SMALL_DENSE_LIMIT:
                 right = dev.matmul(mat, vh, opb='C').reshape(r, n, k)     # U diag(s) as core i of the next two-site system
 
 
@@ -284,7 +321,7 @@ def _micro_mals(st, i, solver, left=None, right=None):
     xi = left if left is not None else st.x[i]
     xj = right if right is not None else st.x[i + 1]
     if xi.dim() == 3 and xj.dim() == 3 and xi.shape[0] == r and xj.shape[2] == r3 and xi.shape[2] == xj.shape[0] \
-            and tuple(xi.shape[1:2]) == (n,) and tuple(xj.shape[1:2]) == (n2,) and r * n * n2 * r3 > _local.DENSE_LIMIT:
+            and tuple(xi.shape[1:2]) == (n,) and tuple(xj.shape[1:2]) == (n2,) and r * n * n2 * r3 > _local.SMALL_DENSE_LIMIT:
         guess = dev.matmul(xi.reshape(r * n, xi.shape[2]), xj.reshape(xj.shape[0], n2 * r3))
     u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_mals(L, A1, A2, R), op, f.reshape(r, n, n2, r3), guess,
                            st.cache)

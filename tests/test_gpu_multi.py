@@ -75,6 +75,35 @@ def _nccl_worker(rank, world, port, out):
         want = np.linalg.solve(M, f.reshape(-1)).reshape(f.shape)
         err = np.linalg.norm(u.cpu().numpy() - want) / np.linalg.norm(want)
         assert err < 1e-10, err
+        # the fused form: rows of y stored into every rank's exchange buffer from the last contraction's epilogue
+        # (peer memory, csrc/peer.cu) + flag barrier; ping-pong buffers over several consecutive matvecs
+        px = multi.PeerExchange(dev, 64 * 16 * 24, torch.float64, None)
+        try:
+            for r in (64, 37):
+                R, m, r2, R2 = 3, 16, 24, 3
+                L, A, Rt, v = _operands(rng, r, R, m, r2, R2)
+                dL, dA, dR, dv = (dev.to_device(x) for x in (L, A, Rt, v))
+                for rep in range(3):
+                    y = px.matvec(dL, dA, dR, dv).clone().cpu().numpy()
+                    want = K.micro_matvec_als(L, A, Rt, v)
+                    assert np.linalg.norm(y - want) <= 1e-13 * np.linalg.norm(want), (r, rep)
+                    dv = dev.to_device(y / np.linalg.norm(y))
+                    v = y / np.linalg.norm(y)
+            px.check()
+        finally:
+            px.close()
+        # sle.als(..., group=): one system swept by both ranks with the micro-matvec sharded, against the one-GPU sweep
+        import workloads
+        from scikit_tt_b200.solvers import sle
+        d, n, rk = 4, 16, 24
+        opc = workloads.c4_spd_cores(d, n, 4)
+        rhs = TT(workloads.rank1_rhs(d, n))
+        x0 = TT(ott.ortho_right(workloads.random_guess(d, n, rk, seed=5)))
+        one = sle.als(TT(opc), x0, rhs, repeats=1, solver='cg')
+        two = sle.als(TT(opc), x0, rhs, repeats=1, solver='cg', group=dist.group.WORLD)
+        assert two.ranks == one.ranks
+        assert ott.norm(ott.sub(two.cores, one.cores)) / ott.norm(one.cores) < 1e-8
+        assert multi.sharded_stats["solves"] > 0 and multi.sharded_stats["worst_relres"] <= 1e-12
         # independent systems: four right-hand sides of one SPD system, two per GPU, gathered in order
         d, n, rk = 4, 6, 3
         S = 2 * np.eye(n) - np.eye(n, k=1) - np.eye(n, k=-1)

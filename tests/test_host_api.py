@@ -110,7 +110,7 @@ def test_warm_start_plumbing_of_the_sweep():
 
     assert sle._wants_guess('cg', 10) and sle._wants_guess('gmres', 10)
     assert not sle._wants_guess('dense', 10 ** 9)
-    assert sle._wants_guess('solve', _local.DENSE_LIMIT + 1) and not sle._wants_guess('solve', _local.DENSE_LIMIT)
+    assert sle._wants_guess('solve', _local.SMALL_DENSE_LIMIT + 1) and not sle._wants_guess('solve', _local.SMALL_DENSE_LIMIT)
     g = torch.Generator().manual_seed(0)
     core = torch.randn(5, 7, 3, dtype=torch.float64, generator=g)
     R = torch.randn(4, 5, dtype=torch.float64, generator=g)                   # k x r: from the QR of the core to the left

@@ -60,6 +60,33 @@ def _worker(rank, world, port, out):
             y = multi.sharded_micro_matvec(L, A, Rt, v, rows=rows_numpy)
             want = K.micro_matvec_als(L, A, Rt, v)
             assert np.linalg.norm(y - want) <= 1e-13 * np.linalg.norm(want)
+        # the CG driver of the sharded micro solve (host logic of multi.solve_sharded): identical scalar recurrences on
+        # every rank around a matvec whose rows are computed rank by rank and assembled by the collective
+        r, m = 6, 4
+        X, Y, Z = rng.standard_normal((r, r)), rng.standard_normal((m, m)), rng.standard_normal((r, r))
+        L = np.stack([np.eye(r), X @ X.T / r], axis=1)
+        A = np.stack([np.stack([Y @ Y.T / m + np.eye(m), np.zeros((m, m))], -1),
+                      np.stack([np.zeros((m, m)), np.eye(m)], -1)], 0)
+        Rt = np.stack([np.eye(r), Z @ Z.T / r + np.eye(r)], axis=1)
+        f = torch.from_numpy(rng.standard_normal((r, m, r)))
+
+        class HostDev:                                                # level-1 helpers of the device wrapper, on the host
+            def axpby(self, alpha, x, beta, y, out=None):
+                res = alpha * x + beta * y
+                if out is None:
+                    return res
+                out.copy_(res)
+                return out
+
+            def dotc(self, x, y):
+                return float(torch.dot(x, y))
+        mv = lambda v: torch.from_numpy(multi.sharded_micro_matvec(L, A, Rt, v.numpy(), rows=rows_numpy))
+        multi.sharded_stats.update(solves=0, matvecs=0, worst_relres=0.0)
+        for guess in (None, torch.from_numpy(rng.standard_normal((r, m, r))), 1e30 * torch.ones((r, m, r), dtype=torch.float64)):
+            u = multi.solve_sharded(HostDev(), mv, f, guess)
+            want = np.linalg.solve(K.micro_matrix_als(L, A, Rt), f.numpy().reshape(-1))
+            assert np.linalg.norm(u.numpy() - want) <= 1e-11 * np.linalg.norm(want)
+        assert multi.sharded_stats["solves"] == 3 and multi.sharded_stats["worst_relres"] <= 1e-12
         out.put((rank, "ok"))
     except Exception as e:                                            # surface the failure in the parent
         out.put((rank, repr(e)))
