@@ -526,7 +526,8 @@ def leg_c4(env, args):
     leg = {"workload": f"C4: sle.als, random SPD TT operator d={d}, n={n}, R={R}, solution rank {r} "
                        f"({r * n * r} unknowns per micro system)",
            "value": 2 * steps * (1 if sharded or env.world == 1 else env.world) / (ms * 1e-3), "unit": "half-sweeps/s",
-           "ms_per_step": ms / steps, "steps": steps, "n_gpus": env.world, "scaling": "strong" if sharded else "weak",
+           "ms_per_step": ms / steps, "steps": steps, "n_gpus": env.world,
+           "scaling": "strong" if (sharded or env.world == 1) else "weak",
            "parallelism": "single GPU" if env.world == 1 else
                           (f"micro-matvec sharded over the output solution-rank index across {env.world} GPUs" if sharded
                            else "replicas")}

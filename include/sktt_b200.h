@@ -290,6 +290,14 @@ int sktt_eig_shift_invert(sktt_ctx* ctx, int dtype, int64_t N, void* Mat, const 
                           double sigma, int64_t k, int64_t ncv, double tol, int max_restarts,
                           void* lam, void* vecs, void* work, int* nconv_host);
 
+/* np.linalg.solve (sle.py:505-506) of one dense fp64 system in ONE cooperative launch (N <=
+ * sktt_lu_fused_max_n()): panel factorisation in shared memory, DMMA trailing updates, the
+ * right-hand side carried as one more column block, blocked back substitution.  Mat is overwritten
+ * by L \ U (LAPACK layout), b by the solution (b == NULL: factorisation only), ipiv_dev [N] gets the
+ * 0-based pivot rows, info_dev 0 or 1 + index of the first zero pivot.  Nothing is read back.   */
+int64_t sktt_lu_fused_max_n(void);
+int sktt_lu_solve_fused(sktt_ctx* ctx, int64_t N, void* Mat, void* b, int32_t* ipiv_dev, int32_t* info_dev);
+
 /* ------------------------------------------------------------------ batched small systems ----
  * a batch of independent systems with identical shapes (BASELINE config 5: the
  * CO-pressure sweep of examples/co_oxidation.py:100-104 loops evp.als over the pressures; here the
@@ -362,9 +370,17 @@ int sktt_sharded_matvec(sktt_ctx* ctx, int dtype, int64_t r, int64_t R, int64_t 
  * exp(-i h M) to a core through scipy's expm_multiply or the fixed-dimension local_krylov
  * (ode.py:1689-1757).  Here the action is a Krylov projection on the device (matvecs and
  * orthogonalisation through the contraction engine) and this entry point exponentiates the small
- * projected matrix: E = exp((c_re + i c_im) H), H and E complex128 row-major, m <= 96, one CTA,
+ * projected matrix: E = exp((c_re + i c_im) H), H and E complex128 row-major, m <= 64, one CTA,
  * scaling and squaring around a degree-18 Taylor polynomial.                                     */
 int sktt_expm_small(sktt_ctx* ctx, int64_t m, const void* H, double c_re, double c_im, void* E);
+
+/* ------------------------------------------------------------------ TT algebra around the path
+ * TT.__matmul__ (scikit_tt/tensor_train.py:422-503), one core:
+ *   out[(p,s), m, n, (q,t)] = sum_k A[p,m,k,q] B[s,k,n,t]
+ * used by the operator-times-train products of the time steppers (ode.py:431-437) and by
+ * tt.residual_error (tensor_train.py:2035-2074).                                                 */
+int sktt_tt_matmul_core(sktt_ctx* ctx, int dtype, int64_t P, int64_t m, int64_t K, int64_t Q, int64_t S,
+                        int64_t n, int64_t T, const void* A, const void* B, void* out);
 
 /* ------------------------------------------------------------------ small helpers ------------ */
 /* out[i] = alpha * x[i] (+ y[i] if y != NULL), n elements */

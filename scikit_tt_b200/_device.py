@@ -352,13 +352,33 @@ class Device:
         self._check(self.lib.sktt_lu_solve(self.h, dtype_code(LU), N, nrhs, _ptr(LU), _ptr(ipiv), _ptr(B)))
         return B
 
+    def solve_fused(self, M, f, want_pivots=False):
+        """np.linalg.solve of one fp64 system in ONE cooperative launch (csrc/lu_fused.cu); M is overwritten by L \\ U.
+        Returns the solution (and the 0-based pivot rows)."""
+        N = M.shape[0]
+        x = f.reshape(-1).clone()
+        ipiv = torch.empty(N, dtype=torch.int32, device=self.device)
+        info = torch.empty(1, dtype=torch.int32, device=self.device)
+        self._check(self.lib.sktt_lu_solve_fused(self.h, N, _ptr(M), _ptr(x), _ptr(ipiv), _ptr(info)))
+        if int(info.item()) != 0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        return (x, ipiv) if want_pivots else x
+
     def solve(self, M, f):
         """np.linalg.solve semantics (M destroyed): raises numpy.linalg.LinAlgError when singular."""
+        if M.dtype == torch.float64 and M.shape[0] <= self.fused_lu_max_n() and f.numel() == M.shape[0]:
+            return self.solve_fused(M, f)
         ipiv, info = self.lu_factor(M)
         if info != 0:
             raise np.linalg.LinAlgError("Singular matrix")
         x = f.reshape(-1).clone()
         return self.lu_solve(M, ipiv, x)
+
+    def fused_lu_max_n(self):
+        n = getattr(self, "_fused_lu_max_n", None)
+        if n is None:
+            n = self._fused_lu_max_n = int(self.lib.sktt_lu_fused_max_n())
+        return n
 
     def chol_factor(self, M):
         info = C.c_int(0)
@@ -613,8 +633,19 @@ class Device:
                                                  int(conj_in), _ptr(out), out[0].numel(), so_i, so_t, int(conj_out)))
         return out
 
+    def tt_matmul_core(self, A, B):
+        """A [P, m, K, Q] (x) B [S, K, n, T] -> [P * S, m, n, Q * T]: one core of TT.__matmul__ (tensor_train.py:422-503)."""
+        A, B = common_dtype(A.contiguous(), B.contiguous())
+        P, m, K, Q = A.shape
+        S, K2, n, T = B.shape
+        if K != K2:
+            raise ValueError("Dimensions do not match.")
+        out = self.empty((P * S, m, n, Q * T), A.dtype)
+        self._check(self.lib.sktt_tt_matmul_core(self.h, dtype_code(A), P, m, K, Q, S, n, T, _ptr(A), _ptr(B), _ptr(out)))
+        return out
+
     def expm_small(self, H, c):
-        """exp(c * H) of a small dense complex128 matrix (m <= 96) on the device."""
+        """exp(c * H) of a small dense complex128 matrix (m <= 64) on the device."""
         m = H.shape[0]
         H = H.contiguous() if H.dtype == torch.complex128 else self.widen(H.contiguous())
         E = self.empty((m, m), torch.complex128)

@@ -54,6 +54,8 @@ SIGNATURES = {
     "sktt_rank1_update": (i32, [vp, i32, i64, dbl, vp, vp]),
     "sktt_lu_factor": (i32, [vp, i32, i64, vp, vp, pint]),
     "sktt_lu_solve": (i32, [vp, i32, i64, i64, vp, vp, vp]),
+    "sktt_lu_fused_max_n": (i64, []),
+    "sktt_lu_solve_fused": (i32, [vp, i64, vp, vp, vp, vp]),
     "sktt_chol_factor": (i32, [vp, i32, i64, vp, pint]),
     "sktt_chol_solve": (i32, [vp, i32, i64, i64, vp, vp]),
     "sktt_chol_trsm": (i32, [vp, i32, i64, i64, vp, vp, i32]),
@@ -93,6 +95,7 @@ SIGNATURES = {
     "sktt_sharded_matvec_work": (i64, [i64] * 7),
     "sktt_sharded_matvec": (i32, [vp, i32] + [i64] * 6 + [vp] * 4 + [i64, i64, vp, i32, C.POINTER(vp), vp]),
     "sktt_expm_small": (i32, [vp, i64, vp, dbl, dbl, vp]),
+    "sktt_tt_matmul_core": (i32, [vp, i32] + [i64] * 7 + [vp] * 3),
     "sktt_axpby": (i32, [vp, i32, i64, pdbl, vp, pdbl, vp, vp]),
     "sktt_nrm2": (i32, [vp, i32, i64, vp, pdbl]),
     "sktt_dotc": (i32, [vp, i32, i64, vp, vp, pdbl]),

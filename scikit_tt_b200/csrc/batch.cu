@@ -705,18 +705,18 @@ extern "C" int sktt_batch_svd_left(sktt_ctx* ctx, int64_t batch, int64_t P, int6
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// E = exp(c * H) for one small dense complex matrix (m <= 96), one CTA: scaling and squaring around a Taylor polynomial of
-// degree 18 on ||c H||_1 / 2^s <= 1/2 (truncation error ~ 0.5^19 / 19! relative, far below fp64 rounding).  The projected
-// problems of the exponential integrators (ode.tdvp*: scipy.sparse.linalg.expm_multiply of the micro matrix, ode.py:1437-1508;
-// local_krylov, ode.py:1689-1757) are of this size.
+// E = exp(c * H) for one small dense complex matrix (m <= 64), one CTA: scaling and squaring around a Taylor polynomial of
+// degree 18 (Horner form) on ||c H||_1 / 2^s <= 1/2 (truncation error ~ 0.5^19 / 19! relative, far below fp64 rounding).
+// The projected problems of the exponential integrators (ode.tdvp*: scipy.sparse.linalg.expm_multiply of the micro matrix,
+// ode.py:1437-1508; local_krylov, ode.py:1689-1757) are of this size.
 #define EX_THREADS 256
+#define EX_MAX_M 64
 __global__ void __launch_bounds__(EX_THREADS) expm_small_kernel(int m, const cplx* __restrict__ H, cplx cc, cplx* __restrict__ E) {
     extern __shared__ unsigned char smem_raw[];
     cplx* A = (cplx*)smem_raw;        // [m][m]  c H / 2^s
-    cplx* T = A + m * m;              // current Taylor term
-    cplx* X = T + m * m;              // accumulated sum / squaring result
+    cplx* X = A + m * m;              // Horner accumulator / squaring result
     cplx* W = X + m * m;              // product scratch
-    __shared__ double colsum[96];
+    __shared__ double colsum[EX_MAX_M];
     __shared__ int s_scale;
     const int tid = threadIdx.x, mm = m * m;
     for (int e = tid; e < mm; e += EX_THREADS) A[e] = CX::mul(cc, H[e]);
@@ -739,24 +739,21 @@ __global__ void __launch_bounds__(EX_THREADS) expm_small_kernel(int m, const cpl
     const double sc = ldexp(1.0, -s);
     for (int e = tid; e < mm; e += EX_THREADS) {
         A[e] = CX::scale(A[e], sc);
-        const cplx id = (e / m == e % m) ? CX::one() : CX::zero();
-        T[e] = id;
-        X[e] = id;
+        X[e] = (e / m == e % m) ? CX::one() : CX::zero();
     }
     __syncthreads();
-    for (int k = 1; k <= 18; ++k) {
+    for (int k = 18; k >= 1; --k) {                           // X <- I + A X / k
         const double invk = 1.0 / k;
-        for (int e = tid; e < mm; e += EX_THREADS) {          // W = T A / k
+        for (int e = tid; e < mm; e += EX_THREADS) {
             const int i = e / m, j = e % m;
             cplx acc = CX::zero();
-            for (int t = 0; t < m; ++t) CX::fma(acc, T[i * m + t], A[t * m + j]);
-            W[e] = CX::scale(acc, invk);
+            for (int t = 0; t < m; ++t) CX::fma(acc, A[i * m + t], X[t * m + j]);
+            acc = CX::scale(acc, invk);
+            if (i == j) acc.re += 1.0;
+            W[e] = acc;
         }
         __syncthreads();
-        for (int e = tid; e < mm; e += EX_THREADS) {
-            T[e] = W[e];
-            X[e] = CX::add(X[e], W[e]);
-        }
+        for (int e = tid; e < mm; e += EX_THREADS) X[e] = W[e];
         __syncthreads();
     }
     for (int q = 0; q < s; ++q) {
@@ -773,17 +770,16 @@ __global__ void __launch_bounds__(EX_THREADS) expm_small_kernel(int m, const cpl
     for (int e = tid; e < mm; e += EX_THREADS) E[e] = X[e];
 }
 
-// E (m x m complex128, row-major) = exp((c_re + i c_im) * H), H complex128 row-major, m <= 96.
+// E (m x m complex128, row-major) = exp((c_re + i c_im) * H), H complex128 row-major, m <= 64.
 extern "C" int sktt_expm_small(sktt_ctx* ctx, int64_t m, const void* H, double c_re, double c_im, void* E) {
     if (!ctx || !H || !E) return SKTT_ERR_ARG;
-    if (m < 1 || m > 96) return sktt_fail(ctx, SKTT_ERR_ARG, "expm_small: m out of range (1..96)");
-    const size_t smem = (size_t)4 * m * m * sizeof(cplx);
+    if (m < 1 || m > EX_MAX_M) return sktt_fail(ctx, SKTT_ERR_ARG, "expm_small: m out of range (1..64)");
+    const size_t smem = (size_t)3 * m * m * sizeof(cplx);
     SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(expm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    if (smem > 200 * 1024) return sktt_fail(ctx, SKTT_ERR_ARG, "expm_small: shared memory budget exceeded");
     expm_small_kernel<<<1, EX_THREADS, smem, ctx->stream>>>((int)m, (const cplx*)H, make_cplx(c_re, c_im), (cplx*)E);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;

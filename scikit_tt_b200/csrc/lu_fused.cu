@@ -1,0 +1,341 @@
+// lu_fused.cu -- np.linalg.solve of one dense fp64 micro system (sle.py:505-509: gesv = LU with partial pivoting + two
+// triangular solves) as ONE cooperative launch, for the sizes of BASELINE config 1 (signaling cascade, solution rank 4:
+// 1024 unknowns) and of the same-configuration leg of the bench.  The host-driven factorisation of lu.cu issues ~100
+// launches per 1024^2 system and is bound by their latency and by one cluster barrier per column (4.0 ms + 0.34 ms for the
+// solve); here the loop over the panels lives on the device:
+//
+//   per panel of 16 columns
+//     CTA 0        : panel factorisation in shared memory ((N - j0) x 16 doubles): per column a block-wide arg-max (LAPACK's
+//                    first-maximum rule), the row interchange, multipliers and the rank-1 update of the panel -- three CTA
+//                    barriers per column;
+//     grid barrier
+//     all CTAs     : one work item per block of 8 trailing columns (the right-hand side is one more item): the rows the
+//                    panel's interchanges touch are gathered once, permuted in shared memory and scattered back; the top 16
+//                    rows are solved against the unit-lower triangle (U12); every remaining row block of 8 gets its rank-16
+//                    update as four DMMA.8x8x4 per warp (C = A[i:i+8, J] -= L21[i:i+8, :] U12[:, J]);
+//     grid barrier
+//   afterwards     : the interchanges of later panels are applied to the L columns of earlier ones (net permutation per
+//                    column block, staged through shared memory), and CTA 0 runs the blocked back substitution with U on the
+//                    right-hand side, which has received every L update on the way as if it were a column of the matrix.
+//
+// Pivot sequence and arithmetic order of the elimination are those of the unblocked right-looking algorithm, so the pivots
+// equal LAPACK's (tests/test_gpu_kernels.py) and the result is bit-reproducible run to run.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "blas1.cuh"
+namespace cg = cooperative_groups;
+
+#define LF_NB 16
+#define LF_CB 8
+#define LF_THREADS 512
+#define LF_MAX_N 2048
+#define LF_LDP (LF_NB + 1)          // pitch of the panel in shared memory
+
+struct LfArgs {
+    int N;
+    double* A;        // [N][N] row-major, overwritten by L \ U
+    double* b;        // [N] right-hand side, overwritten by the solution (may be null: factorisation only)
+    int* ipiv;        // [N] 0-based pivot rows (row j was exchanged with row ipiv[j]), as LAPACK's getrf minus one
+    int* info;        // 0, or 1 + index of the first exactly-zero pivot
+};
+
+__device__ __forceinline__ void lf_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// element (row, col) of a column block that is either part of the matrix or the right-hand side
+struct LfCols {
+    double* base;
+    long long ld;
+    __device__ __forceinline__ double& at(int row, int col) const { return base[(long long)row * ld + col]; }
+};
+
+__global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    const int N = a.N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = LF_THREADS / 32;
+    double* sm = reinterpret_cast<double*>(smem_raw);
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_piv[LF_NB];
+    __shared__ int s_pos[2 * LF_NB], s_content[2 * LF_NB], s_np;
+    const int npan = (N + LF_NB - 1) / LF_NB;
+
+    for (int k = 0; k < npan; ++k) {
+        const int j0 = k * LF_NB, nb = min(LF_NB, N - j0), rows = N - j0;
+        // ------------------------------------------------------------------ panel factorisation (CTA 0)
+        if (blockIdx.x == 0) {
+            double* P = sm;                                   // [rows][LF_LDP]
+            for (int e = tid; e < rows * nb; e += LF_THREADS) {
+                const int r = e / nb, c = e - r * nb;
+                P[r * LF_LDP + c] = a.A[(long long)(j0 + r) * N + j0 + c];
+            }
+            __syncthreads();
+            for (int c = 0; c < nb; ++c) {
+                double best = -1.0;
+                int bi = c;
+                for (int r = c + tid; r < rows; r += LF_THREADS) {
+                    const double v = fabs(P[r * LF_LDP + c]);
+                    if (v > best) { best = v; bi = r; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+                __syncthreads();
+                best = s_val[0];
+                bi = s_idx[0];
+#pragma unroll
+                for (int w = 1; w < LF_THREADS / 32; ++w)
+                    if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
+                // every thread holds the same (best, bi): LAPACK's idamax picks the first maximum
+                if (tid < nb && bi != c) {                    // row interchange inside the panel
+                    const double t = P[c * LF_LDP + tid];
+                    P[c * LF_LDP + tid] = P[bi * LF_LDP + tid];
+                    P[bi * LF_LDP + tid] = t;
+                }
+                if (tid == 0) {
+                    s_piv[c] = j0 + bi;
+                    if (!(best > 0.0) && atomicCAS(a.info, 0, j0 + c + 1) == 0) {}
+                }
+                __syncthreads();
+                const double piv = P[c * LF_LDP + c];
+                const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
+                for (int r = c + 1 + tid; r < rows; r += LF_THREADS) {
+                    double* row = P + r * LF_LDP;
+                    const double l = row[c] * inv;            // multiplier by the reciprocal of the pivot, as LAPACK's getf2
+                    row[c] = l;
+#pragma unroll
+                    for (int cc = 0; cc < LF_NB; ++cc)
+                        if (cc > c && cc < nb) row[cc] = fma(-l, P[c * LF_LDP + cc], row[cc]);
+                }
+                __syncthreads();
+            }
+            for (int e = tid; e < rows * nb; e += LF_THREADS) {
+                const int r = e / nb, c = e - r * nb;
+                a.A[(long long)(j0 + r) * N + j0 + c] = P[r * LF_LDP + c];
+            }
+            if (tid < nb) a.ipiv[j0 + tid] = s_piv[tid];
+            __threadfence();
+        }
+        grid.sync();
+        // ------------------------------------------------------------------ trailing update (all CTAs)
+        const int ctrail = N - j0 - nb;                       // trailing columns
+        const int nmat = (ctrail + LF_CB - 1) / LF_CB;
+        const int nitems = nmat + (a.b ? 1 : 0);
+        if (nitems > 0) {
+            double* L11 = sm;                                 // [nb][LF_LDP] unit-lower triangle of the panel
+            double* top = L11 + LF_NB * LF_LDP;               // [2 nb][LF_CB] gathered rows, then U12 in its first nb rows
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                LfCols cols;
+                int cw;
+                if (item < nmat) {
+                    const int c0 = j0 + nb + item * LF_CB;
+                    cols.base = a.A + c0;
+                    cols.ld = N;
+                    cw = min(LF_CB, N - c0);
+                } else {
+                    cols.base = a.b;
+                    cols.ld = 1;
+                    cw = 1;
+                }
+                __syncthreads();
+                for (int e = tid; e < nb * nb; e += LF_THREADS) {
+                    const int r = e / nb, c = e - r * nb;
+                    L11[r * LF_LDP + c] = a.A[(long long)(j0 + r) * N + j0 + c];
+                }
+                if (tid == 0) {
+                    // positions the interchanges touch: the nb top rows, then every pivot row not yet listed; `content`
+                    // follows the rows through the sequence of interchanges
+                    int np = nb;
+                    for (int c = 0; c < nb; ++c) { s_pos[c] = j0 + c; s_content[c] = c; }
+                    for (int c = 0; c < nb; ++c) {
+                        const int p = a.ipiv[j0 + c];
+                        int ip = -1;
+                        for (int q = 0; q < np; ++q)
+                            if (s_pos[q] == p) ip = q;
+                        if (ip < 0) { ip = np; s_pos[np] = p; s_content[np] = np; ++np; }
+                        const int t = s_content[c];
+                        s_content[c] = s_content[ip];
+                        s_content[ip] = t;
+                    }
+                    s_np = np;
+                }
+                __syncthreads();
+                const int np = s_np;
+                for (int e = tid; e < np * cw; e += LF_THREADS) {
+                    const int q = e / cw, c = e - q * cw;
+                    top[q * LF_CB + c] = cols.at(s_pos[s_content[q]], c);
+                }
+                __syncthreads();
+                // U12 = L11^-1 top (unit lower): column-oriented elimination, one thread per (row, column)
+                for (int c = 0; c < nb - 1; ++c) {
+                    for (int e = tid; e < (nb - 1 - c) * cw; e += LF_THREADS) {
+                        const int r = c + 1 + e / cw, cc = e % cw;
+                        top[r * LF_CB + cc] = fma(-L11[r * LF_LDP + c], top[c * LF_CB + cc], top[r * LF_CB + cc]);
+                    }
+                    __syncthreads();
+                }
+                for (int e = tid; e < np * cw; e += LF_THREADS) {
+                    const int q = e / cw, c = e - q * cw;
+                    cols.at(s_pos[q], c) = top[q * LF_CB + c];
+                }
+                __syncthreads();
+                // rank-nb update of the rows below the panel: one 8-row block per warp and step
+                const int fr = lane >> 2, fk = lane & 3;
+                const int rbeg = j0 + nb, nblk8 = (N - rbeg + 7) / 8;
+                for (int blk = warp; blk < nblk8; blk += nwarps) {
+                    const int i = rbeg + 8 * blk + fr;        // this lane's row of the A-fragment
+                    const bool rok = i < N;
+                    double acc0 = 0.0, acc1 = 0.0;
+                    const double* lrow = a.A + (long long)(rok ? i : rbeg) * N + j0;
+                    double af[4];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const int kk = 4 * s + fk;
+                        af[s] = (rok && kk < nb) ? lrow[kk] : 0.0;
+                    }
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const int kk = 4 * s + fk;
+                        const double bf = (kk < nb && fr < cw) ? top[kk * LF_CB + fr] : 0.0;   // B fragment: k = kk, n = fr
+                        lf_dmma(acc0, acc1, af[s], bf);
+                    }
+                    // C fragment: row fr, columns 2 fk and 2 fk + 1
+                    if (rok) {
+                        const int c = 2 * fk;
+                        if (c < cw) cols.at(i, c) -= acc0;
+                        if (c + 1 < cw) cols.at(i, c + 1) -= acc1;
+                    }
+                }
+            }
+            __threadfence();
+        }
+        grid.sync();
+    }
+    // ---------------------------------------------------------------------- interchanges of later panels on earlier L columns
+    {
+        int* perm = reinterpret_cast<int*>(sm);               // [N]
+        double* stage = sm + ((N + 1) / 2 + 1);               // [N][LF_CB] (doubles; perm occupies N ints in front)
+        const int ncb = (N + LF_CB - 1) / LF_CB;
+        for (int cb = blockIdx.x; cb < ncb; cb += gridDim.x) {
+            const int c0 = cb * LF_CB, cw = min(LF_CB, N - c0);
+            const int kp = c0 / LF_NB;                        // panel these columns belong to (LF_NB is a multiple of LF_CB)
+            const int rfirst = (kp + 1) * LF_NB;              // interchanges of panels > kp act on rows >= rfirst
+            if (rfirst >= N) continue;
+            __syncthreads();
+            for (int i = rfirst + tid; i < N; i += LF_THREADS) perm[i] = i;
+            __syncthreads();
+            if (tid == 0)
+                for (int j = rfirst; j < N; ++j) {
+                    const int p = a.ipiv[j];
+                    if (p != j) {
+                        const int t = perm[j];
+                        perm[j] = perm[p];
+                        perm[p] = t;
+                    }
+                }
+            __syncthreads();
+            for (int e = tid; e < (N - rfirst) * cw; e += LF_THREADS) {
+                const int i = rfirst + e / cw, c = e % cw;
+                stage[(size_t)(i - rfirst) * LF_CB + c] = a.A[(long long)perm[i] * N + c0 + c];
+            }
+            __syncthreads();
+            for (int e = tid; e < (N - rfirst) * cw; e += LF_THREADS) {
+                const int i = rfirst + e / cw, c = e % cw;
+                a.A[(long long)i * N + c0 + c] = stage[(size_t)(i - rfirst) * LF_CB + c];
+            }
+        }
+    }
+    if (!a.b) return;
+    // ---------------------------------------------------------------------- back substitution with U (CTA 0); the L part is done
+    if (blockIdx.x != 0) return;
+    {
+        double* x = sm;                                       // [N]
+        double* D = x + N;                                    // [LF_NB][LF_LDP] diagonal block of U
+        for (int i = tid; i < N; i += LF_THREADS) x[i] = a.b[i];
+        __syncthreads();
+        for (int k = npan - 1; k >= 0; --k) {
+            const int j0 = k * LF_NB, nb = min(LF_NB, N - j0);
+            for (int e = tid; e < nb * nb; e += LF_THREADS) {
+                const int r = e / nb, c = e - r * nb;
+                D[r * LF_LDP + c] = a.A[(long long)(j0 + r) * N + j0 + c];
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double val = lane < nb ? x[j0 + lane] : 0.0;
+                for (int c = nb - 1; c >= 0; --c) {
+                    if (lane == c) val = val / D[c * LF_LDP + c];
+                    const double xc = __shfl_sync(0xffffffffu, val, c);
+                    if (lane < c) val = fma(-D[lane * LF_LDP + c], xc, val);
+                }
+                if (lane < nb) x[j0 + lane] = val;
+            }
+            __syncthreads();
+            for (int i = tid; i < j0; i += LF_THREADS) {      // rows above: x_i -= U[i, block] x_block
+                const double* u = a.A + (long long)i * N + j0;
+                double acc = x[i];
+#pragma unroll
+                for (int c = 0; c < LF_NB; ++c)
+                    if (c < nb) acc = fma(-u[c], x[j0 + c], acc);
+                x[i] = acc;
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < N; i += LF_THREADS) a.b[i] = x[i];
+    }
+}
+
+static size_t lf_smem(int N) {
+    size_t panel = (size_t)N * LF_LDP * sizeof(double);
+    size_t upd = ((size_t)LF_NB * LF_LDP + 2 * LF_NB * LF_CB) * sizeof(double);
+    size_t fix = ((size_t)(N + 1) / 2 + 1 + (size_t)N * LF_CB) * sizeof(double);
+    size_t back = ((size_t)N + LF_NB * LF_LDP) * sizeof(double);
+    size_t m = panel;
+    if (upd > m) m = upd;
+    if (fix > m) m = fix;
+    if (back > m) m = back;
+    return m + 64;
+}
+
+// Largest N the one-launch form takes (shared-memory panel of N x 17 doubles).
+extern "C" int64_t sktt_lu_fused_max_n(void) { return 1536; }
+
+// Solves A x = b for a dense fp64 system in ONE launch: A [N][N] row-major is overwritten by its LU factors (unit lower L,
+// LAPACK layout), b [N] by the solution (b == NULL: factorisation only), ipiv_dev [N] receives the 0-based pivot rows,
+// info_dev (int32, device) 0 or 1 + index of the first exactly-zero pivot.  Nothing is read back.
+extern "C" int sktt_lu_solve_fused(sktt_ctx* ctx, int64_t N, void* A, void* b, int32_t* ipiv_dev, int32_t* info_dev) {
+    if (!ctx || !A || !ipiv_dev || !info_dev) return SKTT_ERR_ARG;
+    if (N < 1 || N > sktt_lu_fused_max_n()) return sktt_fail(ctx, SKTT_ERR_ARG, "lu_solve_fused: N out of range");
+    const size_t smem = lf_smem((int)N);
+    if (smem > 220 * 1024) return sktt_fail(ctx, SKTT_ERR_ARG, "lu_solve_fused: shared memory budget exceeded");
+    SKTT_ONCE_PER_DEVICE(ctx);
+    if (!configured) {
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured = true;
+    }
+    SKTT_CUDA(ctx, cudaMemsetAsync(info_dev, 0, sizeof(int32_t), ctx->stream));
+    LfArgs a;
+    a.N = (int)N;
+    a.A = (double*)A;
+    a.b = (double*)b;
+    a.ipiv = ipiv_dev;
+    a.info = info_dev;
+    int per_sm = 0;
+    SKTT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lu_fused_kernel, LF_THREADS, smem));
+    if (per_sm < 1) return sktt_fail(ctx, SKTT_ERR_ARG, "lu_solve_fused: kernel does not fit an SM");
+    int grid = ctx->sm_count;
+    const int want = (int)((N / LF_CB) + 1);
+    if (grid > want) grid = want;
+    void* args[] = {&a};
+    SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)lu_fused_kernel, dim3(grid), dim3(LF_THREADS), args, smem, ctx->stream));
+    ctx->launches++;
+    return 0;
+}

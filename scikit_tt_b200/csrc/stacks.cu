@@ -700,3 +700,45 @@ extern "C" int sktt_local_matvec_tiled_repeat(sktt_ctx* ctx, int dtype, const sk
                                      nullptr, nullptr, nullptr, (double*)yt, (double*)work, 0.0, 0, 0, 1, reps, part,
                                      part + 4 * 256);
 }
+
+// ---------------------------------------------------------------------------------- TT algebra around the solvers
+// TT.__matmul__ (scikit_tt/tensor_train.py:422-503), one core:
+//   out[(p, s), m, n, (q, t)] = sum_k A[p, m, k, q] B[s, k, n, t]
+// -- the operator-times-train product of the time steppers (ode.py:431-437), of tt.residual_error
+// (tensor_train.py:2035-2074) and of the closeness checks (examples/co_oxidation.py:111).  One thread per output entry, the
+// contraction index k (a mode size) is short; reads of B are coalesced along t.
+template <typename T>
+__global__ void tt_matmul_core_kernel(int P, int m, int K, int Q, int S, int n, int Tt, const T* __restrict__ A,
+                                      const T* __restrict__ B, T* __restrict__ out) {
+    const long long total = (long long)P * S * m * n * Q * Tt;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long r = e;
+        const int t = (int)(r % Tt); r /= Tt;
+        const int q = (int)(r % Q); r /= Q;
+        const int nn = (int)(r % n); r /= n;
+        const int mm = (int)(r % m); r /= m;
+        const int s = (int)(r % S);
+        const int p = (int)(r / S);
+        T acc = Num<T>::zero();
+        for (int k = 0; k < K; ++k)
+            Num<T>::fma(acc, A[(((long long)p * m + mm) * K + k) * Q + q], B[(((long long)s * K + k) * n + nn) * Tt + t]);
+        out[e] = acc;
+    }
+}
+
+extern "C" int sktt_tt_matmul_core(sktt_ctx* ctx, int dtype, int64_t P, int64_t m, int64_t K, int64_t Q, int64_t S, int64_t n,
+                                   int64_t Tt, const void* A, const void* B, void* out) {
+    if (!ctx || !A || !B || !out) return SKTT_ERR_ARG;
+    SKTT_TRY(check_dtype(ctx, dtype));
+    const long long total = P * S * m * n * Q * Tt;
+    if (total <= 0) return 0;
+    int blocks = (int)((total + 255) / 256 < 16LL * ctx->sm_count ? (total + 255) / 256 : 16LL * ctx->sm_count);
+    if (dtype == SKTT_F64)
+        tt_matmul_core_kernel<double><<<blocks, 256, 0, ctx->stream>>>((int)P, (int)m, (int)K, (int)Q, (int)S, (int)n, (int)Tt,
+                                                                       (const double*)A, (const double*)B, (double*)out);
+    else
+        tt_matmul_core_kernel<cplx><<<blocks, 256, 0, ctx->stream>>>((int)P, (int)m, (int)K, (int)Q, (int)S, (int)n, (int)Tt,
+                                                                     (const cplx*)A, (const cplx*)B, (cplx*)out);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}

@@ -15,6 +15,17 @@ import numpy as np
 from . import _device
 
 
+# TT algebra around the solvers: `@` and `residual_error` run on the device once the contraction work
+# is worth an upload (the cores of a TT live on the host by contract, tensor_train.py:149-267); below that the plain numpy
+# statement of the same formula is used.  Both give the same numbers to rounding; set to 0 to force the device.
+DEVICE_ALGEBRA_MIN_WORK = 1 << 22
+
+
+def _device_algebra(work):
+    import torch
+    return work >= DEVICE_ALGEBRA_MIN_WORK and torch.cuda.is_available()
+
+
 def _is_int(v):
     return isinstance(v, (int, np.integer)) and not isinstance(v, bool)
 
@@ -103,10 +114,20 @@ class TT(object):
             raise TypeError('Unsupported argument.')
         if self.col_dims != other.row_dims:
             raise ValueError('Dimensions do not match.')
-        cores = []
-        for a, b in zip(self.cores, other.cores):
-            c = np.einsum('pmkq,sknt->psmnqt', a, b)
-            cores.append(c.reshape(a.shape[0] * b.shape[0], a.shape[1], b.shape[2], a.shape[3] * b.shape[3]))
+        work = sum(a.shape[0] * b.shape[0] * a.shape[1] * a.shape[2] * b.shape[2] * a.shape[3] * b.shape[3]
+                   for a, b in zip(self.cores, other.cores))
+        if _device_algebra(work):                              # one kernel per core (sktt_tt_matmul_core), one DMA each way
+            import torch
+            dev = _device.get_device()
+            cplx = any(np.iscomplexobj(c) for c in self.cores + other.cores)
+            dt = torch.complex128 if cplx else torch.float64
+            da, db = dev.upload_many(self.cores, dt), dev.upload_many(other.cores, dt)
+            cores = dev.download_many([dev.tt_matmul_core(a, b) for a, b in zip(da, db)])
+        else:
+            cores = []
+            for a, b in zip(self.cores, other.cores):
+                c = np.einsum('pmkq,sknt->psmnqt', a, b)
+                cores.append(c.reshape(a.shape[0] * b.shape[0], a.shape[1], b.shape[2], a.shape[3] * b.shape[3]))
         t = TT(cores)
         if np.prod(t.row_dims) == 1 and np.prod(t.col_dims) == 1:
             return t.element([0] * (2 * t.order))
@@ -356,6 +377,10 @@ def residual_error(operator, lhs, rhs):
     train: the running factor is re-compressed by a QR-type factorisation at every core.  Host numpy
     (verification helper either side of the hot path)."""
     d = operator.order
+    work = sum(A.shape[0] * x.shape[0] * A.shape[1] * A.shape[2] * A.shape[3] * x.shape[3]
+               for A, x in zip(operator.cores, lhs.cores))
+    if d > 1 and _device_algebra(work):
+        return _residual_error_device(operator, lhs, rhs)
     carry = None
     err = None
     for i in range(d):
@@ -379,3 +404,36 @@ def residual_error(operator, lhs, rhs):
         else:
             carry = np.linalg.qr(core.reshape(-1, core.shape[2]), mode='r')
     return err
+
+
+def _residual_error_device(operator, lhs, rhs):
+    """The same core-by-core evaluation on the device: A_i x_i by the TT-matmul kernel, the block core [A x | -b] /
+    [[A x, 0], [0, b]] / [A x; b] assembled in HBM, the running triangular factor pushed through by the contraction engine
+    and re-compressed by the QR kernels; one scalar comes back."""
+    import torch
+    dev = _device.get_device()
+    d = operator.order
+    cplx = any(np.iscomplexobj(c) for t in (operator, lhs, rhs) for c in t.cores)
+    dt = torch.complex128 if cplx else torch.float64
+    dA, dx, db = (dev.upload_many(t.cores, dt) for t in (operator, lhs, rhs))
+    carry = None
+    for i in range(d):
+        ax = dev.tt_matmul_core(dA[i], dx[i])[:, :, 0, :]                 # [R r, m, R2 r2]
+        bb = db[i][:, :, 0, :]                                           # [p, m, p2]
+        ra, m, ca = ax.shape
+        rb, _, cb = bb.shape
+        if i == 0:
+            core = torch.cat([ax, -bb], dim=2)
+        elif i == d - 1:
+            core = torch.cat([ax, bb], dim=0)
+        else:
+            core = torch.zeros((ra + rb, m, ca + cb), dtype=dt, device=dev.device)
+            core[:ra, :, :ca] = ax
+            core[ra:, :, ca:] = bb
+        if carry is not None:
+            core = dev.matmul(carry, core.reshape(core.shape[0], -1).contiguous()).reshape(carry.shape[0], m, -1)
+        if i == d - 1:
+            return dev.nrm2(core.reshape(-1).contiguous())
+        mat = core.reshape(-1, core.shape[2]).contiguous()
+        _, carry = dev.qr(mat, want_r=True)
+    return None

@@ -19,7 +19,7 @@ def test_expm_small_and_action(dev):
     import torch
     from scikit_tt_b200.solvers import ode
     rng = np.random.default_rng(5)
-    for m, c in ((1, 0.3), (7, -0.5j), (20, 2.0 - 1.0j), (48, -3.0j), (96, 0.7)):
+    for m, c in ((1, 0.3), (7, -0.5j), (20, 2.0 - 1.0j), (48, -3.0j), (64, 0.7)):
         H = rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m))
         got = dev.expm_small(dev.to_device(H), c).cpu().numpy()
         want = sla.expm(c * H)
@@ -58,3 +58,79 @@ def test_tdvp_against_the_reference(dev, tag, h, solver, normalize):
         from oracle import tt as ott
         nrm = [ott.norm(t.cores) for t in ode.tdvp1site(op, x0, h, 3)]
         assert max(abs(n - nrm[0]) for n in nrm) < 1e-10
+
+
+def test_tt_algebra_on_device(dev, monkeypatch):
+    """`@` and `tt.residual_error` through the device kernels against the host statement of the same
+    formulas (tensor_train.py:422-503, :2035-2074), real and complex, and against the oracle."""
+    import workloads
+    import scikit_tt_b200.tensor_train as tt
+    from scikit_tt_b200 import TT
+    from oracle import tt as ott, sle as osle
+    rng = np.random.default_rng(9)
+    d, n, r = 5, 8, 6
+    op = TT(workloads.laplace_cores(d, n))
+    x = TT(workloads.random_guess(d, n, r, seed=2))
+    b = TT(workloads.rank1_rhs(d, n))
+    xc = TT([c + 1j * rng.standard_normal(c.shape) for c in x.cores])
+    monkeypatch.setattr(tt, "DEVICE_ALGEBRA_MIN_WORK", 1 << 60)
+    host = [op @ x, op @ xc, op @ op]
+    res_host = [tt.residual_error(op, x, b), tt.residual_error(op, xc, b)]
+    l0 = dev.launches()
+    monkeypatch.setattr(tt, "DEVICE_ALGEBRA_MIN_WORK", 0)
+    devi = [op @ x, op @ xc, op @ op]
+    res_dev = [tt.residual_error(op, x, b), tt.residual_error(op, xc, b)]
+    assert dev.launches() > l0
+    for h, g in zip(host, devi):
+        assert g.ranks == h.ranks and g.row_dims == h.row_dims and g.col_dims == h.col_dims
+        for ch, cg in zip(h.cores, g.cores):
+            assert cg.dtype == ch.dtype and np.linalg.norm(cg - ch) <= 1e-14 * max(np.linalg.norm(ch), 1e-300)
+    for h, g in zip(res_host, res_dev):
+        assert abs(g - h) <= 1e-11 * h
+    want = osle.residual(op.cores, x.cores, b.cores) * ott.norm(b.cores)
+    assert abs(res_dev[0] - want) <= 1e-9 * want
+    assert np.isscalar(TT([np.ones((1, 1, 3, 1))]) @ TT([np.ones((1, 3, 1, 1))]))       # fully contracted product -> scalar
+
+
+def test_power_method_against_the_reference(dev):
+    """evp.power_method (evp.py:182-250): inverse power iteration on top of the GPU sle.als, plain and generalised, against
+    the live reference (tests/golden/make_power_golden.py) -- eigenvalue to 1e-10, eigentensor to 1e-8."""
+    import workloads
+    from scikit_tt_b200 import TT
+    from scikit_tt_b200.solvers import evp
+    z = load("power_method")
+    op = TT(workloads.laplace_cores(4, 6, c=0.05))
+    x0, gev = _T(cores(z, "x0")), _T(cores(z, "gev"))
+    for tag, kw in (("plain", {}), ("gevp", {"operator_gevp": gev})):
+        for reps in (1, 3):
+            lam, x = evp.power_method(op, x0, repeats=reps, sigma=0.3, **kw)
+            ref = float(z[f"{tag}/rep{reps}/lam"])
+            assert abs(lam - ref) <= 1e-10 * abs(ref), (tag, reps, lam, ref)
+            assert rel_diff(x.cores, cores(z, f"{tag}/rep{reps}/x")) < 1e-8, (tag, reps)
+
+
+@pytest.mark.parametrize("N", [1, 5, 16, 17, 100, 256, 1000, 1024, 1536])
+def test_fused_lu_solve(dev, N):
+    """np.linalg.solve in one cooperative launch (csrc/lu_fused.cu): solution, LU factors and LAPACK's pivot sequence."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(N)
+    M = rng.standard_normal((N, N))
+    if N >= 100:
+        M[7, :] = M[3, :] * (1 + 1e-3 * rng.standard_normal(N))        # ill-conditioned rows: pivoting matters
+    f = rng.standard_normal(N)
+    dM = dev.to_device(M)
+    x, piv = dev.solve_fused(dM, dev.to_device(f), want_pivots=True)
+    lu_ref, piv_ref = sla.lu_factor(M)
+    assert np.array_equal(piv.cpu().numpy(), piv_ref)
+    got = dM.cpu().numpy()
+    assert np.linalg.norm(got - lu_ref) <= 1e-11 * np.linalg.norm(lu_ref)
+    want = np.linalg.solve(M, f)
+    assert np.linalg.norm(x.cpu().numpy() - want) <= 1e-9 * np.linalg.norm(want)
+    again_M = dev.to_device(M)
+    again = dev.solve_fused(again_M, dev.to_device(f))
+    assert np.array_equal(again.cpu().numpy(), x.cpu().numpy()) and np.array_equal(again_M.cpu().numpy(), got)   # bit-reproducible
+    if N >= 16:
+        S = M.copy()
+        S[:, 9] = 0.0
+        with pytest.raises(np.linalg.LinAlgError):
+            dev.solve(dev.to_device(S), dev.to_device(f))
