@@ -525,6 +525,44 @@ class Device:
         self.last_svd_sweeps = sweeps.value
         return U, S, Vh, rank.value
 
+    SVD_DIRECT_LIMIT = 1024     # min(m, n) up to which the full Jacobi SVD is the route whatever max_rank says
+    svd_topk_stats = {"calls": 0, "iterations": 0, "fallbacks": 0}
+
+    def svd_truncated(self, A, threshold=0.0, max_rank=0):
+        """The truncated SVD of sle.py:603-614 / :626-639 for a super-core whose full SVD is out of reach (C3 / C4 two-site
+        blocks: 4096 x 4096) but of which only `max_rank` << min(m, n) singular triplets are kept: subspace iteration for the
+        dominant left subspace of dimension max_rank + oversampling (products through the DMMA contraction engine,
+        orthonormalisation by the QR kernels), then the accurate one-sided Jacobi SVD of the small projected matrix
+        Q^H A.  Iterated until the kept singular values stop moving (1e-12 relative); falls back to the full SVD when they do
+        not settle (flat spectrum at the cut).  Same return convention as `svd`: (U, S, Vh, rank) with at least `rank`
+        columns / rows."""
+        m, n = A.shape
+        mr = 0 if (max_rank is None or max_rank == np.inf or max_rank <= 0) else int(max_rank)
+        k = min(m, n)
+        if mr == 0 or k <= self.SVD_DIRECT_LIMIT or 4 * mr > k:
+            return self.svd(A, threshold=threshold, max_rank=max_rank)
+        self.svd_topk_stats["calls"] += 1
+        l = min(k, mr + max(16, mr // 2))
+        g = torch.Generator(device=self.device).manual_seed(20240229)
+        Om = torch.randn((n, l), dtype=torch.float64, device=self.device, generator=g)
+        if A.dtype == torch.complex128:
+            Om = self.widen(Om)
+        Q = self.qr(self.matmul(A, Om))                            # [m, l]
+        S_prev = None
+        for it in range(12):
+            Z = self.qr(self.matmul(A, Q, opa='C'))                # [n, l]: A^H Q, orthonormalised
+            Q = self.qr(self.matmul(A, Z))                         # [m, l]
+            B = self.matmul(Q, A, opa='C')                         # [l, n] = Q^H A
+            Ub, S, Vh, rank = self.svd(B, threshold=threshold, max_rank=mr)
+            self.svd_topk_stats["iterations"] += 1
+            Sh = S[:mr].cpu().numpy()
+            if S_prev is not None and np.all(np.abs(Sh - S_prev) <= 1e-12 * Sh[0]):
+                U = self.matmul(Q, Ub)                             # [m, l]
+                return U, S, Vh, rank
+            S_prev = Sh
+        self.svd_topk_stats["fallbacks"] += 1
+        return self.svd(A, threshold=threshold, max_rank=max_rank)
+
     # ------------------------------------------------------------------ eigen
     def eigh(self, M):
         N = M.shape[0]

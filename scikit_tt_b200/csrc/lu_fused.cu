@@ -90,11 +90,14 @@ __global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs a) {
                 }
                 if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
                 __syncthreads();
-                best = s_val[0];
-                bi = s_idx[0];
+                best = s_val[lane & (LF_THREADS / 32 - 1)];   // 16 warp results, combined by a 4-step butterfly in every warp
+                bi = s_idx[lane & (LF_THREADS / 32 - 1)];
 #pragma unroll
-                for (int w = 1; w < LF_THREADS / 32; ++w)
-                    if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
+                for (int o = LF_THREADS / 64; o > 0; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
                 // every thread holds the same (best, bi): LAPACK's idamax picks the first maximum
                 if (tid < nb && bi != c) {                    // row interchange inside the panel
                     const double t = P[c * LF_LDP + tid];
@@ -151,13 +154,15 @@ __global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs a) {
                     const int r = e / nb, c = e - r * nb;
                     L11[r * LF_LDP + c] = a.A[(long long)(j0 + r) * N + j0 + c];
                 }
+                if (tid < nb) s_piv[tid] = a.ipiv[j0 + tid];
+                __syncthreads();
                 if (tid == 0) {
                     // positions the interchanges touch: the nb top rows, then every pivot row not yet listed; `content`
                     // follows the rows through the sequence of interchanges
                     int np = nb;
                     for (int c = 0; c < nb; ++c) { s_pos[c] = j0 + c; s_content[c] = c; }
                     for (int c = 0; c < nb; ++c) {
-                        const int p = a.ipiv[j0 + c];
+                        const int p = s_piv[c];
                         int ip = -1;
                         for (int q = 0; q < np; ++q)
                             if (s_pos[q] == p) ip = q;
@@ -176,13 +181,19 @@ __global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs a) {
                 }
                 __syncthreads();
                 // U12 = L11^-1 top (unit lower): column-oriented elimination, one thread per (row, column)
-                for (int c = 0; c < nb - 1; ++c) {
-                    for (int e = tid; e < (nb - 1 - c) * cw; e += LF_THREADS) {
-                        const int r = c + 1 + e / cw, cc = e % cw;
-                        top[r * LF_CB + cc] = fma(-L11[r * LF_LDP + c], top[c * LF_CB + cc], top[r * LF_CB + cc]);
+                // (row-oriented inside one warp: lane = (row, column); row r needs rows < r only, so the rows are walked in
+                // order with a warp barrier between them instead of a CTA barrier per column)
+                if (warp == 0) {
+                    for (int r = 1; r < nb; ++r) {
+                        if (lane < cw) {
+                            double acc = top[r * LF_CB + lane];
+                            for (int c = 0; c < r; ++c) acc = fma(-L11[r * LF_LDP + c], top[c * LF_CB + lane], acc);
+                            top[r * LF_CB + lane] = acc;
+                        }
+                        __syncwarp();
                     }
-                    __syncthreads();
                 }
+                __syncthreads();
                 for (int e = tid; e < np * cw; e += LF_THREADS) {
                     const int q = e / cw, c = e - q * cw;
                     cols.at(s_pos[q], c) = top[q * LF_CB + c];
@@ -191,28 +202,41 @@ __global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs a) {
                 // rank-nb update of the rows below the panel: one 8-row block per warp and step
                 const int fr = lane >> 2, fk = lane & 3;
                 const int rbeg = j0 + nb, nblk8 = (N - rbeg + 7) / 8;
-                for (int blk = warp; blk < nblk8; blk += nwarps) {
-                    const int i = rbeg + 8 * blk + fr;        // this lane's row of the A-fragment
-                    const bool rok = i < N;
-                    double acc0 = 0.0, acc1 = 0.0;
-                    const double* lrow = a.A + (long long)(rok ? i : rbeg) * N + j0;
-                    double af[4];
+                double bfrag[4];                              // B fragments: k = 4 s + fk, n = fr (U12, shared memory)
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        const int kk = 4 * s + fk;
-                        af[s] = (rok && kk < nb) ? lrow[kk] : 0.0;
+                for (int s = 0; s < 4; ++s) {
+                    const int kk = 4 * s + fk;
+                    bfrag[s] = (kk < nb && fr < cw) ? top[kk * LF_CB + fr] : 0.0;
+                }
+                const int cc0 = 2 * fk;
+                for (int blk0 = warp; blk0 < nblk8; blk0 += 4 * nwarps) {
+                    // four row blocks per warp and pass: every load is issued before the first store
+                    double af[4][4], cv[4][2];
+                    int irow[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int blk = blk0 + u * nwarps;
+                        const int i = rbeg + 8 * blk + fr;
+                        const bool rok = blk < nblk8 && i < N;
+                        irow[u] = rok ? i : -1;
+                        const double* lrow = a.A + (long long)(rok ? i : rbeg) * N + j0;
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            const int kk = 4 * s + fk;
+                            af[u][s] = (rok && kk < nb) ? lrow[kk] : 0.0;
+                        }
+                        cv[u][0] = (rok && cc0 < cw) ? cols.at(i, cc0) : 0.0;
+                        cv[u][1] = (rok && cc0 + 1 < cw) ? cols.at(i, cc0 + 1) : 0.0;
                     }
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        const int kk = 4 * s + fk;
-                        const double bf = (kk < nb && fr < cw) ? top[kk * LF_CB + fr] : 0.0;   // B fragment: k = kk, n = fr
-                        lf_dmma(acc0, acc1, af[s], bf);
-                    }
-                    // C fragment: row fr, columns 2 fk and 2 fk + 1
-                    if (rok) {
-                        const int c = 2 * fk;
-                        if (c < cw) cols.at(i, c) -= acc0;
-                        if (c + 1 < cw) cols.at(i, c + 1) -= acc1;
+                    for (int u = 0; u < 4; ++u) {
+                        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) lf_dmma(acc0, acc1, af[u][s], bfrag[s]);
+                        if (irow[u] >= 0) {
+                            if (cc0 < cw) cols.at(irow[u], cc0) = cv[u][0] - acc0;
+                            if (cc0 + 1 < cw) cols.at(irow[u], cc0 + 1) = cv[u][1] - acc1;
+                        }
                     }
                 }
             }

@@ -290,7 +290,7 @@ def _run_mals(st, repeats, solver, threshold, max_rank):
             if i < d - 2:
                 u, (r, n, n2, r3) = _micro_mals(st, i, solver, left=carry)
                 mat = u.reshape(r * n, n2 * r3)
-                U, S, Vh, k = dev.svd(mat, threshold=threshold, max_rank=max_rank)   # sle.py:603-614
+                U, S, Vh, k = dev.svd_truncated(mat, threshold=threshold, max_rank=max_rank)   # sle.py:603-614
                 uk = U[:, :k].contiguous()
                 x[i] = uk.reshape(r, n, k)                                # sle.py:616-620
                 carry = dev.matmul(uk, mat, opa='C').reshape(k, n2, r3) if mat.numel() > _local.SMALL_DENSE_LIMIT else None
@@ -300,7 +300,7 @@ def _run_mals(st, repeats, solver, threshold, max_rank):
             u, (r, n, n2, r3) = _micro_mals(st, i, solver, left=left, right=right)
             left = None
             mat = u.reshape(r * n, n2 * r3)
-            U, S, Vh, k = dev.svd(mat, threshold=threshold, max_rank=max_rank)                             # sle.py:626-639
+            U, S, Vh, k = dev.svd_truncated(mat, threshold=threshold, max_rank=max_rank)                             # sle.py:626-639
             vh = Vh[:k, :].contiguous()
             x[i + 1] = vh.reshape(k, n2, r3)                              # sle.py:645
             right = None

@@ -379,7 +379,10 @@ def residual_error(operator, lhs, rhs):
     d = operator.order
     work = sum(A.shape[0] * x.shape[0] * A.shape[1] * A.shape[2] * A.shape[3] * x.shape[3]
                for A, x in zip(operator.cores, lhs.cores))
-    if d > 1 and _device_algebra(work):
+    # the device route re-compresses the running factor with the shared-memory QR kernels: bond dimensions R r' + p' up to
+    # 512 (C3: 193); wider bonds (C4 at r >= 128: 1025) stay on the host
+    width = max(A.shape[3] * x.shape[3] + b.shape[3] for A, x, b in zip(operator.cores, lhs.cores, rhs.cores))
+    if d > 1 and width <= 512 and _device_algebra(work):
         return _residual_error_device(operator, lhs, rhs)
     carry = None
     err = None
@@ -435,5 +438,17 @@ def _residual_error_device(operator, lhs, rhs):
         if i == d - 1:
             return dev.nrm2(core.reshape(-1).contiguous())
         mat = core.reshape(-1, core.shape[2]).contiguous()
-        _, carry = dev.qr(mat, want_r=True)
+        carry = _r_factor(dev, mat)
     return None
+
+
+def _r_factor(dev, mat):
+    """Triangular factor of a tall matrix; row blocks that exceed what the cooperative QR kernel holds in shared memory are
+    factorised separately and their triangles stacked (TSQR)."""
+    import torch
+    rows, cols = mat.shape
+    limit = max(2 * cols, 3_000_000 // (cols + 1))
+    if rows <= limit:
+        return dev.qr(mat, want_r=True)[1]
+    parts = [_r_factor(dev, mat[i:i + limit].contiguous()) for i in range(0, rows, limit)]
+    return _r_factor(dev, torch.cat(parts, dim=0).contiguous())
