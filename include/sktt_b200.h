@@ -382,6 +382,20 @@ int sktt_expm_small(sktt_ctx* ctx, int64_t m, const void* H, double c_re, double
 int sktt_tt_matmul_core(sktt_ctx* ctx, int dtype, int64_t P, int64_t m, int64_t K, int64_t Q, int64_t S,
                         int64_t n, int64_t T, const void* A, const void* B, void* out);
 
+/* ------------------------------------------------------------------ alternating ridge regression
+ * scikit_tt/data_driven/regression.py:297-420 (fp64): the ALS skeleton with sample-indexed stacks.
+ * which = 0: __arr_construct_stack_left  (:323-325)  out[l,j] = sum L[a,j] Phi[k,j] C[a,k,l]
+ * which = 1: __arr_construct_stack_right (:354-356)  out[a,j] = sum C[a,k,l] Phi[k,j] R[l,j]
+ * stack [r or r2, m], Phi [n, m] (basis functions of the mode evaluated on the m samples), core
+ * [r, n, r2].  sktt_arr_micro_matrix (:388-392): out[(a,k,l), j] = L[a,j] Phi[k,j] R[l,j].
+ * sktt_pinv_scale: the singular-value cut of lstsq(..., cond=rcond) (:419): t_i <- t_i / s_i where
+ * s_i > rcond * s_0, else 0.                                                                     */
+int sktt_arr_stack(sktt_ctx* ctx, int which, int64_t r, int64_t n, int64_t r2, int64_t m, const void* stack,
+                   const void* Phi, const void* core, void* out);
+int sktt_arr_micro_matrix(sktt_ctx* ctx, int64_t r, int64_t n, int64_t r2, int64_t m, const void* L,
+                          const void* Phi, const void* R, void* out);
+int sktt_pinv_scale(sktt_ctx* ctx, int64_t k, const double* s, double rcond, double* t);
+
 /* ------------------------------------------------------------------ small helpers ------------ */
 /* out[i] = alpha * x[i] (+ y[i] if y != NULL), n elements */
 int sktt_axpby(sktt_ctx* ctx, int dtype, int64_t n, const double* alpha, const void* x,

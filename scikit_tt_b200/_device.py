@@ -682,6 +682,36 @@ class Device:
         self._check(self.lib.sktt_tt_matmul_core(self.h, dtype_code(A), P, m, K, Q, S, n, T, _ptr(A), _ptr(B), _ptr(out)))
         return out
 
+    # ------------------------------------------------------------------ alternating ridge regression (fp64)
+    def arr_stack_left(self, L, Phi, core):
+        r, n, r2 = core.shape
+        m = Phi.shape[1]
+        out = self.empty((r2, m), torch.float64)
+        self._check(self.lib.sktt_arr_stack(self.h, 0, r, n, r2, m, _ptr(L), _ptr(Phi), _ptr(core), _ptr(out)))
+        return out
+
+    def arr_stack_right(self, R, Phi, core):
+        r, n, r2 = core.shape
+        m = Phi.shape[1]
+        out = self.empty((r, m), torch.float64)
+        self._check(self.lib.sktt_arr_stack(self.h, 1, r, n, r2, m, _ptr(R), _ptr(Phi), _ptr(core), _ptr(out)))
+        return out
+
+    def arr_micro_matrix(self, L, Phi, R):
+        r, n, r2, m = L.shape[0], Phi.shape[0], R.shape[0], Phi.shape[1]
+        out = self.empty((r * n * r2, m), torch.float64)
+        self._check(self.lib.sktt_arr_micro_matrix(self.h, r, n, r2, m, _ptr(L), _ptr(Phi), _ptr(R), _ptr(out)))
+        return out
+
+    def lstsq_gelss(self, A, b, rcond):
+        """Minimum-norm least-squares solution of A x = b (A [m, N], b [m]) with the singular values below rcond * s_0
+        dropped -- scipy.linalg.lstsq(A, b, cond=rcond, lapack_driver='gelss') (regression.py:419) on the device: one-sided
+        Jacobi SVD, two thin products, the cut in between."""
+        U, S, Vh, _ = self.svd(A.contiguous())
+        t = self.matmul(U, b.reshape(-1, 1), opa='C').reshape(-1)
+        self._check(self.lib.sktt_pinv_scale(self.h, S.numel(), _ptr(S), float(rcond), _ptr(t)))
+        return self.matmul(Vh, t.reshape(-1, 1), opa='C').reshape(-1)
+
     def expm_small(self, H, c):
         """exp(c * H) of a small dense complex128 matrix (m <= 64) on the device."""
         m = H.shape[0]

@@ -96,6 +96,9 @@ SIGNATURES = {
     "sktt_sharded_matvec": (i32, [vp, i32] + [i64] * 6 + [vp] * 4 + [i64, i64, vp, i32, C.POINTER(vp), vp]),
     "sktt_expm_small": (i32, [vp, i64, vp, dbl, dbl, vp]),
     "sktt_tt_matmul_core": (i32, [vp, i32] + [i64] * 7 + [vp] * 3),
+    "sktt_arr_stack": (i32, [vp, i32, i64, i64, i64, i64, vp, vp, vp, vp]),
+    "sktt_arr_micro_matrix": (i32, [vp, i64, i64, i64, i64, vp, vp, vp, vp]),
+    "sktt_pinv_scale": (i32, [vp, i64, vp, dbl, vp]),
     "sktt_axpby": (i32, [vp, i32, i64, pdbl, vp, pdbl, vp, vp]),
     "sktt_nrm2": (i32, [vp, i32, i64, vp, pdbl]),
     "sktt_dotc": (i32, [vp, i32, i64, vp, vp, pdbl]),

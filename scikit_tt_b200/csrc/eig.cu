@@ -166,7 +166,9 @@ static int eig_si_impl(sktt_ctx* ctx, int dtype, long long N, T* Mat, const T* B
     ipiv = (int*)(Ysel + (size_t)m * k);
     int* flags = ipiv + 2 * N;                  // [0] nconv, [1] hess info
     cplx* hwork = (cplx*)((((uintptr_t)(flags + 8)) + 15) & ~(uintptr_t)15);   // [3][m][m], used when m > EIG_SMEM_NCV
-    double* slots = (double*)ctx->scratch;      // [0..1] nrm2
+    // scalar slots [0..1] (nrm2) at the head of the context scratch: re-derived at every use, because the LU / GEMM calls in
+    // between may grow the scratch allocation (sktt_scratch_reserve frees and reallocates it)
+#define slots ((double*)ctx->scratch)
     const int nbk = (int)((N + 255) / 256 < 4LL * ctx->sm_count ? (N + 255) / 256 : 4LL * ctx->sm_count);
 
     // S = M - sigma B, LU
@@ -278,6 +280,7 @@ static int eig_si_impl(sktt_ctx* ctx, int dtype, long long N, T* Mat, const T* B
     SKTT_LAUNCH_CHECK(ctx);
     if (nconv_host) *nconv_host = nconv;
     return 0;
+#undef slots
 }
 
 extern "C" int sktt_eig_shift_invert(sktt_ctx* ctx, int dtype, int64_t N, void* Mat, const void* Bmat, double sigma,

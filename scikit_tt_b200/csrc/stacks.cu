@@ -742,3 +742,100 @@ extern "C" int sktt_tt_matmul_core(sktt_ctx* ctx, int dtype, int64_t P, int64_t 
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
 }
+
+// ---------------------------------------------------------------------------------- alternating ridge regression
+// scikit_tt/data_driven/regression.py:297-420 -- the ALS sweep skeleton with SAMPLE-indexed stacks:
+//   left  : out[l, j] = sum_{a,k} L[a, j] Phi[k, j] C[a, k, l]          (regression.py:323-325)
+//   right : out[a, j] = sum_{k,l} C[a, k, l] Phi[k, j] R[l, j]          (regression.py:354-356)
+//   micro : M[(a, k, l), j] = L[a, j] Phi[k, j] R[l, j]                  (regression.py:388-392)
+// j runs over the m samples (thousands), the other extents are ranks / basis sizes: one thread per output entry, the sample
+// index fastest so that every read of L, Phi, R is coalesced.
+__global__ void arr_stack_left_kernel(int r, int n, int r2, long long m, const double* __restrict__ L, const double* __restrict__ Phi,
+                                      const double* __restrict__ C, double* __restrict__ out) {
+    const long long total = (long long)r2 * m;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long j = e % m;
+        const int l = (int)(e / m);
+        double acc = 0.0;
+        for (int a = 0; a < r; ++a) {
+            const double la = L[a * m + j];
+            double inner = 0.0;
+            for (int k = 0; k < n; ++k) inner = fma(Phi[k * m + j], C[((long long)a * n + k) * r2 + l], inner);
+            acc = fma(la, inner, acc);
+        }
+        out[e] = acc;
+    }
+}
+
+__global__ void arr_stack_right_kernel(int r, int n, int r2, long long m, const double* __restrict__ C, const double* __restrict__ Phi,
+                                       const double* __restrict__ R, double* __restrict__ out) {
+    const long long total = (long long)r * m;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long j = e % m;
+        const int a = (int)(e / m);
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double pk = Phi[k * m + j];
+            double inner = 0.0;
+            for (int l = 0; l < r2; ++l) inner = fma(C[((long long)a * n + k) * r2 + l], R[l * m + j], inner);
+            acc = fma(pk, inner, acc);
+        }
+        out[e] = acc;
+    }
+}
+
+__global__ void arr_micro_matrix_kernel(int r, int n, int r2, long long m, const double* __restrict__ L, const double* __restrict__ Phi,
+                                        const double* __restrict__ R, double* __restrict__ out) {
+    const long long total = (long long)r * n * r2 * m;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long j = e % m;
+        long long t = e / m;
+        const int l = (int)(t % r2);
+        t /= r2;
+        const int k = (int)(t % n);
+        const int a = (int)(t / n);
+        out[e] = L[a * m + j] * Phi[k * m + j] * R[l * m + j];
+    }
+}
+
+// t[i] <- t[i] / s[i] where s[i] > rcond * s[0], 0 elsewhere (the singular-value cut of lstsq(..., cond=rcond), gelss)
+__global__ void pinv_scale_kernel(int k, const double* __restrict__ s, double rcond, double* __restrict__ t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) t[i] = (s[i] > rcond * s[0]) ? t[i] / s[i] : 0.0;
+}
+
+extern "C" int sktt_arr_stack(sktt_ctx* ctx, int which, int64_t r, int64_t n, int64_t r2, int64_t m, const void* stack,
+                              const void* Phi, const void* core, void* out) {
+    if (!ctx || !stack || !Phi || !core || !out) return SKTT_ERR_ARG;
+    const long long total = (which == 0 ? r2 : r) * m;
+    if (total <= 0) return 0;
+    int blocks = (int)((total + 255) / 256 < 8LL * ctx->sm_count ? (total + 255) / 256 : 8LL * ctx->sm_count);
+    if (which == 0)
+        arr_stack_left_kernel<<<blocks, 256, 0, ctx->stream>>>((int)r, (int)n, (int)r2, m, (const double*)stack, (const double*)Phi,
+                                                              (const double*)core, (double*)out);
+    else
+        arr_stack_right_kernel<<<blocks, 256, 0, ctx->stream>>>((int)r, (int)n, (int)r2, m, (const double*)core, (const double*)Phi,
+                                                               (const double*)stack, (double*)out);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int sktt_arr_micro_matrix(sktt_ctx* ctx, int64_t r, int64_t n, int64_t r2, int64_t m, const void* L, const void* Phi,
+                                     const void* R, void* out) {
+    if (!ctx || !L || !Phi || !R || !out) return SKTT_ERR_ARG;
+    const long long total = r * n * r2 * m;
+    if (total <= 0) return 0;
+    int blocks = (int)((total + 255) / 256 < 16LL * ctx->sm_count ? (total + 255) / 256 : 16LL * ctx->sm_count);
+    arr_micro_matrix_kernel<<<blocks, 256, 0, ctx->stream>>>((int)r, (int)n, (int)r2, m, (const double*)L, (const double*)Phi,
+                                                            (const double*)R, (double*)out);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int sktt_pinv_scale(sktt_ctx* ctx, int64_t k, const double* s, double rcond, double* t) {
+    if (!ctx || !s || !t || k < 0) return SKTT_ERR_ARG;
+    if (k == 0) return 0;
+    pinv_scale_kernel<<<(unsigned)((k + 127) / 128), 128, 0, ctx->stream>>>((int)k, s, rcond, t);
+    SKTT_LAUNCH_CHECK(ctx);
+    return 0;
+}

@@ -259,3 +259,30 @@ def test_c5_mini_batch(dev):
             return ott.norm(ott.sub(ott.matmul(ops[j].cores, v), ott.scale(v, l))) / ott.norm(v)
         q_new, q_ref = quality(batch[j][0], batch[j][1].cores), quality(float(np.real(lam_o)), x_o)
         assert q_new <= 10 * q_ref + 1e-6, (j, q_new, q_ref)
+
+
+@pytest.mark.gpu
+def test_nearly_symmetric_operator_takes_the_safe_route(dev, monkeypatch):
+    """The matrix-free route is entered on a randomised Hermitian probe of the local operator.  An operator that is symmetric
+    only up to a 1e-7 relative perturbation must NOT be handed to CG as if it were symmetric: the probe rejects it (GMRES or
+    the dense LU take over) and the sweep agrees with the dense reference algorithm to 1e-8; a perturbation at rounding level
+    (1e-15) is indistinguishable from symmetric and converges with CG to the same answer."""
+    from scikit_tt_b200 import TT
+    from scikit_tt_b200.solvers import sle, _local
+    d, n, r = 5, 16, 8
+    rng = np.random.default_rng(3)
+    for eps in (1e-7, 1e-15):
+        opc = workloads.laplace_cores(d, n)
+        skew = rng.standard_normal((n, n))
+        opc[2] = opc[2].copy()
+        opc[2][2, :, :, 0] += eps * (skew - skew.T)                 # breaks the symmetry of one block by eps
+        op, rhs = TT(opc), TT(workloads.rank1_rhs(d, n))
+        x0 = TT(ott.ortho_right(workloads.random_guess(d, n, r, seed=4)))
+        ref = osle.als(opc, x0.cores, rhs.cores, repeats=2)         # the reference algorithm: dense LU throughout
+        monkeypatch.setattr(_local, "DENSE_LIMIT", 64)              # r n r = 1024 > 64 -> matrix-free route for 'solve'
+        monkeypatch.setattr(_local, "SMALL_DENSE_LIMIT", 64)
+        monkeypatch.setattr(_local, "DENSE_FALLBACK_LIMIT", 64)     # ... and no dense rescue: the Krylov route must be right
+        sol = sle.als(op, x0, rhs, repeats=2)
+        monkeypatch.undo()
+        assert rel_diff(sol.cores, ref) < SOL_TOL, eps
+        assert _local.stats["krylov_solves"] > 0 and _local.stats["worst_relres"] <= 1e-12

@@ -134,3 +134,37 @@ def test_fused_lu_solve(dev, N):
         S[:, 9] = 0.0
         with pytest.raises(np.linalg.LinAlgError):
             dev.solve(dev.to_device(S), dev.to_device(f))
+
+
+def test_arr_against_the_reference(dev):
+    """data_driven.regression.arr (regression.py:15-142): alternating ridge regression with sample-indexed stacks and an
+    SVD-based least-squares micro solve, against the live reference (tests/golden/make_arr_golden.py): coefficient tensors to
+    1e-8, and the fit they represent reproduces the targets."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_arr_golden import basis
+    from scikit_tt_b200 import TT
+    from scikit_tt_b200.data_driven import regression as reg
+    z = load("arr")
+    x, y = z["x"], z["y"]
+    d = x.shape[0]
+    guess = TT([z[f"guess/{i}"] for i in range(d)])
+    for reps in (1, 3):
+        sol = reg.arr(x, y, basis(d), guess, repeats=reps, rcond=1e-10, progress=False)
+        assert len(sol) == 2 and all(isinstance(t, TT) for t in sol)
+        for k, t in enumerate(sol):
+            ref = [z[f"rep{reps}/row{k}/{i}"] for i in range(d)]
+            assert t.ranks == [c.shape[0] for c in ref] + [1]
+            assert rel_diff(t.cores, ref) < 1e-8, (reps, k)
+    # the fit the coefficient tensors represent is the reference's fit (same training error to 1e-8)
+    Phi = [np.array([[f(x[:, j]) for j in range(x.shape[1])] for f in mode]) for mode in basis(d)]
+
+    def predict(cores_):
+        acc = np.ones((1, x.shape[1]))
+        for c, P in zip(cores_, Phi):
+            acc = np.einsum('aj,kj,akl->lj', acc, P, c[:, :, 0, :])
+        return acc[0]
+    for k, t in enumerate(sol):
+        ref = [z[f"rep3/row{k}/{i}"] for i in range(d)]
+        e_new, e_ref = np.linalg.norm(predict(t.cores) - y[k]), np.linalg.norm(predict(ref) - y[k])
+        assert abs(e_new - e_ref) <= 1e-8 * np.linalg.norm(y[k]), (k, e_new, e_ref)
