@@ -30,6 +30,12 @@ int sktt_fused_matvec_ex(sktt_ctx* ctx, long long r, long long R, long long m, l
 int sktt_fused_stack_update(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
                             const double* xt, double* out, double* T1p, double* part);
 
+// stack_nat.cu: the one-launch form that reads the operands in their natural layout (solution ranks 64, operator ranks 3)
+bool sktt_stack_nat_supported(const sktt_ctx* ctx, int dtype, long long rin, long long Rin, long long m, long long n,
+                              long long rout, long long Rout, const void* stack, const void* x, const void* A);
+int sktt_stack_nat_update(sktt_ctx* ctx, long long m, long long n, const double* stack, const double* x, const double* A,
+                          double* out, double* T1p, double* part, int mirror);
+
 // scratch of the persistent stack-update kernel for an input side (rin, Rin): T1 (padded) | tiled core | tile partials
 static int64_t fused_stack_need(int64_t rin, int64_t Rin, int64_t m, int64_t n) {
     const int64_t rp = fused_rpad(rin);
@@ -55,6 +61,11 @@ extern "C" int64_t sktt_stack_op_work(int64_t r, int64_t R, int64_t m, int64_t n
 static int fused_stack(sktt_ctx* ctx, long long rin, long long Rin, long long m, long long n, const void* stack,
                        const void* x, const void* A, void* out, void* work, int mirror) {
     const long long rp = fused_rpad(rin);                    // the output side is exactly (64, 3) here
+    if (sktt_stack_nat_supported(ctx, SKTT_F64, rin, Rin, m, n, 64, 3, stack, x, A)) {
+        double* T1n = (double*)work;
+        return sktt_stack_nat_update(ctx, m, n, (const double*)stack, (const double*)x, (const double*)A, (double*)out, T1n,
+                                     T1n + Rin * rp * n * 68 + n * rp * 68, mirror);
+    }
     const size_t img_bytes = (size_t)sktt_fused_image_elems(rp, Rin, m, n) * sizeof(double);
     SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + img_bytes));
     double* image = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);

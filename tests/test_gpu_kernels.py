@@ -532,3 +532,41 @@ def test_gauge_products(dev, shape):
     carry2 = rng.standard_normal((r, k))
     core2 = rng.standard_normal((L, r))
     assert relerr(host(dev.gauge_push(dev.to_device(carry2), dev.to_device(core2), left=False)), core2 @ carry2) < 1e-13
+
+
+@pytest.mark.parametrize("n", [32, 64, 96])
+@pytest.mark.parametrize("sparse", [False, True])
+def test_stack_update_natural_layout_kernel(dev, n, sparse):
+    """The one-launch interface-stack update that reads L, x and A where they lie (csrc/stack_nat.cu; solution ranks 64,
+    operator ranks 3): left update and mirrored (right) update against the einsum restatement of sle.py:217-219 / :274-276
+    and against the image-based kernel it replaces (debug bit 64), dense and block-sparse operator cores (the mask of zero
+    rank blocks is found by the kernel itself and cleared again: a dense core right after a sparse one must not inherit
+    it), bit-identical reruns."""
+    r, R = 64, 3
+    rng = np.random.default_rng(1000 + n + sparse)
+    L, Rt = rnd(rng, (r, R, r), False), rnd(rng, (r, R, r), False)
+    x = rnd(rng, (r, n, r), False)
+    A = rnd(rng, (R, n, n, R), False)
+    if sparse:                                            # the Laplacian-type pattern of the bench operator: 5 of 9 blocks
+        for (b, q) in ((0, 1), (0, 2), (1, 1), (1, 2)):
+            A[b, :, :, q] = 0.0
+    dL, dR, dx, dA = (dev.to_device(a) for a in (L, Rt, x, A))
+    l0 = dev.launches()
+    got_l = host(dev.stack_left_op(dL, dx, dA))
+    assert dev.launches() - l0 == 1                       # one kernel: no image build, no tiling pass, no memset
+    got_r = host(dev.stack_right_op(dR, dx, dA))
+    assert relerr(got_l, K.stack_left_op(L, x, A)) < 1e-13
+    assert relerr(got_r, K.stack_right_op(Rt, x, A)) < 1e-13
+    assert np.array_equal(got_l, host(dev.stack_left_op(dL, dx, dA)))
+    assert np.array_equal(got_r, host(dev.stack_right_op(dR, dx, dA)))
+    dev.set_debug(64)
+    try:
+        old_l, old_r = host(dev.stack_left_op(dL, dx, dA)), host(dev.stack_right_op(dR, dx, dA))
+    finally:
+        dev.set_debug(0)
+    assert relerr(got_l, old_l) < 1e-13 and relerr(got_r, old_r) < 1e-13
+    # a dense core after the sparse one: the block mask of the previous launch is gone
+    A2 = rnd(rng, (R, n, n, R), False)
+    dA2 = dev.to_device(A2)
+    assert relerr(host(dev.stack_left_op(dL, dx, dA2)), K.stack_left_op(L, x, A2)) < 1e-13
+    assert relerr(host(dev.stack_right_op(dR, dx, dA2)), K.stack_right_op(Rt, x, A2)) < 1e-13
