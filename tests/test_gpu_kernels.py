@@ -538,7 +538,7 @@ def test_gauge_products(dev, shape):
 @pytest.mark.parametrize("sparse", [False, True])
 def test_stack_update_natural_layout_kernel(dev, n, sparse):
     """The one-launch interface-stack update that reads L, x and A where they lie (csrc/stack_nat.cu; solution ranks 64,
-    operator ranks 3): left update and mirrored (right) update against the einsum restatement of sle.py:217-219 / :274-276
+    operator ranks 3, mode size 32 or 64): left update and mirrored (right) update against the einsum restatement of sle.py:217-219 / :274-276
     and against the image-based kernel it replaces (debug bit 64), dense and block-sparse operator cores (the mask of zero
     rank blocks is found by the kernel itself and cleared again: a dense core right after a sparse one must not inherit
     it), bit-identical reruns."""
@@ -553,7 +553,8 @@ def test_stack_update_natural_layout_kernel(dev, n, sparse):
     dL, dR, dx, dA = (dev.to_device(a) for a in (L, Rt, x, A))
     l0 = dev.launches()
     got_l = host(dev.stack_left_op(dL, dx, dA))
-    assert dev.launches() - l0 == 1                       # one kernel: no image build, no tiling pass, no memset
+    if n <= 64:                                           # mode sizes above 64 keep the image-based kernel
+        assert dev.launches() - l0 == 1                   # one kernel: no image build, no tiling pass, no memset
     got_r = host(dev.stack_right_op(dR, dx, dA))
     assert relerr(got_l, K.stack_left_op(L, x, A)) < 1e-13
     assert relerr(got_r, K.stack_right_op(Rt, x, A)) < 1e-13

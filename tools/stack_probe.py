@@ -42,10 +42,12 @@ dev.set_debug(1)
 for side, fn in (("left", lambda: dev.stack_left_op(dL, dx, dA)), ("right", lambda: dev.stack_right_op(dL, dx, dA))):
     for _ in range(3):
         fn()
-    st = dev.scratch_peek(3600, 10)
-    k = int(st[0])
-    t = [int(v) for v in st[1:1 + k]]
-    names = ["phase 1 (+ mask scan)", "grid barrier", "phase 2", "grid barrier", "ordered reduction"]
-    print(side, "phases of CTA 0 [us]:", ", ".join(f"{nm} {(b - a) / 1e3:.2f}" for nm, a, b in zip(names, t, t[1:])),
-          f"| total {(t[-1] - t[0]) / 1e3:.2f}")
+    st = [int(v) for v in dev.scratch_peek(3600, 24)]
+    us = lambda i, j: (st[j] - st[i]) / 1e3
+    print(f"{side}: CTA 0 [us]: phase 1 (+ conj-side rows) {us(0, 1):.2f}, grid barrier {us(1, 2):.2f}, phase 2 {us(2, 3):.2f}, "
+          f"grid barrier {us(3, 4):.2f}, ordered reduction {us(4, 5):.2f} | total {us(0, 5):.2f}")
+    print(f"      phase 1: until the consumers wait {us(0, 20):.2f}, first K group arrives {us(20, 21):.2f}, contraction "
+          f"{us(21, 22):.2f}, K-half exchange + store {us(22, 23):.2f}")
+    print(f"      phase 2: operator rows there {us(2, 12):.2f}, first T1 slot arrives {us(12, 13):.2f}, second contraction "
+          f"{us(13, 14):.2f}, T2 exchange {us(14, 15):.2f}, last contraction {us(15, 16):.2f}, partial store {us(16, 17):.2f}")
 dev.set_debug(0)
