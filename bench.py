@@ -45,7 +45,7 @@ import workloads  # noqa: E402
 from workloads import laplace_cores, workload_cores  # noqa: E402,F401  (kept importable from here: tests, tools)
 
 FP64_TENSOR_PEAK_TFLOPS = 37.1      # measured on this pool's B200: profiles/r01_fp64_peaks.txt (DMMA m8n8k4, sustained)
-NCU_STACK_DRAM_BYTES = None         # per launch of stack_persistent_kernel, from profiles/ (written by tools/ncu_summary.py)
+NCU_STACK_DRAM_BYTES = None         # per launch of stack_nat_kernel, from an ncu --set full capture (profiles/r02_stack_traffic.json)
 _TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_stack_traffic.json")
 if os.path.exists(_TRAFFIC_FILE):
     try:
@@ -408,13 +408,14 @@ def leg_c3(env, args, cfg):
     achieved = F_stack / (stack_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": NCU_STACK_DRAM_BYTES,
-                "kernel": "sktt_stack_left_op at r=64, R=3, n=64 (image build + tiling + stack_persistent_kernel): the "
-                          "interface-stack update the metric names",
+                "kernel": "sktt_stack_left_op at r=64, R=3, n=64 = ONE launch of stack_nat_kernel (csrc/stack_nat.cu: operands read "
+                          "in their natural layout, no image build / tiling pass): the interface-stack update the metric names",
                 "flops_per_update": F_stack, "us_per_update": stack_ms * 1e3, "algorithmic_bytes": B_stack,
                 "arithmetic_intensity": F_stack / B_stack,
                 "peak_source": "measured fp64 DMMA pipe peak, profiles/r01_fp64_peaks.txt (MEASURED_PEAKS.json has no fp64 entry)",
-                "traffic_note": "dram bytes of one stack_persistent_kernel launch under ncu --set full (cold caches), "
-                                "profiles/r02_stack_traffic.json; null until captured",
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one stack_nat_kernel launch under ncu --set full, "
+                                "profiles/r02_stack_traffic.json (source capture named there); the operands are L2-resident in the "
+                                "sweep, the op is compute-bound (AI ~ 194 flop/B)",
                 "pcg_in_situ": pcg, "matvec_loop": loop}
 
     out = {"ms": ms, "ms_e2e": ms_e2e, "launches": launches, "clocks": clocks, "roofline": roofline, "krylov": krylov}

@@ -519,6 +519,12 @@ int sktt_stack_nat_update(sktt_ctx* ctx, long long m, long long n, const double*
     }
     void* args[] = {&a};
     const void* fn = mirror ? (const void*)stack_nat_kernel<true> : (const void*)stack_nat_kernel<false>;
+    if (ctx->debug & 128) {                                // diagnostics: plain launch (no co-residency guarantee)
+        if (mirror) stack_nat_kernel<true><<<ctx->sm_count, THREADS, smem, ctx->stream>>>(a);
+        else stack_nat_kernel<false><<<ctx->sm_count, THREADS, smem, ctx->stream>>>(a);
+        SKTT_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     SKTT_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->sm_count), dim3(THREADS), args, smem, ctx->stream));
     ctx->launches++;
     return 0;

@@ -33,11 +33,19 @@ def timed(fn, reps=200):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-for name, dbg in (("natural-layout kernel", 0), ("image-based kernel", 64)):
+import time
+t0 = time.perf_counter()
+for _ in range(2000):
+    dev.stack_left_op(dL, dx, dA)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+t2 = time.perf_counter()
+print(f"host: {1e6 * (t1 - t0) / 2000:.1f} us per call to issue, {1e6 * (t2 - t0) / 2000:.1f} us per call until the device is done")
+for name, dbg in (("natural-layout kernel", 0), ("natural-layout, plain launch", 128), ("image-based kernel", 64)):
     dev.set_debug(dbg)
     for side, fn in (("left", lambda: dev.stack_left_op(dL, dx, dA)), ("right", lambda: dev.stack_right_op(dL, dx, dA))):
         us = timed(fn)
-        print(f"{name:24s} {side:5s}: {us:7.2f} us per update  {F / us / 1e6:6.2f} TFLOP/s  frac {F / us / 1e6 / 37.1:.3f}")
+        print(f"{name:30s} {side:5s}: {us:7.2f} us per update  {F / us / 1e6:6.2f} TFLOP/s  frac {F / us / 1e6 / 37.1:.3f}")
 dev.set_debug(1)
 for side, fn in (("left", lambda: dev.stack_left_op(dL, dx, dA)), ("right", lambda: dev.stack_right_op(dL, dx, dA))):
     for _ in range(3):
