@@ -203,17 +203,29 @@ struct KWalk {
     }
 };
 
-template <int BM, int BN, int WM, int WN, int STAGES>
+// 16-byte asynchronous copy with zero fill: `bytes` (0, 8 or 16) are read from global memory, the rest of the 16 is zeroed
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+
+// AKM / BKM: the operand is K-MAJOR in memory (unit stride along the contracted index, e.g. a row-major A or a
+// column-major B).  Such an operand is staged as [m][k] rows of 16 k (pitch 20 = 4 mod 16: conflict-free fragment loads)
+// by 16-byte copies with eight consecutive lanes on one 128-byte row segment; the m-fastest loader below would read it
+// with every lane in a different sector (measured: 2048^3 with a row-major A at 20 TFLOP/s against 34 for cuBLAS).
+template <int BM, int BN, int WM, int WN, int STAGES, bool AKM, bool BKM>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 gemm_dmma_kernel(GemmParams p) {
     constexpr int BK = 16;
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int LDA = BM + 4, LDB = BN + 4;  // (LD mod 16) == 4 -> conflict-free 64-bit fragment loads
-    constexpr int A_STAGE = BK * LDA, B_STAGE = BK * LDB;
-    constexpr int TPK = NT / BK;               // threads sharing one k row
-    constexpr int A_PER = BM / TPK, B_PER = BN / TPK;
+    constexpr int LDK = BK + 4;                // pitch of a k-major operand row
+    constexpr int A_STAGE = AKM ? BM * LDK : BK * LDA, B_STAGE = BKM ? BN * LDK : BK * LDB;
+    constexpr int TPK = NT / BK;               // threads sharing one k row (m-fastest loader)
+    constexpr int A_PER = AKM ? (BM * (BK / 2)) / NT : BM / TPK, B_PER = BKM ? (BN * (BK / 2)) / NT : BN / TPK;
     static_assert(NT % BK == 0 && BM % TPK == 0 && BN % TPK == 0, "tile/thread mismatch");
-    extern __shared__ double smem[];
+    static_assert((BM * (BK / 2)) % NT == 0 && (BN * (BK / 2)) % NT == 0, "tile/thread mismatch (k-major loader)");
+    extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + STAGES * A_STAGE;
 
@@ -226,42 +238,69 @@ gemm_dmma_kernel(GemmParams p) {
     const int kend = min(p.K, kbeg + p.k_chunk);
     const int ntiles = (kend - kbeg + BK - 1) / BK;
 
-    // loader role: fixed k row (tid / TPK), A_PER m's and B_PER n's strided by TPK
+    // loader roles.  m-fastest: fixed k row (tid / TPK), *_PER m's (n's) strided by TPK.  k-major: fixed 16-byte piece of
+    // the k range (tid % 8), *_PER rows strided by NT / 8.
     const int lk = tid / TPK, lt = tid % TPK;
+    const int kp = tid & 7, lr = tid >> 3;
     int aoff[A_PER], boff[B_PER];
     unsigned amask = 0, bmask = 0;
 #pragma unroll
     for (int j = 0; j < A_PER; ++j) {
-        int m = m0 + lt + j * TPK;
+        int m = m0 + (AKM ? lr + j * (NT / 8) : lt + j * TPK);
         bool ok = m < p.M;
         aoff[j] = ok ? (int)p.am(m) : 0;
         amask |= (ok ? 1u : 0u) << j;
     }
 #pragma unroll
     for (int j = 0; j < B_PER; ++j) {
-        int n = n0 + lt + j * TPK;
+        int n = n0 + (BKM ? lr + j * (NT / 8) : lt + j * TPK);
         bool ok = n < p.N;
         boff[j] = ok ? (int)p.bn(n) : 0;
         bmask |= (ok ? 1u : 0u) << j;
     }
     KWalk wa, wb;
-    wa.init(p.ak, kbeg + lk);
-    wb.init(p.bk, kbeg + lk);
-    int kload = kbeg + lk;
+    wa.init(p.ak, kbeg + (AKM ? 0 : lk));
+    wb.init(p.bk, kbeg + (BKM ? 0 : lk));
+    int kload = kbeg;                          // first k of the tile being requested
 
     auto issue = [&](int stage) {
-        bool kok = kload < kend;
-        const double* ap = A + (kok ? wa.off() : 0);
-        const double* bp = B + (kok ? wb.off() : 0);
-        double* as = As + stage * A_STAGE + lk * LDA + lt;
-        double* bs = Bs + stage * B_STAGE + lk * LDB + lt;
+        if (AKM) {
+            const int left = kend - (kload + 2 * kp);                 // valid k from this piece on
+            const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+            const double* ap = A + wa.off() + 2 * kp;
+            double* as = As + stage * A_STAGE + lr * LDK + 2 * kp;
 #pragma unroll
-        for (int j = 0; j < A_PER; ++j) cp_async8(as + j * TPK, ap + aoff[j], kok && ((amask >> j) & 1u));
+            for (int j = 0; j < A_PER; ++j) {
+                const bool ok = bytes > 0 && ((amask >> j) & 1u);
+                cp_async16(as + j * (NT / 8) * LDK, ok ? ap + aoff[j] : A, ok ? bytes : 0);
+            }
+        } else {
+            const bool kok = kload + lk < kend;
+            const double* ap = A + (kok ? wa.off() : 0);
+            double* as = As + stage * A_STAGE + lk * LDA + lt;
 #pragma unroll
-        for (int j = 0; j < B_PER; ++j) cp_async8(bs + j * TPK, bp + boff[j], kok && ((bmask >> j) & 1u));
+            for (int j = 0; j < A_PER; ++j) cp_async8(as + j * TPK, ap + aoff[j], kok && ((amask >> j) & 1u));
+        }
+        if (BKM) {
+            const int left = kend - (kload + 2 * kp);
+            const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+            const double* bp = B + wb.off() + 2 * kp;
+            double* bs = Bs + stage * B_STAGE + lr * LDK + 2 * kp;
+#pragma unroll
+            for (int j = 0; j < B_PER; ++j) {
+                const bool ok = bytes > 0 && ((bmask >> j) & 1u);
+                cp_async16(bs + j * (NT / 8) * LDK, ok ? bp + boff[j] : B, ok ? bytes : 0);
+            }
+        } else {
+            const bool kok = kload + lk < kend;
+            const double* bp = B + (kok ? wb.off() : 0);
+            double* bs = Bs + stage * B_STAGE + lk * LDB + lt;
+#pragma unroll
+            for (int j = 0; j < B_PER; ++j) cp_async8(bs + j * TPK, bp + boff[j], kok && ((bmask >> j) & 1u));
+        }
         kload += BK;
-        wa.advance(BK);
-        wb.advance(BK);
+        if (kload < kend || !AKM) wa.advance(BK);
+        if (kload < kend || !BKM) wb.advance(BK);
     };
 
     // accumulators
@@ -286,15 +325,15 @@ gemm_dmma_kernel(GemmParams p) {
         // prefetch tile t + STAGES - 1 into the slot freed at iteration t - 1
         if (t + STAGES - 1 < ntiles) issue((t + STAGES - 1) % STAGES);
         cp_async_commit();
-        const double* as = As + (t % STAGES) * A_STAGE + wm0 + fr;
-        const double* bs = Bs + (t % STAGES) * B_STAGE + wn0 + fr;
+        const double* as = As + (t % STAGES) * A_STAGE + (AKM ? (wm0 + fr) * LDK + fk : fk * LDA + wm0 + fr);
+        const double* bs = Bs + (t % STAGES) * B_STAGE + (BKM ? (wn0 + fr) * LDK + fk : fk * LDB + wn0 + fr);
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
             double af[MI], bf[NI];
 #pragma unroll
-            for (int i = 0; i < MI; ++i) af[i] = as[(kk + fk) * LDA + i * 8];
+            for (int i = 0; i < MI; ++i) af[i] = AKM ? as[i * 8 * LDK + kk] : as[kk * LDA + i * 8];
 #pragma unroll
-            for (int j = 0; j < NI; ++j) bf[j] = bs[(kk + fk) * LDB + j * 8];
+            for (int j = 0; j < NI; ++j) bf[j] = BKM ? bs[j * 8 * LDK + kk] : bs[kk * LDB + j * 8];
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -373,20 +412,39 @@ static inline long long max_off(const Idx2& ix, long long n) {
     return a + b;
 }
 
-template <int BM, int BN, int WM, int WN, int STAGES>
-static int launch_dmma(sktt_ctx* ctx, GemmParams& p) {
+template <int BM, int BN, int WM, int WN, int STAGES, bool AKM, bool BKM>
+static int launch_dmma_v(sktt_ctx* ctx, GemmParams& p) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
-    constexpr size_t smem = (size_t)STAGES * 16 * ((BM + 4) + (BN + 4)) * sizeof(double);
+    constexpr size_t smem = (size_t)STAGES * ((AKM ? BM * 20 : 16 * (BM + 4)) + (BKM ? BN * 20 : 16 * (BN + 4))) * sizeof(double);
     SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
-        SKTT_CUDA(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WM, WN, STAGES>,
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WM, WN, STAGES, AKM, BKM>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits * p.batch);
-    gemm_dmma_kernel<BM, BN, WM, WN, STAGES><<<grid, NT, smem, ctx->stream>>>(p);
+    gemm_dmma_kernel<BM, BN, WM, WN, STAGES, AKM, BKM><<<grid, NT, smem, ctx->stream>>>(p);
     SKTT_LAUNCH_CHECK(ctx);
     return 0;
+}
+template <int BM, int BN, int WM, int WN, int STAGES>
+static int launch_dmma(sktt_ctx* ctx, GemmParams& p, bool akm, bool bkm) {
+    if (akm && bkm) return launch_dmma_v<BM, BN, WM, WN, STAGES, true, true>(ctx, p);
+    if (akm) return launch_dmma_v<BM, BN, WM, WN, STAGES, true, false>(ctx, p);
+    if (bkm) return launch_dmma_v<BM, BN, WM, WN, STAGES, false, true>(ctx, p);
+    return launch_dmma_v<BM, BN, WM, WN, STAGES, false, false>(ctx, p);
+}
+
+// An operand can take the k-major loader when its contracted index has unit stride in runs that a 16-k tile never straddles,
+// every 16-byte piece is aligned (even row offsets, aligned base, even batch stride) and the other index is NOT the
+// unit-stride one (then the m-fastest loader is already coalesced).
+static bool kmajor_ok(const Idx2& ik, const Idx2& im, long long K, long long M, const void* ptr, long long batch_stride) {
+    if (ik.s_lo != 1 || !(ik.d >= K || ik.d % 16 == 0)) return false;
+    if (ik.d < K && (ik.s_hi & 1)) return false;
+    if (im.s_lo == 1 && im.d >= 8) return false;
+    if ((im.s_lo & 1) && M > 1 && im.d > 1) return false;
+    if (im.d < M && (im.s_hi & 1)) return false;
+    return ((uintptr_t)ptr & 15u) == 0 && (batch_stride & 1) == 0;
 }
 
 template <typename T, int BM, int BN, int BK, int TM, int TN>
@@ -446,8 +504,11 @@ int sktt_gemm_run(sktt_ctx* ctx, int dtype, const GemmDesc& g) {
             SKTT_TRY(sktt_scratch_reserve(ctx, (size_t)p.batch * p.splits * g.M * g.N * sizeof(double) + SKTT_SCRATCH_BULK_OFF));
             p.partial = (char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF;
         }
-        if (big) SKTT_TRY((launch_dmma<128, 128, 64, 32, 3>(ctx, p)));
-        else SKTT_TRY((launch_dmma<64, 64, 32, 32, 4>(ctx, p)));
+        const bool akm = kmajor_ok(g.ak, g.am, g.K, g.M, g.A, p.sA), bkm = kmajor_ok(g.bk, g.bn, g.K, g.N, g.B, p.sB);
+        // 128 x 128 tiles: sixteen warps of 32 x 32 (64 accumulator registers per thread: a 64 x 32 warp tile needs 216
+        // registers, i.e. eight warps per SM -- too few to cover the LDS -> DMMA latency; measured 0.5 of the pipe peak)
+        if (big) SKTT_TRY((launch_dmma<128, 128, 32, 32, 4>(ctx, p, akm, bkm)));
+        else SKTT_TRY((launch_dmma<64, 64, 32, 32, 4>(ctx, p, akm, bkm)));
         if (p.splits > 1) {
             long long total = g.M * g.N;
             int blocks = (int)(cdiv(total, 256) < 4LL * sms ? cdiv(total, 256) : 4LL * sms);
