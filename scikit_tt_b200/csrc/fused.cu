@@ -922,6 +922,7 @@ struct PcgParams {
     int max_iters, max_cycles, mode, reps;   // mode 0: solve; 1: `reps` matvecs w = M f (timing)
     double* part;             // [2][gridDim.x][2] partial sums (double-buffered)
     double* out;              // [0] iterations, [1] true relres, [2] cycles, [3] status (0 ok, 1 iteration limit, 2 breakdown)
+    unsigned long long* dbg;  // optional: %globaltimer stamps of CTA 0 during a solve (ctx debug bit 0)
 };
 
 namespace {
@@ -1013,10 +1014,10 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
         parity ^= 1;
     };
     // dst = M src (tiled vectors); yd = <dst, dvec> when dvec is given (one grid barrier more inside grid_sum2)
-    unsigned long long* stamps = a.mode == 1 ? reinterpret_cast<unsigned long long*>(a.out + 8) : nullptr;
+    unsigned long long* stamps = a.mode == 1 ? reinterpret_cast<unsigned long long*>(a.out + 8) : a.dbg;
     int nstamp = 0;
     auto stamp = [&]() {
-        if (stamps && cta == 0 && tid == 0 && nstamp < 60) {
+        if (stamps && cta == 0 && tid == 0 && nstamp < (a.mode == 1 ? 60 : 30)) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
             stamps[1 + nstamp++] = t;
@@ -1048,7 +1049,8 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
 
     if (a.mode == 1) {
         double dummy = 0.0;
-        for (int rep = 0; rep < a.reps; ++rep) matvec(a.f, a.w, nullptr, dummy);
+        // max_iters == -1 (ctx debug bit 8): with the fused dot <w, f> and its grid-wide sum, as inside a CG iteration
+        for (int rep = 0; rep < a.reps; ++rep) matvec(a.f, a.w, a.max_iters == -1 ? a.f : nullptr, dummy);
         stamp();
         if (stamps && cta == 0 && tid == 0) stamps[0] = (unsigned long long)nstamp;
         return;
@@ -1178,7 +1180,9 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
                     }
                 }
             }
+            stamp();
             grid_sum2(acc, 0.0, rr_rec, tmp);
+            stamp();
             gamma_old = gamma;
             alpha_old = alpha;
             ++iters;
@@ -1200,6 +1204,7 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
         }
     }
     if (!(relres <= a.tol)) status = hit_limit ? 1 : (broke ? 2 : 0);   // 0 with relres > tol: stagnated at the eps * cond floor
+    if (stamps && cta == 0 && tid == 0) stamps[0] = (unsigned long long)nstamp;
     if (gtid == 0) {
         a.out[0] = (double)iters;
         a.out[1] = relres;
@@ -1363,6 +1368,7 @@ int sktt_fused_pcg_persistent(sktt_ctx* ctx, long long r, long long R, long long
     a.reps = reps;
     a.part = part;
     a.out = out_dev;
+    a.dbg = (mode == 0 && (ctx->debug & 1)) ? (unsigned long long*)((char*)ctx->scratch + 3600) : nullptr;
     const size_t smem = pcg_phase_bytes((int)r) + pcg_rres_bytes() + 128;
     SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {

@@ -708,7 +708,7 @@ extern "C" int sktt_local_matvec_tiled_repeat(sktt_ctx* ctx, int dtype, const sk
     SKTT_TRY(sktt_scratch_reserve(ctx, SKTT_SCRATCH_BULK_OFF + (4 * 256 + 128) * sizeof(double)));
     double* part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
     return sktt_fused_pcg_persistent(ctx, fused_rpad(op->r), op->R, op->m, op->n, (const double*)op->image, (const double*)vt, nullptr,
-                                     nullptr, nullptr, nullptr, (double*)yt, (double*)work, 0.0, 0, 0, 1, reps, part,
+                                     nullptr, nullptr, nullptr, (double*)yt, (double*)work, 0.0, (ctx->debug & 256) ? -1 : 0, 0, 1, reps, part,
                                      part + 4 * 256);
 }
 
