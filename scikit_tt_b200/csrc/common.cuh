@@ -24,6 +24,9 @@ struct sktt_ctx {
     void* mailbox = nullptr;
     // two reusable events for the lagged convergence checks of the Krylov loops
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // panel flags of the one-launch LU (lu_fused.cu): "published" means flags[k] == lu_epoch of the running launch
+    void* lu_flags = nullptr;
+    unsigned lu_epoch = 0;
 };
 
 static inline int sktt_fail(sktt_ctx* ctx, int code, const char* fmt, const char* a = "") {

@@ -49,6 +49,7 @@ extern "C" int sktt_ctx_destroy(sktt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->lu_flags) cudaFree(ctx->lu_flags);
     if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
     for (int i = 0; i < 2; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

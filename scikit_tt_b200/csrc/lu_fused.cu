@@ -53,7 +53,8 @@ struct LfCols {
     __device__ __forceinline__ double& at(int row, int col) const { return base[(long long)row * ld + col]; }
 };
 
-__global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs a) {
+// First form (kept for A/B timing, ctx debug bit 10): panels by CTA 0 in shared memory, two grid barriers per panel.
+__global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel_v1(LfArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::grid_group grid = cg::this_grid();
     const int N = a.N;
@@ -317,10 +318,385 @@ __global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs a) {
     }
 }
 
+
+// ================================================================================================ dataflow form
+// Second form: no grid barrier at all.  The matrix is cut into blocks of 16 columns, block p belongs to CTA p (the
+// right-hand side is one more block with its own CTA).  CTA p applies the updates of panels 0 .. p-1 to ITS columns as soon
+// as each panel is published (one flag per panel, release / acquire), then factorises its own block as panel p and
+// publishes it.  The critical path per panel is therefore [flag, update of ONE block, panel factorisation] -- the updates of
+// all other blocks run beside it (look-ahead for free) -- instead of [panel, grid barrier, slowest trailing item, grid
+// barrier].
+//
+// Panel factorisation: every thread keeps its rows of the (N - j0) x 16 panel in REGISTERS (row r of the panel lives in
+// thread r mod 512), so the rank-1 update of a column touches no shared memory; per column there are two CTA barriers
+// (pivot candidates of the 16 warps, then the pivot row and the row it is exchanged with), the candidates of column
+// c + 1 are taken from the registers the update of column c has just written.  Arithmetic and pivot rule (first maximum)
+// are those of the unblocked right-looking elimination, multipliers by the reciprocal of the pivot (LAPACK's getf2).
+struct LfArgs2 {
+    int N;
+    double* A;
+    double* b;
+    int* ipiv;
+    int* info;
+    unsigned* flags;      // [npan] panel k is published when flags[k] == epoch
+    unsigned epoch;
+    unsigned long long* stamps;   // optional %globaltimer stamps of the CTA of the middle block (ctx debug bit 0)
+};
+
+__device__ __forceinline__ unsigned lf_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lf_st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// (best, bi) <- the larger value, the smaller row on ties (idamax: first maximum)
+__device__ __forceinline__ void lf_take(double& best, int& bi, double ob, int oi) {
+    const bool t = ob > best || (ob == best && oi < bi);
+    best = t ? ob : best;
+    bi = t ? oi : bi;
+}
+
+template <int RPT>
+__device__ void lf2_panel(const LfArgs2& a, int j0, int nb, double* s_prow, double* s_crow, double* s_val, int* s_idx,
+                          int* s_piv, unsigned long long* clk) {
+    const int N = a.N, rows = N - j0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double pr[RPT][LF_NB];
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const int r = tid + u * LF_THREADS;
+        const double* src = a.A + (long long)(j0 + (r < rows ? r : 0)) * N + j0;
+#pragma unroll
+        for (int c = 0; c < LF_NB; ++c) pr[u][c] = (r < rows && c < nb) ? __ldcg(src + c) : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < LF_NB; ++c) {
+        if (c < nb) {                                         // uniform
+            if (clk && c == 8) clk[0] = clock64();
+            double best = -1.0;
+            int bi = c;
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) {
+                const int r = tid + u * LF_THREADS;
+                if (r >= c && r < rows) lf_take(best, bi, fabs(pr[u][c]), r);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                lf_take(best, bi, ob, oi);
+            }
+            if (lane == 0) {
+                s_val[warp] = best;
+                s_idx[warp] = bi;
+            }
+            if (clk && c == 8) clk[1] = clock64();
+            __syncthreads();
+            if (clk && c == 8) clk[2] = clock64();
+            best = s_val[lane & 15];
+            bi = s_idx[lane & 15];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                lf_take(best, bi, ob, oi);
+            }
+            // every thread holds the same (best, bi).  The owner of the pivot row and the owner of row c publish their rows.
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) {
+                const int r = tid + u * LF_THREADS;
+                if (r == bi) {
+#pragma unroll
+                    for (int cc = 0; cc < LF_NB; ++cc) s_prow[cc] = pr[u][cc];
+                }
+                if (r == c && bi != c) {
+#pragma unroll
+                    for (int cc = 0; cc < LF_NB; ++cc) s_crow[cc] = pr[u][cc];
+                }
+            }
+            if (tid == 0) {
+                s_piv[c] = j0 + bi;
+                if (!(best > 0.0)) atomicCAS(a.info, 0, j0 + c + 1);
+            }
+            if (clk && c == 8) clk[3] = clock64();
+            __syncthreads();
+            if (clk && c == 8) clk[4] = clock64();
+            const double piv = s_prow[c];
+            const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) {
+                const int r = tid + u * LF_THREADS;
+                if (bi != c) {                                // the interchange, in registers
+                    if (r == c) {
+#pragma unroll
+                        for (int cc = 0; cc < LF_NB; ++cc) pr[u][cc] = s_prow[cc];
+                    } else if (r == bi) {
+#pragma unroll
+                        for (int cc = 0; cc < LF_NB; ++cc) pr[u][cc] = s_crow[cc];
+                    }
+                }
+                if (r > c && r < rows) {
+                    const double l = pr[u][c] * inv;
+                    pr[u][c] = l;
+#pragma unroll
+                    for (int cc = 0; cc < LF_NB; ++cc)
+                        if (cc > c) pr[u][cc] = fma(-l, s_prow[cc], pr[u][cc]);
+                }
+            }
+            if (clk && c == 8) clk[5] = clock64();
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const int r = tid + u * LF_THREADS;
+        if (r < rows) {
+            double* dst = a.A + (long long)(j0 + r) * N + j0;
+#pragma unroll
+            for (int c = 0; c < LF_NB; ++c)
+                if (c < nb) dst[c] = pr[u][c];
+        }
+    }
+    __syncthreads();
+    if (tid < nb) a.ipiv[j0 + tid] = s_piv[tid];
+}
+
+__global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs2 a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = a.N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = LF_THREADS / 32;
+    double* sm = reinterpret_cast<double*>(smem_raw);
+    __shared__ double s_val[16], s_prow[LF_NB], s_crow[LF_NB];
+    __shared__ int s_idx[16], s_piv[LF_NB], s_pos[2 * LF_NB], s_content[2 * LF_NB], s_np;
+    const int npan = (N + LF_NB - 1) / LF_NB;
+    const int p = blockIdx.x;                                 // my block: columns 16 p ..; p == npan: the right-hand side
+    const bool is_rhs = p == npan;
+    LfCols cols;
+    int cw;
+    if (is_rhs) {
+        cols.base = a.b;
+        cols.ld = 1;
+        cw = 1;
+    } else {
+        cols.base = a.A + (long long)p * LF_NB;
+        cols.ld = N;
+        cw = min(LF_NB, N - p * LF_NB);
+    }
+    double* L11 = sm;                                         // [nb][LF_LDP]
+    double* top = L11 + LF_NB * LF_LDP;                       // [<= 2 nb][LF_NB]: rows the interchanges touch, then U12 on top
+
+    const int nupd = is_rhs ? npan : p;
+    unsigned long long* st = (a.stamps && p == npan / 2 && tid == 0) ? a.stamps : nullptr;
+    auto tick = [&](int i) {
+        if (st) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(st[i]));
+    };
+    for (int k = 0; k < nupd; ++k) {
+        const int j0 = k * LF_NB, nb = min(LF_NB, N - j0);
+        if (tid == 0)
+            while (lf_ld_acquire(a.flags + k) != a.epoch) {}
+        __syncthreads();
+        if (k == nupd - 1) tick(0);
+        // ---- unit-lower triangle and pivots of panel k
+        for (int e = tid; e < nb * nb; e += LF_THREADS) {
+            const int r = e / nb, c = e - r * nb;
+            L11[r * LF_LDP + c] = __ldcg(a.A + (long long)(j0 + r) * N + j0 + c);
+        }
+        if (warp == 0) {
+            // rows the interchanges touch: the nb top rows, then every pivot row not yet listed (slot = lane); `content`
+            // follows the rows through the sequence of interchanges
+            int pos = lane < nb ? j0 + lane : -1, content = lane, np = nb;
+            const int mypiv = lane < nb ? __ldcg(a.ipiv + j0 + lane) : -1;
+            for (int c = 0; c < nb; ++c) {
+                const int pv = __shfl_sync(0xffffffffu, mypiv, c);
+                const unsigned found = __ballot_sync(0xffffffffu, pos == pv);
+                int ip;
+                if (found) {
+                    ip = __ffs(found) - 1;
+                } else {
+                    ip = np;
+                    if (lane == np) pos = pv;
+                    ++np;
+                }
+                const int ca = __shfl_sync(0xffffffffu, content, c), cb = __shfl_sync(0xffffffffu, content, ip);
+                if (lane == c) content = cb;
+                if (lane == ip) content = ca;
+            }
+            s_pos[lane] = pos;
+            s_content[lane] = content;
+            if (lane == 0) s_np = np;
+        }
+        __syncthreads();
+        if (k == nupd - 1) tick(1);
+        const int np = s_np;
+        for (int e = tid; e < np * cw; e += LF_THREADS) {
+            const int q = e / cw, c = e - q * cw;
+            top[q * LF_NB + c] = __ldcg(&cols.at(s_pos[s_content[q]], c));
+        }
+        __syncthreads();
+        if (k == nupd - 1) tick(2);
+        // ---- U12 = L11^-1 top: warp w takes column w, lane r holds row r; right-looking elimination through shuffles
+        if (warp < cw) {
+            double v = lane < nb ? top[lane * LF_NB + warp] : 0.0;
+            for (int c = 0; c + 1 < nb; ++c) {
+                const double vc = __shfl_sync(0xffffffffu, v, c);
+                if (lane > c && lane < nb) v = fma(-L11[lane * LF_LDP + c], vc, v);
+            }
+            if (lane < nb) top[lane * LF_NB + warp] = v;
+        }
+        __syncthreads();
+        if (k == nupd - 1) tick(3);
+        for (int e = tid; e < np * cw; e += LF_THREADS) {
+            const int q = e / cw, c = e - q * cw;
+            cols.at(s_pos[q], c) = top[q * LF_NB + c];
+        }
+        __syncthreads();
+        if (k == nupd - 1) tick(4);
+        // ---- rank-nb update of the rows below the panel: C[i, :] -= L21[i, :] U12, one 8-row block per warp and step, four
+        // blocks in flight
+        {
+            const int fr = lane >> 2, fk = lane & 3;
+            const int rbeg = j0 + nb, nblk8 = (N - rbeg + 7) / 8;
+            double bfrag[2][4];                               // B fragments: k = 4 s + fk, n = 8 h + fr (U12, shared memory)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int kk = 4 * s + fk, n = 8 * h + fr;
+                    bfrag[h][s] = (kk < nb && n < cw) ? top[kk * LF_NB + n] : 0.0;
+                }
+            const int cc0 = 2 * fk;
+            for (int blk0 = warp; blk0 < nblk8; blk0 += 4 * nwarps) {
+                double af[4][4], cv[4][2][2];
+                int irow[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int blk = blk0 + u * nwarps;
+                    const int i = rbeg + 8 * blk + fr;
+                    const bool rok = blk < nblk8 && i < N;
+                    irow[u] = rok ? i : -1;
+                    const double* lrow = a.A + (long long)(rok ? i : rbeg) * N + j0;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const int kk = 4 * s + fk;
+                        af[u][s] = (rok && kk < nb) ? __ldcg(lrow + kk) : 0.0;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int cc = 8 * h + cc0;
+                        cv[u][h][0] = (rok && cc < cw) ? cols.at(i, cc) : 0.0;
+                        cv[u][h][1] = (rok && cc + 1 < cw) ? cols.at(i, cc + 1) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (8 * h < cw) {                     // uniform
+                            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) lf_dmma(acc0, acc1, af[u][s], bfrag[h][s]);
+                            const int cc = 8 * h + cc0;
+                            if (irow[u] >= 0) {
+                                if (cc < cw) cols.at(irow[u], cc) = cv[u][h][0] - acc0;
+                                if (cc + 1 < cw) cols.at(irow[u], cc + 1) = cv[u][h][1] - acc1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    tick(5);
+    if (!is_rhs) {
+        // ---- my block is panel p
+        const int j0 = p * LF_NB, rows = N - j0;
+        unsigned long long* clk = st ? st + 8 : nullptr;
+        if (rows <= LF_THREADS) lf2_panel<1>(a, j0, cw, s_prow, s_crow, s_val, s_idx, s_piv, clk);
+        else if (rows <= 2 * LF_THREADS) lf2_panel<2>(a, j0, cw, s_prow, s_crow, s_val, s_idx, s_piv, clk);
+        else lf2_panel<3>(a, j0, cw, s_prow, s_crow, s_val, s_idx, s_piv, clk);
+        __syncthreads();
+        tick(6);
+        if (tid == 0) {
+            __threadfence();
+            lf_st_release(a.flags + p, a.epoch);
+        }
+        tick(7);
+        // ---- interchanges of later panels on my L columns (LAPACK's layout of the factors)
+        const int rfirst = (p + 1) * LF_NB;
+        if (rfirst >= N) return;
+        if (tid == 0)
+            while (lf_ld_acquire(a.flags + npan - 1) != a.epoch) {}
+        __syncthreads();
+        int* perm = reinterpret_cast<int*>(sm);               // [N]
+        double* stage = sm + ((N + 1) / 2 + 1);               // [N - rfirst][LF_NB]
+        for (int i = rfirst + tid; i < N; i += LF_THREADS) perm[i] = i;
+        __syncthreads();
+        if (tid == 0)
+            for (int j = rfirst; j < N; ++j) {
+                const int pv = __ldcg(a.ipiv + j);
+                if (pv != j) {
+                    const int t = perm[j];
+                    perm[j] = perm[pv];
+                    perm[pv] = t;
+                }
+            }
+        __syncthreads();
+        for (int e = tid; e < (N - rfirst) * cw; e += LF_THREADS) {
+            const int i = rfirst + e / cw, c = e % cw;
+            stage[(size_t)(i - rfirst) * LF_NB + c] = cols.at(perm[i], c);
+        }
+        __syncthreads();
+        for (int e = tid; e < (N - rfirst) * cw; e += LF_THREADS) {
+            const int i = rfirst + e / cw, c = e % cw;
+            cols.at(i, c) = stage[(size_t)(i - rfirst) * LF_NB + c];
+        }
+        return;
+    }
+    // ---- right-hand side: every L update has been applied; back substitution with U (all panels are published)
+    {
+        double* x = sm;                                       // [N]
+        double* D = x + N;                                    // [LF_NB][LF_LDP] diagonal block of U
+        for (int i = tid; i < N; i += LF_THREADS) x[i] = a.b[i];
+        __syncthreads();
+        for (int k = npan - 1; k >= 0; --k) {
+            const int j0 = k * LF_NB, nb = min(LF_NB, N - j0);
+            for (int e = tid; e < nb * nb; e += LF_THREADS) {
+                const int r = e / nb, c = e - r * nb;
+                D[r * LF_LDP + c] = __ldcg(a.A + (long long)(j0 + r) * N + j0 + c);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double val = lane < nb ? x[j0 + lane] : 0.0;
+                for (int c = nb - 1; c >= 0; --c) {
+                    if (lane == c) val = val / D[c * LF_LDP + c];
+                    const double xc = __shfl_sync(0xffffffffu, val, c);
+                    if (lane < c) val = fma(-D[lane * LF_LDP + c], xc, val);
+                }
+                if (lane < nb) x[j0 + lane] = val;
+            }
+            __syncthreads();
+            for (int i = tid; i < j0; i += LF_THREADS) {      // rows above: x_i -= U[i, block] x_block
+                const double* u = a.A + (long long)i * N + j0;
+                double acc = x[i];
+#pragma unroll
+                for (int c = 0; c < LF_NB; ++c)
+                    if (c < nb) acc = fma(-__ldcg(u + c), x[j0 + c], acc);
+                x[i] = acc;
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < N; i += LF_THREADS) a.b[i] = x[i];
+    }
+}
+
 static size_t lf_smem(int N) {
     size_t panel = (size_t)N * LF_LDP * sizeof(double);
-    size_t upd = ((size_t)LF_NB * LF_LDP + 2 * LF_NB * LF_CB) * sizeof(double);
-    size_t fix = ((size_t)(N + 1) / 2 + 1 + (size_t)N * LF_CB) * sizeof(double);
+    size_t upd = ((size_t)LF_NB * LF_LDP + 2 * LF_NB * LF_NB) * sizeof(double);
+    size_t fix = ((size_t)(N + 1) / 2 + 1 + (size_t)N * LF_NB) * sizeof(double);
     size_t back = ((size_t)N + LF_NB * LF_LDP) * sizeof(double);
     size_t m = panel;
     if (upd > m) m = upd;
@@ -343,9 +719,33 @@ extern "C" int sktt_lu_solve_fused(sktt_ctx* ctx, int64_t N, void* A, void* b, i
     SKTT_ONCE_PER_DEVICE(ctx);
     if (!configured) {
         SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        SKTT_CUDA(ctx, cudaFuncSetAttribute(lu_fused_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         configured = true;
     }
     SKTT_CUDA(ctx, cudaMemsetAsync(info_dev, 0, sizeof(int32_t), ctx->stream));
+    const int npan = (int)((N + LF_NB - 1) / LF_NB), want2 = npan + (b ? 1 : 0);
+    if (!(ctx->debug & 1024) && want2 <= ctx->sm_count) {
+        // dataflow form: one CTA per block of 16 columns (+ one for the right-hand side), flags instead of grid barriers
+        if (!ctx->lu_flags) {
+            SKTT_CUDA(ctx, cudaMalloc(&ctx->lu_flags, 256 * sizeof(unsigned)));
+            SKTT_CUDA(ctx, cudaMemsetAsync(ctx->lu_flags, 0, 256 * sizeof(unsigned), ctx->stream));
+            ctx->lu_epoch = 0;
+        }
+        LfArgs2 a2;
+        a2.N = (int)N;
+        a2.A = (double*)A;
+        a2.b = (double*)b;
+        a2.ipiv = ipiv_dev;
+        a2.info = info_dev;
+        a2.flags = (unsigned*)ctx->lu_flags;
+        a2.stamps = (ctx->debug & 1) ? (unsigned long long*)((char*)ctx->scratch + 3600) : nullptr;
+        a2.epoch = ++ctx->lu_epoch;
+        if (a2.epoch == 0) a2.epoch = ++ctx->lu_epoch;        // 0 is the cleared state
+        void* args2[] = {&a2};
+        SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)lu_fused_kernel, dim3(want2), dim3(LF_THREADS), args2, smem, ctx->stream));
+        ctx->launches++;
+        return 0;
+    }
     LfArgs a;
     a.N = (int)N;
     a.A = (double*)A;
@@ -353,13 +753,13 @@ extern "C" int sktt_lu_solve_fused(sktt_ctx* ctx, int64_t N, void* A, void* b, i
     a.ipiv = ipiv_dev;
     a.info = info_dev;
     int per_sm = 0;
-    SKTT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lu_fused_kernel, LF_THREADS, smem));
+    SKTT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lu_fused_kernel_v1, LF_THREADS, smem));
     if (per_sm < 1) return sktt_fail(ctx, SKTT_ERR_ARG, "lu_solve_fused: kernel does not fit an SM");
     int grid = ctx->sm_count;
     const int want = (int)((N / LF_CB) + 1);
     if (grid > want) grid = want;
     void* args[] = {&a};
-    SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)lu_fused_kernel, dim3(grid), dim3(LF_THREADS), args, smem, ctx->stream));
+    SKTT_CUDA(ctx, cudaLaunchCooperativeKernel((void*)lu_fused_kernel_v1, dim3(grid), dim3(LF_THREADS), args, smem, ctx->stream));
     ctx->launches++;
     return 0;
 }
