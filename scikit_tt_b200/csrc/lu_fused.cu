@@ -1,6 +1,8 @@
 // lu_fused.cu -- np.linalg.solve of one dense fp64 micro system (sle.py:505-509: gesv = LU with partial pivoting + two
 // triangular solves) as ONE cooperative launch, for the sizes of BASELINE config 1 (signaling cascade, solution rank 4:
-// 1024 unknowns) and of the same-configuration leg of the bench.  The host-driven factorisation of lu.cu issues ~100
+// 1024 unknowns) and of the same-configuration leg of the bench.  Two forms live here: the DATAFLOW form further down (one
+// CTA per block of 16 columns, a flag per panel instead of grid barriers, the panel in registers: 2.1 ms for 1024 unknowns)
+// is the one that runs; the first form described next (3.5 ms) is kept behind ctx debug bit 10 for A/B timing.  The host-driven factorisation of lu.cu issues ~100
 // launches per 1024^2 system and is bound by their latency and by one cluster barrier per column (4.0 ms + 0.34 ms for the
 // solve); here the loop over the panels lives on the device:
 //
@@ -358,73 +360,90 @@ __device__ __forceinline__ void lf_take(double& best, int& bi, double ob, int oi
     best = t ? ob : best;
     bi = t ? oi : bi;
 }
+// The same rule over a warp with three redux.sync instead of five shuffle rounds (measured: 120 cycles per round of
+// 64-bit shuffles + compares): the bit pattern of a non-negative double orders like an unsigned integer, so the maximum is
+// found word by word, then the smallest row among the lanes that hold it.  Lanes without a candidate pass (0, 0, INT_MAX).
+__device__ __forceinline__ void lf_warp_argmax(unsigned& hi, unsigned& lo, int& idx) {
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const bool c1 = hi == mh;
+    const unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+    const bool c2 = c1 && lo == ml;
+    idx = (int)__reduce_min_sync(0xffffffffu, c2 ? (unsigned)idx : 0x7fffffffu);
+    hi = mh;
+    lo = ml;
+}
 
+// stage: shared memory for 512 rows x 17 doubles -- the panel enters and leaves the registers through it, so that global
+// memory sees whole 128-byte rows read by eight lanes each (every thread fetching its own row with sixteen 8-byte loads
+// cost 4 us per direction: one line per lane and instruction).
+// s_rows: [16 warps][16] candidate rows, s_crow: row c before the interchange.
 template <int RPT>
-__device__ void lf2_panel(const LfArgs2& a, int j0, int nb, double* s_prow, double* s_crow, double* s_val, int* s_idx,
-                          int* s_piv, unsigned long long* clk) {
+__device__ void lf2_panel(const LfArgs2& a, int j0, int nb, double* stage, double* s_rows, double* s_crow, unsigned* s_key,
+                          int* s_idx, int* s_piv) {
     const int N = a.N, rows = N - j0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double pr[RPT][LF_NB];
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
-        const int r = tid + u * LF_THREADS;
-        const double* src = a.A + (long long)(j0 + (r < rows ? r : 0)) * N + j0;
+        const int r0 = u * LF_THREADS, cnt = min(LF_THREADS, rows - r0);       // rows of this chunk (block-uniform)
+        __syncthreads();
+        for (int e = tid; e < cnt * LF_NB; e += LF_THREADS) {
+            const int rr = e >> 4, c = e & 15;
+            stage[rr * LF_LDP + c] = c < nb ? __ldcg(a.A + (long long)(j0 + r0 + rr) * N + j0 + c) : 0.0;
+        }
+        __syncthreads();
 #pragma unroll
-        for (int c = 0; c < LF_NB; ++c) pr[u][c] = (r < rows && c < nb) ? __ldcg(src + c) : 0.0;
+        for (int c = 0; c < LF_NB; ++c) pr[u][c] = tid < cnt ? stage[tid * LF_LDP + c] : 0.0;
     }
 #pragma unroll
     for (int c = 0; c < LF_NB; ++c) {
         if (c < nb) {                                         // uniform
-            if (clk && c == 8) clk[0] = clock64();
+            // the exchange buffers alternate between columns: what column c + 1 publishes is not what a slow thread may
+            // still be reading for column c, so ONE barrier per column is enough
+            double* const x_rows = s_rows + (c & 1) * (16 * LF_NB);
+            double* const x_crow = s_crow + (c & 1) * LF_NB;
+            unsigned* const x_key = s_key + (c & 1) * 32;
+            int* const x_idx = s_idx + (c & 1) * 16;
             double best = -1.0;
-            int bi = c;
+            int bi = 0x7fffffff;
 #pragma unroll
             for (int u = 0; u < RPT; ++u) {
                 const int r = tid + u * LF_THREADS;
                 if (r >= c && r < rows) lf_take(best, bi, fabs(pr[u][c]), r);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                lf_take(best, bi, ob, oi);
-            }
-            if (lane == 0) {
-                s_val[warp] = best;
-                s_idx[warp] = bi;
-            }
-            if (clk && c == 8) clk[1] = clock64();
-            __syncthreads();
-            if (clk && c == 8) clk[2] = clock64();
-            best = s_val[lane & 15];
-            bi = s_idx[lane & 15];
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                lf_take(best, bi, ob, oi);
-            }
-            // every thread holds the same (best, bi).  The owner of the pivot row and the owner of row c publish their rows.
+            unsigned hi = best >= 0.0 ? (unsigned)__double2hiint(best) : 0u, lo = best >= 0.0 ? (unsigned)__double2loint(best) : 0u;
+            lf_warp_argmax(hi, lo, bi);
+            // the warp's candidate row goes to shared memory together with its key: ONE barrier per column
 #pragma unroll
             for (int u = 0; u < RPT; ++u) {
                 const int r = tid + u * LF_THREADS;
                 if (r == bi) {
 #pragma unroll
-                    for (int cc = 0; cc < LF_NB; ++cc) s_prow[cc] = pr[u][cc];
+                    for (int cc = 0; cc < LF_NB; ++cc) x_rows[warp * LF_NB + cc] = pr[u][cc];
                 }
-                if (r == c && bi != c) {
+                if (r == c) {
 #pragma unroll
-                    for (int cc = 0; cc < LF_NB; ++cc) s_crow[cc] = pr[u][cc];
+                    for (int cc = 0; cc < LF_NB; ++cc) x_crow[cc] = pr[u][cc];
                 }
             }
+            if (lane == 0) {
+                x_key[2 * warp] = hi;
+                x_key[2 * warp + 1] = lo;
+                x_idx[warp] = bi;
+            }
+            __syncthreads();
+            hi = x_key[2 * (lane & 15)];
+            lo = x_key[2 * (lane & 15) + 1];
+            bi = x_idx[lane & 15];
+            lf_warp_argmax(hi, lo, bi);
+            // every thread holds the same key and pivot row bi; the warp that offered it: the first whose candidate is bi
+            const int wwin = __ffs(__ballot_sync(0xffffffffu, lane < 16 && x_idx[lane & 15] == bi)) - 1;
+            const double* prow = x_rows + wwin * LF_NB;
             if (tid == 0) {
                 s_piv[c] = j0 + bi;
-                if (!(best > 0.0)) atomicCAS(a.info, 0, j0 + c + 1);
+                if (hi == 0u && lo == 0u) atomicCAS(a.info, 0, j0 + c + 1);
             }
-            if (clk && c == 8) clk[3] = clock64();
-            __syncthreads();
-            if (clk && c == 8) clk[4] = clock64();
-            const double piv = s_prow[c];
+            const double piv = prow[c];
             const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
 #pragma unroll
             for (int u = 0; u < RPT; ++u) {
@@ -432,31 +451,34 @@ __device__ void lf2_panel(const LfArgs2& a, int j0, int nb, double* s_prow, doub
                 if (bi != c) {                                // the interchange, in registers
                     if (r == c) {
 #pragma unroll
-                        for (int cc = 0; cc < LF_NB; ++cc) pr[u][cc] = s_prow[cc];
+                        for (int cc = 0; cc < LF_NB; ++cc) pr[u][cc] = prow[cc];
                     } else if (r == bi) {
 #pragma unroll
-                        for (int cc = 0; cc < LF_NB; ++cc) pr[u][cc] = s_crow[cc];
+                        for (int cc = 0; cc < LF_NB; ++cc) pr[u][cc] = x_crow[cc];
                     }
                 }
                 if (r > c && r < rows) {
-                    const double l = pr[u][c] * inv;
+                    const double l = pr[u][c] * inv;          // multiplier by the reciprocal of the pivot, as LAPACK's getf2
                     pr[u][c] = l;
 #pragma unroll
                     for (int cc = 0; cc < LF_NB; ++cc)
-                        if (cc > c) pr[u][cc] = fma(-l, s_prow[cc], pr[u][cc]);
+                        if (cc > c) pr[u][cc] = fma(-l, prow[cc], pr[u][cc]);
                 }
             }
-            if (clk && c == 8) clk[5] = clock64();
         }
     }
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
-        const int r = tid + u * LF_THREADS;
-        if (r < rows) {
-            double* dst = a.A + (long long)(j0 + r) * N + j0;
+        const int r0 = u * LF_THREADS, cnt = min(LF_THREADS, rows - r0);
+        __syncthreads();
+        if (tid < cnt) {
 #pragma unroll
-            for (int c = 0; c < LF_NB; ++c)
-                if (c < nb) dst[c] = pr[u][c];
+            for (int c = 0; c < LF_NB; ++c) stage[tid * LF_LDP + c] = pr[u][c];
+        }
+        __syncthreads();
+        for (int e = tid; e < cnt * LF_NB; e += LF_THREADS) {
+            const int rr = e >> 4, c = e & 15;
+            if (c < nb) a.A[(long long)(j0 + r0 + rr) * N + j0 + c] = stage[rr * LF_LDP + c];
         }
     }
     __syncthreads();
@@ -468,8 +490,9 @@ __global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs2 a) {
     const int N = a.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = LF_THREADS / 32;
     double* sm = reinterpret_cast<double*>(smem_raw);
-    __shared__ double s_val[16], s_prow[LF_NB], s_crow[LF_NB];
-    __shared__ int s_idx[16], s_piv[LF_NB], s_pos[2 * LF_NB], s_content[2 * LF_NB], s_np;
+    __shared__ double s_rows[2 * 16 * LF_NB], s_crow[2 * LF_NB];
+    __shared__ unsigned s_key[2 * 32];
+    __shared__ int s_idx[2 * 16], s_piv[LF_NB], s_pos[2 * LF_NB], s_content[2 * LF_NB], s_np;
     const int npan = (N + LF_NB - 1) / LF_NB;
     const int p = blockIdx.x;                                 // my block: columns 16 p ..; p == npan: the right-hand side
     const bool is_rhs = p == npan;
@@ -539,9 +562,13 @@ __global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs2 a) {
         // ---- U12 = L11^-1 top: warp w takes column w, lane r holds row r; right-looking elimination through shuffles
         if (warp < cw) {
             double v = lane < nb ? top[lane * LF_NB + warp] : 0.0;
-            for (int c = 0; c + 1 < nb; ++c) {
+            double lrow[LF_NB];                               // my row of the unit-lower triangle (zero from the diagonal on)
+#pragma unroll
+            for (int c = 0; c < LF_NB; ++c) lrow[c] = (lane < nb && c < lane) ? L11[lane * LF_LDP + c] : 0.0;
+#pragma unroll
+            for (int c = 0; c + 1 < LF_NB; ++c) {
                 const double vc = __shfl_sync(0xffffffffu, v, c);
-                if (lane > c && lane < nb) v = fma(-L11[lane * LF_LDP + c], vc, v);
+                v = fma(-lrow[c], vc, v);
             }
             if (lane < nb) top[lane * LF_NB + warp] = v;
         }
@@ -555,7 +582,53 @@ __global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs2 a) {
         if (k == nupd - 1) tick(4);
         // ---- rank-nb update of the rows below the panel: C[i, :] -= L21[i, :] U12, one 8-row block per warp and step, four
         // blocks in flight
-        {
+        if (nb == LF_NB && cw == LF_NB && (N & 1) == 0) {
+            // full block, 16-byte aligned rows.  The fragment maps are permuted so that a lane's four k (its four columns of C)
+            // are CONTIGUOUS: k = 4 fk + s in step s, local column j of tile h <-> column 4 (j >> 1) + 2 h + (j & 1).  A row of
+            // L21 and a row of C are then one 128-byte line read by four lanes with two 16-byte loads each (the textbook
+            // map k = 4 s + fk costs four 8-byte loads per lane and twice the load instructions -- the update was bound by
+            // the LSU, one line per row and instruction: 4.4 us for 512 rows)
+            const int fr = lane >> 2, fk = lane & 3;
+            const int rbeg = j0 + LF_NB, nblk8 = (N - rbeg + 7) / 8;
+            double bfrag[2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int s2 = 0; s2 < 4; ++s2) bfrag[h][s2] = top[(4 * fk + s2) * LF_NB + 4 * (fr >> 1) + 2 * h + (fr & 1)];
+            for (int blk0 = warp; blk0 < nblk8; blk0 += 4 * nwarps) {
+                double2 af[4][2], cv[4][2];
+                int irow[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int blk = blk0 + u * nwarps;
+                    const int i = rbeg + 8 * blk + fr;
+                    const bool rok = blk < nblk8 && i < N;
+                    irow[u] = rok ? i : -1;
+                    const double2* lrow = reinterpret_cast<const double2*>(a.A + (long long)(rok ? i : rbeg) * N + j0 + 4 * fk);
+                    const double2* crow = reinterpret_cast<const double2*>(&cols.at(rok ? i : rbeg, 4 * fk));
+                    af[u][0] = __ldcg(lrow);
+                    af[u][1] = __ldcg(lrow + 1);
+                    cv[u][0] = crow[0];
+                    cv[u][1] = crow[1];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        lf_dmma(acc[h][0], acc[h][1], af[u][0].x, bfrag[h][0]);
+                        lf_dmma(acc[h][0], acc[h][1], af[u][0].y, bfrag[h][1]);
+                        lf_dmma(acc[h][0], acc[h][1], af[u][1].x, bfrag[h][2]);
+                        lf_dmma(acc[h][0], acc[h][1], af[u][1].y, bfrag[h][3]);
+                    }
+                    if (irow[u] >= 0) {
+                        double2* crow = reinterpret_cast<double2*>(&cols.at(irow[u], 4 * fk));
+                        crow[0] = make_double2(cv[u][0].x - acc[0][0], cv[u][0].y - acc[0][1]);
+                        crow[1] = make_double2(cv[u][1].x - acc[1][0], cv[u][1].y - acc[1][1]);
+                    }
+                }
+            }
+        } else {
             const int fr = lane >> 2, fk = lane & 3;
             const int rbeg = j0 + nb, nblk8 = (N - rbeg + 7) / 8;
             double bfrag[2][4];                               // B fragments: k = 4 s + fk, n = 8 h + fr (U12, shared memory)
@@ -614,10 +687,9 @@ __global__ void __launch_bounds__(LF_THREADS) lu_fused_kernel(LfArgs2 a) {
     if (!is_rhs) {
         // ---- my block is panel p
         const int j0 = p * LF_NB, rows = N - j0;
-        unsigned long long* clk = st ? st + 8 : nullptr;
-        if (rows <= LF_THREADS) lf2_panel<1>(a, j0, cw, s_prow, s_crow, s_val, s_idx, s_piv, clk);
-        else if (rows <= 2 * LF_THREADS) lf2_panel<2>(a, j0, cw, s_prow, s_crow, s_val, s_idx, s_piv, clk);
-        else lf2_panel<3>(a, j0, cw, s_prow, s_crow, s_val, s_idx, s_piv, clk);
+        if (rows <= LF_THREADS) lf2_panel<1>(a, j0, cw, sm, s_rows, s_crow, s_key, s_idx, s_piv);
+        else if (rows <= 2 * LF_THREADS) lf2_panel<2>(a, j0, cw, sm, s_rows, s_crow, s_key, s_idx, s_piv);
+        else lf2_panel<3>(a, j0, cw, sm, s_rows, s_crow, s_key, s_idx, s_piv);
         __syncthreads();
         tick(6);
         if (tid == 0) {
@@ -699,6 +771,8 @@ static size_t lf_smem(int N) {
     size_t fix = ((size_t)(N + 1) / 2 + 1 + (size_t)N * LF_NB) * sizeof(double);
     size_t back = ((size_t)N + LF_NB * LF_LDP) * sizeof(double);
     size_t m = panel;
+    size_t stage = (size_t)LF_THREADS * LF_LDP * sizeof(double);
+    if (stage > m) m = stage;
     if (upd > m) m = upd;
     if (fix > m) m = fix;
     if (back > m) m = back;

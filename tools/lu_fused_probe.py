@@ -40,7 +40,7 @@ rng = np.random.default_rng(N)
 M = rng.standard_normal((N, N)); f = rng.standard_normal(N)
 dev.set_debug(1)
 x = dev.solve_fused(dev.to_device(M), dev.to_device(f))
-st = [int(v) for v in dev.scratch_peek(3600, 8)]
+st = [int(v) for v in dev.scratch_peek(3600, 14)]
 dev.set_debug(0)
 names = ["L11 + pivots + row list", "gather", "U12", "scatter", "rank-16 update", "panel (load, 16 columns, store)", "publish"]
 print("CTA of the middle block, last update and own panel [us]:", ", ".join(f"{n} {(b - a) / 1e3:.2f}" for n, a, b in zip(names, st, st[1:])))
