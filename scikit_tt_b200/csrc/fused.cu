@@ -923,6 +923,12 @@ struct PcgParams {
     double* part;             // [2][gridDim.x][2] partial sums (double-buffered)
     double* out;              // [0] iterations, [1] true relres, [2] cycles, [3] status (0 ok, 1 iteration limit, 2 breakdown)
     unsigned long long* dbg;  // optional: %globaltimer stamps of CTA 0 during a solve (ctx debug bit 0)
+    // optional: right-hand side and iterate in the NATURAL layout [r_act][n][c_act] -- the kernel builds the tiled vectors f
+    // and u itself (and clears w) in the pass that forms |f|^2, and leaves the solution in u_nat: four stream operations
+    // (two tiling kernels, a memset, the back conversion) less per micro solve
+    const double* f_nat;
+    double* u_nat;
+    int r_act, c_act;
 };
 
 namespace {
@@ -1056,15 +1062,41 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
         return;
     }
 
+    // natural index of tiled element e = (nn, row, col) of a vector [n][r][68], or -1 for padding
+    auto nat_index = [&](int e) -> long long {
+        const int col = e % Cfg::LDB, t = e / Cfg::LDB, row = t % a.r, nn = t / a.r;
+        return (col < a.c_act && row < a.r_act) ? ((long long)row * a.ntot + nn) * a.c_act + col : -1;
+    };
+    auto store_solution = [&]() {                          // tiled iterate -> the caller's natural layout
+        if (!a.u_nat) return;
+        for (long long i = gtid; i < a.N; i += gstride) {
+            const long long j = nat_index((int)i);
+            if (j >= 0) a.u_nat[j] = __ldcg(a.u + i);
+        }
+    };
     // |f|^2
     double fn2, rr, tmp;
     {
         double acc = 0.0;
-        for (long long i = gtid; i < a.N; i += gstride) acc = fma(a.f[i], a.f[i], acc);
+        if (a.f_nat) {
+            double* ft = const_cast<double*>(a.f);
+            for (long long i = gtid; i < a.N; i += gstride) {
+                const long long j = nat_index((int)i);
+                const double fv = j >= 0 ? a.f_nat[j] : 0.0;
+                ft[i] = fv;
+                a.u[i] = j >= 0 ? a.u_nat[j] : 0.0;
+                a.w[i] = 0.0;                              // the matvec never writes the padding columns of w
+                acc = fma(fv, fv, acc);
+            }
+        } else {
+            for (long long i = gtid; i < a.N; i += gstride) acc = fma(a.f[i], a.f[i], acc);
+        }
         grid_sum2(acc, 0.0, fn2, tmp);
     }
     if (fn2 == 0.0) {
         for (long long i = gtid; i < a.N; i += gstride) a.u[i] = 0.0;
+        if (a.u_nat)
+            for (long long i = gtid; i < (long long)a.r_act * a.ntot * a.c_act; i += gstride) a.u_nat[i] = 0.0;
         if (gtid == 0) a.out[0] = a.out[1] = a.out[2] = a.out[3] = 0.0;
         return;
     }
@@ -1204,6 +1236,7 @@ __global__ void __launch_bounds__(THREADS) pcg_persistent_kernel(PcgParams a) {
         }
     }
     if (!(relres <= a.tol)) status = hit_limit ? 1 : (broke ? 2 : 0);   // 0 with relres > tol: stagnated at the eps * cond floor
+    store_solution();                                      // every CTA is behind the barriers of the last true residual
     if (stamps && cta == 0 && tid == 0) stamps[0] = (unsigned long long)nstamp;
     if (gtid == 0) {
         a.out[0] = (double)iters;
@@ -1343,7 +1376,7 @@ int sktt_fused_matvec(sktt_ctx* ctx, long long r, long long R, long long m, long
 int sktt_fused_pcg_persistent(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
                               const double* f, double* u, double* rv, double* p, double* s, double* w, double* T1p,
                               double tol, int max_iters, int max_cycles, int mode, int reps, double* part,
-                              double* out_dev) {
+                              double* out_dev, const double* f_nat, double* u_nat, long long r_act, long long c_act) {
     PcgParams a;
     a.image = image;
     a.na = img_a_elems(R, m, n);
@@ -1368,6 +1401,10 @@ int sktt_fused_pcg_persistent(sktt_ctx* ctx, long long r, long long R, long long
     a.reps = reps;
     a.part = part;
     a.out = out_dev;
+    a.f_nat = f_nat;
+    a.u_nat = u_nat;
+    a.r_act = (int)r_act;
+    a.c_act = (int)c_act;
     a.dbg = (mode == 0 && (ctx->debug & 1)) ? (unsigned long long*)((char*)ctx->scratch + 3600) : nullptr;
     const size_t smem = pcg_phase_bytes((int)r) + pcg_rres_bytes() + 128;
     SKTT_ONCE_PER_DEVICE(ctx);

@@ -23,7 +23,8 @@ int sktt_fused_matvec_tiled_dots(sktt_ctx* ctx, long long r, long long R, long l
 int sktt_fused_pcg_persistent(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
                               const double* f, double* u, double* rv, double* p, double* s, double* w, double* T1p,
                               double tol, int max_iters, int max_cycles, int mode, int reps, double* part,
-                              double* out_dev);
+                              double* out_dev, const double* f_nat = nullptr, double* u_nat = nullptr, long long r_act = 0,
+                              long long c_act = 0);
 
 // The operator as the Krylov loops see it: either the generic contraction chain on natural-layout vectors, or the
 // prepared fused matvec on tiled-layout vectors (all Krylov vectors then live in that layout; padding stays zero).
@@ -601,7 +602,7 @@ static int cg_tiled_refined_host(sktt_ctx* ctx, const KOp& op, const double* f, 
 #define PERSISTENT_CG_ITERS 300
 static int cg_tiled_persistent(sktt_ctx* ctx, const KOp& op, const double* f, double* u, double tol, int max_cycles,
                                double* work, int* iters_host, double* relres_host, int* cycles_host, bool* finished,
-                               double* result_dev = nullptr) {
+                               double* result_dev = nullptr, const double* f_nat = nullptr, double* u_nat = nullptr) {
     const CgTiledBufs b = cg_tiled_bufs(op, work);
     const sktt_local_op& o = op.op;
     double* part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
@@ -611,10 +612,12 @@ static int cg_tiled_persistent(sktt_ctx* ctx, const KOp& op, const double* f, do
     part = (double*)((char*)ctx->scratch + SKTT_SCRATCH_BULK_OFF);
     outd = part + 4 * 256;
     // the matvec never writes the four padding columns of w; they enter r = f - w and every norm, so they must be zero
-    SKTT_CUDA(ctx, cudaMemsetAsync(b.w, 0, (size_t)op.N * sizeof(double), ctx->stream));
+    // (with natural-layout operands the kernel clears w itself while it tiles f and u)
+    if (!f_nat) SKTT_CUDA(ctx, cudaMemsetAsync(b.w, 0, (size_t)op.N * sizeof(double), ctx->stream));
     if (result_dev) {                                          // deferred form: the outcome stays on the device
         return sktt_fused_pcg_persistent(ctx, fused_rpad(o.r), o.R, o.m, o.n, (const double*)o.image, f, u, b.r, b.p, b.s, b.w,
-                                         b.mvwork, tol, PERSISTENT_CG_ITERS, max_cycles, 0, 0, part, result_dev);
+                                         b.mvwork, tol, PERSISTENT_CG_ITERS, max_cycles, 0, 0, part, result_dev, f_nat, u_nat,
+                                         o.r, o.r3);
     }
     SKTT_TRY(sktt_fused_pcg_persistent(ctx, fused_rpad(o.r), o.R, o.m, o.n, (const double*)o.image, f, u, b.r, b.p, b.s, b.w, b.mvwork,
                                        tol, PERSISTENT_CG_ITERS, max_cycles, 0, 0, part, outd));
@@ -669,11 +672,10 @@ extern "C" int sktt_krylov_solve_refined_async(sktt_ctx* ctx, int dtype, const s
     if (!k.op.image) return sktt_fail(ctx, SKTT_ERR_ARG, "krylov_solve_refined_async: unsupported operator");
     k.tiled = true;
     k.N = sktt_fused_tiled_len(fused_rpad(k.op.r), k.op.n);
-    SKTT_TRY(sktt_fused_to_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, (const double*)f, ft, 0, k.op.r, k.op.r3));
-    SKTT_TRY(sktt_fused_to_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, (const double*)u, ut, 0, k.op.r, k.op.r3));
+    // f and u stay in the caller's natural layout: the kernel tiles them, clears w and writes the solution back itself
     bool finished = false;
-    SKTT_TRY(cg_tiled_persistent(ctx, k, ft, ut, tol, max_cycles, w, nullptr, nullptr, nullptr, &finished, result_dev));
-    return sktt_fused_from_tiled_ex(ctx, fused_rpad(k.op.r), k.op.n, ut, (double*)u, k.op.r, k.op.r3);
+    return cg_tiled_persistent(ctx, k, ft, ut, tol, max_cycles, w, nullptr, nullptr, nullptr, &finished, result_dev,
+                               (const double*)f, (double*)u);
 }
 
 // ------------------------------------------------------------------------------------------------

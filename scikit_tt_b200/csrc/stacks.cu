@@ -696,7 +696,8 @@ extern "C" int sktt_local_matvec_tiled(sktt_ctx* ctx, int dtype, const sktt_loca
 int sktt_fused_pcg_persistent(sktt_ctx* ctx, long long r, long long R, long long m, long long n, const double* image,
                               const double* f, double* u, double* rv, double* p, double* s, double* w, double* T1p,
                               double tol, int max_iters, int max_cycles, int mode, int reps, double* part,
-                              double* out_dev);
+                              double* out_dev, const double* f_nat = nullptr, double* u_nat = nullptr, long long r_act = 0,
+                              long long c_act = 0);
 
 // `reps` applications yt = M vt of a prepared operator inside ONE persistent cooperative launch (the form the matvec
 // takes inside the persistent CG kernel): the contraction chain without per-launch overheads, for the roofline line.
