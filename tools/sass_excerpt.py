@@ -15,8 +15,8 @@ for line in sass.splitlines():
         continue
     if cur is not None and re.match(r"\s*/\*[0-9a-f]{4,}\*/", line):
         cur.append(line.rstrip())
-KEYS = ["DMMA", "DFMA", "UBLKCP", "UTMALDG", "SYNCS", "LDS", "LDG", "STG", "BAR", "LDGSTS", "ATOM", "RED", "SHFL", "MEMBAR", "UCGABAR", "CCTL"]
-HOT = ["pcg_persistent_kernel", "stack_persistent_kernel", "gemm_dmma_kernel<128, 128", "gemm_dmma_kernel<64, 64", "mv_stage23_kernel",
+KEYS = ["DMMA", "DFMA", "UBLKCP", "UTMALDG", "SYNCS", "LDS", "LDG", "STG", "BAR", "LDGSTS", "ARRIVES", "REDUX", "ATOM", "RED", "SHFL", "MEMBAR", "UCGABAR", "CCTL"]
+HOT = ["pcg_persistent_kernel", "stack_nat_kernel<false>", "lu_fused_kernel(", "stack_persistent_kernel", "gemm_dmma_kernel<128, 128", "gemm_dmma_kernel<64, 64", "mv_stage23_kernel",
        "mv_stage1_kernel", "beig_kernel<cplx>", "bsvd_kernel", "cholqr_kernel<double", "lu_panel_cluster_kernel<double>"]
 def op(line):
     m = re.search(r"\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
