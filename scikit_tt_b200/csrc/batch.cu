@@ -85,117 +85,309 @@ __global__ void __launch_bounds__(BE_THREADS) beig_kernel(BeigArgs a) {
     //   2. multipliers l_i = S[i,j] / pivot: written back and staged in shared memory
     //   3. rank-1 update of the trailing block from the two staged vectors; the threads that produce column j + 1 also
     //      vote for the next pivot (atomicMax on a key made of the truncated magnitude and the row index)
-    unsigned long long* pkey = reinterpret_cast<unsigned long long*>(dred);        // [0]: next pivot key (dred is free here)
-    {
-        // pivot of column 0
-        double best = -1.0;
-        int bi = 0;
-        for (int i = tid; i < N; i += BE_THREADS) {
-            cplx v = S[(long long)i * N];
-            double c1 = fabs(v.re) + fabs(v.im);
-            if (c1 > best) { best = c1; bi = i; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        if (lane == 0) { tmp[warp].re = best; ired[warp] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < nwarps; ++w)
-                if (tmp[w].re > best || (tmp[w].re == best && ired[w] < bi)) { best = tmp[w].re; bi = ired[w]; }
-            sflag[0] = bi;
-        }
-        __syncthreads();
-    }
-    for (int j = 0; j < N; ++j) {
-        const int p = sflag[0];
-        cplx* rowj = S + (long long)j * N;
-        cplx* rowp = S + (long long)p * N;
-        for (int c = tid; c < N; c += BE_THREADS) {                 // (1)
-            cplx aj = rowj[c], ap = rowp[c];
-            if (p != j) {
-                rowj[c] = ap;
-                rowp[c] = aj;
+    // Blocked form (used whenever the Krylov basis lives in shared memory, whose space is idle during the factorisation):
+    // panels of 8 columns are factorised in shared memory, the interchanges reach the rest of the matrix as ONE gather /
+    // scatter per column (net permutation of the <= 16 touched rows), U12 by forward substitution in registers, and the
+    // trailing block is read and written once per PANEL instead of once per column (N = 192: 9 MB instead of 75 MB through
+    // one SM's L2 port, 24 instead of 192 rounds of dependent L2 round trips).  Same elimination order, same fma sequence
+    // per entry as the column form below: the factors are bit-identical; the pivot is the exact first maximum of
+    // |re| + |im| (LAPACK's izamax).
+    constexpr int PB = 8;
+    const bool blocked = a.v_in_smem && m + 1 >= 2 * PB;
+    if (blocked) {
+        cplx* Pn = V;                                   // [N][PB] panel rows (row i = matrix row j0 + i)
+        cplx* Ust = Pn + (size_t)N * PB;                // [PB][N] rows of U12 (absolute column index)
+        __shared__ int b_pos[2 * PB], b_content[2 * PB], b_piv[PB], b_np;
+        for (int j0 = 0; j0 < N; j0 += PB) {
+            const int nb = min(PB, N - j0), R = N - j0;
+            for (int e = tid; e < R * PB; e += BE_THREADS) {
+                const int i = e / PB, c = e % PB;
+                Pn[e] = c < nb ? S[(long long)(j0 + i) * N + j0 + c] : CX::zero();
             }
-            if (c >= j) urow[c] = ap;
-        }
-        if (tid == 0) {
-            int t = perm[j];
-            perm[j] = perm[p];
-            perm[p] = t;
-            pkey[0] = 0ull;
-        }
-        __syncthreads();
-        const cplx piv = urow[j];
-        const bool okp = (fabs(piv.re) + fabs(piv.im)) > 0.0;
-        const cplx inv = okp ? CX::div(CX::one(), piv) : CX::zero();
-        for (int i = j + 1 + tid; i < N; i += BE_THREADS) {         // (2)
-            cplx l = CX::mul(S[(long long)i * N + j], inv);
-            S[(long long)i * N + j] = l;
-            lcol[i] = l;
-        }
-        if (tid == 0) {
-            invd[j] = inv;
-            if (!okp) sflag[3] |= 2;
-        }
-        __syncthreads();
-        // (3): a warp per row, lanes along the row (coalesced), four independent 16-byte loads in flight per thread -- the
-        // trailing block lives in L2, so the update is bound by how many loads a CTA keeps outstanding
-        for (int i = j + 1 + 2 * warp; i < N; i += 2 * nwarps) {
-            const bool two = i + 1 < N;
-            const cplx l0 = lcol[i], l1 = two ? lcol[i + 1] : CX::zero();
-            cplx* row0 = S + (long long)i * N;
-            cplx* row1 = row0 + N;
-            for (int c0 = j + 1 + lane; c0 < N; c0 += 32 * 4) {
-                cplx v0[4], v1[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int c = c0 + 32 * u;
-                    if (c < N) {
-                        v0[u] = row0[c];
-                        if (two) v1[u] = row1[c];
-                    }
+            __syncthreads();
+            for (int c = 0; c < nb; ++c) {
+                double best = -1.0;
+                int bi = c;
+                for (int i = c + tid; i < R; i += BE_THREADS) {
+                    const cplx v = Pn[i * PB + c];
+                    const double c1 = fabs(v.re) + fabs(v.im);
+                    if (c1 > best) { best = c1; bi = i; }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int c = c0 + 32 * u;
-                    if (c < N) {
-                        const cplx uu = urow[c];
-                        cplx w = v0[u];
-                        w.re = fma(-l0.re, uu.re, w.re);
-                        w.re = fma(l0.im, uu.im, w.re);
-                        w.im = fma(-l0.re, uu.im, w.im);
-                        w.im = fma(-l0.im, uu.re, w.im);
-                        row0[c] = w;
-                        cplx w1 = v1[u];
-                        if (two) {
-                            w1.re = fma(-l1.re, uu.re, w1.re);
-                            w1.re = fma(l1.im, uu.im, w1.re);
-                            w1.im = fma(-l1.re, uu.im, w1.im);
-                            w1.im = fma(-l1.im, uu.re, w1.im);
-                            row1[c] = w1;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (lane == 0) { tmp[warp].re = best; ired[warp] = bi; }
+                __syncthreads();
+                best = tmp[0].re;
+                bi = ired[0];
+                for (int w = 1; w < nwarps; ++w)
+                    if (tmp[w].re > best || (tmp[w].re == best && ired[w] < bi)) { best = tmp[w].re; bi = ired[w]; }
+                const int p = bi;                             // the same in every thread
+                cplx mine = CX::zero(), theirs = CX::zero();
+                if (tid < PB) { mine = Pn[c * PB + tid]; theirs = Pn[p * PB + tid]; }
+                __syncthreads();                              // everybody has read the candidates and the two rows
+                if (tid < PB && p != c) {
+                    Pn[c * PB + tid] = theirs;
+                    Pn[p * PB + tid] = mine;
+                }
+                if (tid == 0) {
+                    b_piv[c] = j0 + p;
+                    const int t = perm[j0 + c];
+                    perm[j0 + c] = perm[j0 + p];
+                    perm[j0 + p] = t;
+                }
+                __syncthreads();
+                const cplx piv = Pn[c * PB + c];
+                const bool okp = (fabs(piv.re) + fabs(piv.im)) > 0.0;
+                const cplx inv = okp ? CX::div(CX::one(), piv) : CX::zero();
+                for (int i = c + 1 + tid; i < R; i += BE_THREADS) {
+                    cplx* row = Pn + i * PB;
+                    const cplx l = CX::mul(row[c], inv);
+                    row[c] = l;
+#pragma unroll
+                    for (int cc = 1; cc < PB; ++cc)
+                        if (cc > c && cc < nb) {
+                            const cplx uu = Pn[c * PB + cc];
+                            cplx w = row[cc];
+                            w.re = fma(-l.re, uu.re, w.re);
+                            w.re = fma(l.im, uu.im, w.re);
+                            w.im = fma(-l.re, uu.im, w.im);
+                            w.im = fma(-l.im, uu.re, w.im);
+                            row[cc] = w;
                         }
-                        if (c == j + 1) {
-                            // key: magnitude with its 10 lowest mantissa bits replaced by (1023 - row): the largest |.|
-                            // wins, ties (to 2^-42 relative) go to the smaller row; positive doubles order like their bits
-                            const double c1 = fabs(w.re) + fabs(w.im);
-                            atomicMax(pkey, ((unsigned long long)__double_as_longlong(c1) & ~0x3FFull) | (unsigned long long)(1023 - i));
+                }
+                if (tid == 0) {
+                    invd[j0 + c] = inv;
+                    if (!okp) sflag[3] |= 2;
+                }
+                __syncthreads();
+            }
+            for (int e = tid; e < R * PB; e += BE_THREADS) {
+                const int i = e / PB, c = e % PB;
+                if (c < nb) S[(long long)(j0 + i) * N + j0 + c] = Pn[e];
+            }
+            if (warp == 0) {
+                // rows the interchanges touch: the nb top rows, then every pivot row not yet listed (slot = lane);
+                // `content` follows the rows through the sequence of interchanges
+                int pos = lane < nb ? j0 + lane : -1, content = lane, np = nb;
+                const int mypiv = lane < nb ? b_piv[lane] : -1;
+                for (int c = 0; c < nb; ++c) {
+                    const int pv = __shfl_sync(0xffffffffu, mypiv, c);
+                    const unsigned found = __ballot_sync(0xffffffffu, pos == pv);
+                    int ip;
+                    if (found) {
+                        ip = __ffs(found) - 1;
+                    } else {
+                        ip = np;
+                        if (lane == np) pos = pv;
+                        ++np;
+                    }
+                    const int ca = __shfl_sync(0xffffffffu, content, c), cb = __shfl_sync(0xffffffffu, content, ip);
+                    if (lane == c) content = cb;
+                    if (lane == ip) content = ca;
+                }
+                if (lane < 2 * PB) {
+                    b_pos[lane] = pos;
+                    b_content[lane] = content;
+                }
+                if (lane == 0) b_np = np;
+            }
+            __syncthreads();
+            const int np = b_np;
+            // the interchanges on the columns outside the panel (a thread per column, all its loads in flight), and U12 on the
+            // columns to the right
+            for (int col = tid; col < N; col += BE_THREADS) {
+                if (col >= j0 && col < j0 + nb) continue;
+                cplx v[2 * PB];
+#pragma unroll
+                for (int q = 0; q < 2 * PB; ++q)
+                    v[q] = q < np ? S[(long long)b_pos[b_content[q]] * N + col] : CX::zero();
+                if (col >= j0 + nb) {
+#pragma unroll
+                    for (int r = 1; r < PB; ++r)
+                        if (r < nb) {
+#pragma unroll
+                            for (int c = 0; c < PB; ++c)
+                                if (c < r) {
+                                    const cplx l = Pn[r * PB + c], uu = v[c];
+                                    cplx w = v[r];
+                                    w.re = fma(-l.re, uu.re, w.re);
+                                    w.re = fma(l.im, uu.im, w.re);
+                                    w.im = fma(-l.re, uu.im, w.im);
+                                    w.im = fma(-l.im, uu.re, w.im);
+                                    v[r] = w;
+                                }
+                        }
+#pragma unroll
+                    for (int r = 0; r < PB; ++r)
+                        if (r < nb) Ust[r * N + col] = v[r];
+                }
+#pragma unroll
+                for (int q = 0; q < 2 * PB; ++q)
+                    if (q < np) S[(long long)b_pos[q] * N + col] = v[q];
+            }
+            __syncthreads();
+            // trailing block: S[i, col] -= sum_c L21[i, c] U12[c, col], a warp per pair of rows, lanes along the row
+            for (int i = j0 + nb + 2 * warp; i < N; i += 2 * nwarps) {
+                const bool two = i + 1 < N;
+                cplx l0[PB], l1[PB];
+#pragma unroll
+                for (int c = 0; c < PB; ++c) {
+                    l0[c] = c < nb ? Pn[(i - j0) * PB + c] : CX::zero();
+                    l1[c] = (two && c < nb) ? Pn[(i + 1 - j0) * PB + c] : CX::zero();
+                }
+                cplx* row0 = S + (long long)i * N;
+                cplx* row1 = row0 + N;
+                for (int c0 = j0 + nb + lane; c0 < N; c0 += 32 * 2) {
+                    cplx v0[2], v1[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int c = c0 + 32 * u;
+                        v0[u] = c < N ? row0[c] : CX::zero();
+                        v1[u] = (c < N && two) ? row1[c] : CX::zero();
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int c = c0 + 32 * u;
+                        if (c < N) {
+                            cplx w0 = v0[u], w1 = v1[u];
+#pragma unroll
+                            for (int cc = 0; cc < PB; ++cc)
+                                if (cc < nb) {
+                                    const cplx uu = Ust[cc * N + c];
+                                    w0.re = fma(-l0[cc].re, uu.re, w0.re);
+                                    w0.re = fma(l0[cc].im, uu.im, w0.re);
+                                    w0.im = fma(-l0[cc].re, uu.im, w0.im);
+                                    w0.im = fma(-l0[cc].im, uu.re, w0.im);
+                                    w1.re = fma(-l1[cc].re, uu.re, w1.re);
+                                    w1.re = fma(l1[cc].im, uu.im, w1.re);
+                                    w1.im = fma(-l1[cc].re, uu.im, w1.im);
+                                    w1.im = fma(-l1[cc].im, uu.re, w1.im);
+                                }
+                            row0[c] = w0;
+                            if (two) row1[c] = w1;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        unsigned long long* pkey = reinterpret_cast<unsigned long long*>(dred);        // [0]: next pivot key (dred is free here)
+        {
+            // pivot of column 0
+            double best = -1.0;
+            int bi = 0;
+            for (int i = tid; i < N; i += BE_THREADS) {
+                cplx v = S[(long long)i * N];
+                double c1 = fabs(v.re) + fabs(v.im);
+                if (c1 > best) { best = c1; bi = i; }
+            }
+    #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (lane == 0) { tmp[warp].re = best; ired[warp] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < nwarps; ++w)
+                    if (tmp[w].re > best || (tmp[w].re == best && ired[w] < bi)) { best = tmp[w].re; bi = ired[w]; }
+                sflag[0] = bi;
+            }
+            __syncthreads();
+        }
+        for (int j = 0; j < N; ++j) {
+            const int p = sflag[0];
+            cplx* rowj = S + (long long)j * N;
+            cplx* rowp = S + (long long)p * N;
+            for (int c = tid; c < N; c += BE_THREADS) {                 // (1)
+                cplx aj = rowj[c], ap = rowp[c];
+                if (p != j) {
+                    rowj[c] = ap;
+                    rowp[c] = aj;
+                }
+                if (c >= j) urow[c] = ap;
+            }
+            if (tid == 0) {
+                int t = perm[j];
+                perm[j] = perm[p];
+                perm[p] = t;
+                pkey[0] = 0ull;
+            }
+            __syncthreads();
+            const cplx piv = urow[j];
+            const bool okp = (fabs(piv.re) + fabs(piv.im)) > 0.0;
+            const cplx inv = okp ? CX::div(CX::one(), piv) : CX::zero();
+            for (int i = j + 1 + tid; i < N; i += BE_THREADS) {         // (2)
+                cplx l = CX::mul(S[(long long)i * N + j], inv);
+                S[(long long)i * N + j] = l;
+                lcol[i] = l;
+            }
+            if (tid == 0) {
+                invd[j] = inv;
+                if (!okp) sflag[3] |= 2;
+            }
+            __syncthreads();
+            // (3): a warp per row, lanes along the row (coalesced), four independent 16-byte loads in flight per thread -- the
+            // trailing block lives in L2, so the update is bound by how many loads a CTA keeps outstanding
+            for (int i = j + 1 + 2 * warp; i < N; i += 2 * nwarps) {
+                const bool two = i + 1 < N;
+                const cplx l0 = lcol[i], l1 = two ? lcol[i + 1] : CX::zero();
+                cplx* row0 = S + (long long)i * N;
+                cplx* row1 = row0 + N;
+                for (int c0 = j + 1 + lane; c0 < N; c0 += 32 * 4) {
+                    cplx v0[4], v1[4];
+    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = c0 + 32 * u;
+                        if (c < N) {
+                            v0[u] = row0[c];
+                            if (two) v1[u] = row1[c];
+                        }
+                    }
+    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = c0 + 32 * u;
+                        if (c < N) {
+                            const cplx uu = urow[c];
+                            cplx w = v0[u];
+                            w.re = fma(-l0.re, uu.re, w.re);
+                            w.re = fma(l0.im, uu.im, w.re);
+                            w.im = fma(-l0.re, uu.im, w.im);
+                            w.im = fma(-l0.im, uu.re, w.im);
+                            row0[c] = w;
+                            cplx w1 = v1[u];
                             if (two) {
-                                const double c2 = fabs(w1.re) + fabs(w1.im);
-                                atomicMax(pkey, ((unsigned long long)__double_as_longlong(c2) & ~0x3FFull) |
-                                                    (unsigned long long)(1023 - (i + 1)));
+                                w1.re = fma(-l1.re, uu.re, w1.re);
+                                w1.re = fma(l1.im, uu.im, w1.re);
+                                w1.im = fma(-l1.re, uu.im, w1.im);
+                                w1.im = fma(-l1.im, uu.re, w1.im);
+                                row1[c] = w1;
+                            }
+                            if (c == j + 1) {
+                                // key: magnitude with its 10 lowest mantissa bits replaced by (1023 - row): the largest |.|
+                                // wins, ties (to 2^-42 relative) go to the smaller row; positive doubles order like their bits
+                                const double c1 = fabs(w.re) + fabs(w.im);
+                                atomicMax(pkey, ((unsigned long long)__double_as_longlong(c1) & ~0x3FFull) | (unsigned long long)(1023 - i));
+                                if (two) {
+                                    const double c2 = fabs(w1.re) + fabs(w1.im);
+                                    atomicMax(pkey, ((unsigned long long)__double_as_longlong(c2) & ~0x3FFull) |
+                                                        (unsigned long long)(1023 - (i + 1)));
+                                }
                             }
                         }
                     }
                 }
             }
+            __syncthreads();
+            if (tid == 0 && j + 1 < N) sflag[0] = 1023 - (int)(pkey[0] & 0x3FFull);
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid == 0 && j + 1 < N) sflag[0] = 1023 - (int)(pkey[0] & 0x3FFull);
-        __syncthreads();
     }
     // ---- the 32 x 32 diagonal blocks of L and U are replaced by their inverses (in place: strictly lower part L_kk^-1,
     // upper part U_kk^-1), so that the triangular solves below apply them as small dense products instead of walking a
