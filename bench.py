@@ -19,9 +19,11 @@ factorisations of 4096 x 64 unfoldings.
             of the step's solves), and `matvec_loop`, the matvec phases alone inside one cooperative launch.
 `same_config`: the GPU arm on the configuration the reference arm can run (same operator family at solution rank
             --sample-rank, dense micro systems + LU on both sides) so that the driver's ratio has a same-work counterpart.
+`c1`       : BASELINE configuration 0 at full size (signaling cascade d=20, implicit Euler via sle.als, rank 4) against the
+            reference itself on the host cores, with the parity of the first time step.
 `c5`, `c4`: the two configurations that shard (north_star): the batch of 64 co_oxidation(20) eigenproblems, block-sharded
             over the ranks with the systems of a rank batched inside its GPU, and one sle.als sweep of the d=10, n=16, R=8
-            operator at solution rank 128 whose micro-matvec is rank-sharded over the ranks.  With --gpus N these legs are
+            operator at solution rank 256 (--c4-rank) whose micro-matvec is rank-sharded over the ranks.  With --gpus N these legs are
             the strong-scaling curves (total work fixed); the headline stays N independent C3 replicas (the single C3
             system is sequential in the core index and does not shard: SURVEY.md 8e "replicas only").
 `cpu_baseline` / `--impl reference`: the reference's own CPU implementation on the host cores -- PGelss/scikit_tt itself when
@@ -206,7 +208,7 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    warm = min(args.warmup, 1)
+    warm = min(args.warmup, 3)                                # the same warm-up as the GPU arm up to three steps (~2 s each)
     steps = max(1, min(args.steps, args.ref_max_steps))
     val, per_step, kind = cpu_sample(cfg["d"], cfg["n"], args.sample_rank, steps=steps, warmup=warm)
     sample = (f"same operator family (d={cfg['d']}, n={cfg['n']}, R=3) at solution rank {args.sample_rank}: dense micro "
@@ -456,6 +458,59 @@ def leg_same_config(env, args, cfg):
             "note": "what --impl reference runs (dense micro systems + LU at this rank), here on the GPU"}
 
 
+def leg_c1(env, args):
+    """BASELINE config 0 ("the repo's own example, runs on CPU") at FULL size: signaling_cascade(d=20) CME operator (first /
+    middle / last core of the live reference's operator, tests/golden/euler_cascade.npz; the cascade repeats its middle core),
+    ode.implicit_euler via sle.als at solution rank 4 -- dense 1024 x 1024 micro systems, LU with partial pivoting on both
+    sides.  Timed through the public API with host TT objects in and out (end to end by construction)."""
+    from scikit_tt_b200 import TT
+    from scikit_tt_b200.solvers import ode
+    from oracle import tt as ott
+    z = np.load(os.path.join(ROOT, "tests", "golden", "euler_cascade.npz"))
+    d, n, steps = 20, 64, 2
+    opc = [z["op/first"]] + [z["op/mid"].copy() for _ in range(d - 2)] + [z["op/last"]]
+    iv = [np.zeros((1, n, 1, 1)) for _ in range(d)]
+    for c in iv:
+        c[0, 0, 0, 0] = 1.0
+    ranks = [1] + [4] * (d - 1) + [1]
+    guess = ott.ortho_right([np.ones((ranks[i], n, 1, ranks[i + 1])) for i in range(d)])
+    out = {}
+
+    def run():
+        env.flush.zero_()
+        out["sol"] = ode.implicit_euler(TT(opc), TT(iv), TT(guess), [1.0] * steps, progress=False)
+    reps = 3
+    ms, wall = env.timed(run, reps, 1)
+    ms = max(ms, wall)
+    leg = {"workload": "C1: ode.implicit_euler(signaling_cascade(20), sle.als, solution rank 4), 2 time steps = 4 half-sweeps per "
+                       "call, dense 1024^2 micro systems + LU with partial pivoting (one cooperative launch per solve)",
+           "value": 2 * steps * reps * env.world / (ms * 1e-3), "unit": "half-sweeps/s", "ms_per_call": ms / reps, "n_gpus": env.world,
+           "scaling": "weak", "parallelism": "replicas" if env.world > 1 else "single GPU",
+           "e2e_note": "timed through the public API with host numpy cores in and out every call"}
+    if env.rank == 0 and env.world == 1 and not args.no_cpu:
+        mods = _reference_modules()
+        t0 = time.perf_counter()
+        if mods is not None:
+            RTT = mods[0]
+            import io
+            import contextlib
+            with contextlib.redirect_stdout(io.StringIO()):
+                import scikit_tt.solvers.ode as rode
+                ref = rode.implicit_euler(RTT([c.copy() for c in opc]), RTT([c.copy() for c in iv]), RTT([c.copy() for c in guess]),
+                                          [1.0], progress=False)
+            ref1, kind = ref[1].cores, "reference"
+        else:
+            from oracle import ode as oode
+            ref1, kind = oode.implicit_euler(opc, iv, guess, [1.0])[1], "port"
+        dt = time.perf_counter() - t0
+        a = [np.asarray(c) for c in out["sol"][1].cores]
+        b = [np.asarray(c) for c in ref1]
+        leg["cpu_baseline"] = {"value": 2 / dt, "unit": "half-sweeps/s", "cores": len(os.sched_getaffinity(0)), "kind": kind,
+                               "sample": "the first time step of the same call (2 half-sweeps), all BLAS threads"}
+        leg["step1_rel_diff_vs_reference"] = float(ott.norm(ott.sub(a, b)) / ott.norm(b))
+    return leg
+
+
 def leg_c5(env, args):
     """BASELINE config 5: 64 co_oxidation(20) pressures, evp.als (solver as examples/co_oxidation.py:104), rank-8 guess.
     The 64 systems are block-sharded over the ranks (no data-path collective); inside a rank its block runs through the
@@ -560,8 +615,8 @@ def run_ours(args, cfg):
     legs = [s for s in args.legs.split(",") if s]
     c3 = leg_c3(env, args, cfg)
     extra = {}
-    for name, fn in (("same", lambda: leg_same_config(env, args, cfg)), ("c5", lambda: leg_c5(env, args)),
-                     ("c4", lambda: leg_c4(env, args))):
+    for name, fn in (("same", lambda: leg_same_config(env, args, cfg)), ("c1", lambda: leg_c1(env, args)),
+                     ("c5", lambda: leg_c5(env, args)), ("c4", lambda: leg_c4(env, args))):
         if name not in legs:
             continue
         key = "same_config" if name == "same" else name
@@ -608,11 +663,13 @@ def main():
     ap.add_argument("--sample-rank", type=int, default=4, dest="sample_rank")
     ap.add_argument("--ref-max-steps", type=int, default=20, dest="ref_max_steps")
     ap.add_argument("--e2e-steps", type=int, default=3, dest="e2e_steps")
-    ap.add_argument("--legs", default="same,c5,c4", help="extra legs besides the C3 headline: same,c5,c4 (comma separated)")
+    ap.add_argument("--legs", default="same,c1,c5,c4", help="extra legs besides the C3 headline: same,c1,c5,c4 (comma separated)")
     ap.add_argument("--c5-systems", type=int, default=64, dest="c5_systems")
     ap.add_argument("--c5-rank", type=int, default=8, dest="c5_rank")
     ap.add_argument("--c5-solver", default="eigs", dest="c5_solver")
-    ap.add_argument("--c4-rank", type=int, default=128, dest="c4_rank")
+    ap.add_argument("--c4-rank", type=int, default=256, dest="c4_rank",
+                    help="solution rank of the C4 leg (BASELINE names 128 and 256; sharding the micro-matvec over GPUs only pays "
+                         "at 256: 0.15 ms of compute per matvec at 128 does not amortise the exchange, profiles/README.md)")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
     args = ap.parse_args()
     cfg = {"d": args.d, "n": args.n, "r": args.rank, "gpus": args.gpus}
