@@ -62,6 +62,13 @@ int sktt_ctx_set_gemm_mode(sktt_ctx* ctx, int mode);
 /* diagnostics (tools/ only): kernels that support it leave per-phase %globaltimer stamps in the context's scalar
  * scratch area; sktt_scratch_peek synchronises the stream and copies a piece of that area to the host           */
 int sktt_ctx_set_debug(sktt_ctx* ctx, int on);
+/* Deferred mode of sktt_qr_left / sktt_rq_right for tall matrices (the QR / RQ steps of the sweeps, scikit_tt/solvers/sle.py:517-525,
+ * :533-541): the sketched CholeskyQR kernel runs alone, the Householder kernel that normally stands behind its failure flag is
+ * not launched; a failure sets a sticky word that sktt_qr_deferred_failures reads (synchronising) and clears.  A caller that
+ * switches the mode on inspects the word before it trusts the factors (the sweeps do so once per half sweep, together with
+ * the outcomes of the deferred micro solves) and redoes its work with the mode off when it is set. */
+int sktt_ctx_set_qr_deferred(sktt_ctx* ctx, int on);
+int sktt_qr_deferred_failures(sktt_ctx* ctx, int32_t* out_host);
 int sktt_scratch_peek(sktt_ctx* ctx, int64_t byte_offset, int64_t bytes, void* out_host);
 
 /* ------------------------------------------------------------------ generic contraction ------

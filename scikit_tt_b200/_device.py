@@ -86,6 +86,17 @@ class Device:
     def sync(self):
         torch.cuda.synchronize(self.device)
 
+    def set_qr_deferred(self, on):
+        """Tall QR / RQ without the Householder launch behind the failure flag of the sketched CholeskyQR (see
+        qr_deferred_failures)."""
+        self._check(self.lib.sktt_ctx_set_qr_deferred(self.h, int(bool(on))))
+
+    def qr_deferred_failures(self):
+        """1 when a sketched CholeskyQR failed since the last call (synchronises, clears the sticky word), else 0."""
+        out = C.c_int32(0)
+        self._check(self.lib.sktt_qr_deferred_failures(self.h, C.byref(out)))
+        return int(out.value)
+
     def set_debug(self, on):
         self._check(self.lib.sktt_ctx_set_debug(self.h, int(on)))
 

@@ -36,6 +36,8 @@ SIGNATURES = {
     "sktt_launch_count": (i64, [vp]),
     "sktt_ctx_set_gemm_mode": (i32, [vp, i32]),
     "sktt_ctx_set_debug": (i32, [vp, i32]),
+    "sktt_ctx_set_qr_deferred": (i32, [vp, i32]),
+    "sktt_qr_deferred_failures": (i32, [vp, vp]),
     "sktt_scratch_peek": (i32, [vp, i64, i64, vp]),
     "sktt_gemm2": (i32, [vp, i32, i64, i64, i64, pdbl, vp, Idx2, Idx2, i32, vp, Idx2, Idx2, i32, pdbl, vp, Idx2, Idx2]),
     "sktt_stack_op_work": (i64, [i64] * 6),

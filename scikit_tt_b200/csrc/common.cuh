@@ -27,6 +27,8 @@ struct sktt_ctx {
     // panel flags of the one-launch LU (lu_fused.cu): "published" means flags[k] == lu_epoch of the running launch
     void* lu_flags = nullptr;
     unsigned lu_epoch = 0;
+    // deferred mode of the tall QR / RQ (qr.cu): no Householder launch behind the failure flag of the sketched CholeskyQR
+    int qr_deferred = 0;
 };
 
 static inline int sktt_fail(sktt_ctx* ctx, int code, const char* fmt, const char* a = "") {

@@ -269,6 +269,7 @@ __device__ __forceinline__ cplx shfl_xor_num<cplx>(cplx v, int o) {
 // Passes end when ||G - I||_F <= 1e-8 before a pass (that pass squares the defect) or <= 1e-13 (nothing left to do).
 #define CQ_FLOOR 1e-13
 #define CQ_DEBUG_OFF 1536    // byte offset of the optional phase time stamps (globaltimer, CTA 0) in the scalar area
+#define CQ_STICKY_OFF 3864   // sticky "a sketched CholeskyQR failed" word of the deferred mode (sktt_ctx_set_qr_deferred)
 
 __device__ __forceinline__ unsigned long long cq_now() {
     unsigned long long t;
@@ -1103,6 +1104,7 @@ cholqr_kernel(const T* __restrict__ src, QrView lv, int m, int n, int rows_per_c
     if (cta == 0 && tid == 0) {
         status[0] = fail;
         status[1] = passes;
+        if (fail) atomicOr(status + (CQ_STICKY_OFF - CQ_STATUS_OFF) / (int)sizeof(int), 1);
         if (dbg) dbg[0] = (unsigned long long)ndbg;
     }
 }
@@ -1161,8 +1163,29 @@ static int qr_dispatch(sktt_ctx* ctx, int m, int n, const T* src, QrView lv, T* 
         else if (nt <= 2) SKTT_TRY((cholqr_launch_nt<T, 2>(ctx, m, n, src, lv, qdst, qv, rdst, rv, &used)));
         else if (nt <= 4) SKTT_TRY((cholqr_launch_nt<T, 4>(ctx, m, n, src, lv, qdst, qv, rdst, rv, &used)));
     }
+    // deferred mode: the Householder kernel behind the failure flag is not even launched (a cooperative launch that finds
+    // the flag clear and exits still costs ~40 us of stream time: 4.5 % of the bench step); a failure sets the sticky word
+    // the sweep inspects once per half sweep (sktt_qr_deferred_failures) and redoes its work in the careful mode
+    if (used && ctx->qr_deferred) return 0;
     const int* flag = used ? (const int*)((char*)ctx->scratch + CQ_STATUS_OFF) : nullptr;
     return qr_launch<T>(ctx, m, n, src, lv, qdst, qv, rdst, rv, flag);
+}
+
+extern "C" int sktt_ctx_set_qr_deferred(sktt_ctx* ctx, int on) {
+    if (!ctx) return SKTT_ERR_ARG;
+    ctx->qr_deferred = on ? 1 : 0;
+    return 0;
+}
+// Number of sketched CholeskyQR factorisations that failed since the last call (0 or 1: the word is sticky); synchronises the
+// stream and clears the word.
+extern "C" int sktt_qr_deferred_failures(sktt_ctx* ctx, int32_t* out_host) {
+    if (!ctx || !out_host) return SKTT_ERR_ARG;
+    int* sticky = (int*)((char*)ctx->scratch + CQ_STICKY_OFF);
+    SKTT_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, sticky, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SKTT_CUDA(ctx, cudaMemsetAsync(sticky, 0, sizeof(int), ctx->stream));
+    SKTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_host = *(int*)ctx->mailbox;
+    return 0;
 }
 
 extern "C" int64_t sktt_qr_work(int64_t m, int64_t n) {

@@ -150,14 +150,22 @@ def _run_als(st, repeats, solver):
     sig = tuple(tuple(c.shape) for c in st.A.cores) + tuple(tuple(c.shape) for c in x_initial)
     if solver in ('solve', 'lu', 'krylov', 'cg') and st.dtype == torch.float64 and _DEFER_MISSES.get(sig, 0) < 2:
         st.cache['defer'] = _local.Deferred(st.dev, 2 * st.d)
+        # the QR / RQ steps of the optimistic pass run the sketched CholeskyQR alone (no Householder launch behind its
+        # failure flag); a failure shows up in the sticky word that is read with the deferred outcomes of the micro solves
+        st.dev.set_qr_deferred(True)
+        check = lambda: bool(st.cache['defer'].check()) & (st.dev.qr_deferred_failures() == 0)
+        ok = False
         try:
-            ok = _sweeps_als(st, repeats, solver, check=st.cache['defer'].check)
+            ok = _sweeps_als(st, repeats, solver, check=check)
         except (_device.SkttError, np.linalg.LinAlgError) as exc:
             if getattr(exc, 'status', 0) == 3:                            # SKTT_ERR_CUDA: a broken context cannot be redone
                 raise
             ok = False                                                    # let the host-driven pass raise what there is to raise
         finally:
             st.cache['defer'] = None
+            st.dev.set_qr_deferred(False)
+            if not ok:
+                st.dev.qr_deferred_failures()                             # leave the sticky word clear
         if ok:
             _DEFER_MISSES.pop(sig, None)
             return

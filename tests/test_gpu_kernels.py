@@ -571,3 +571,28 @@ def test_stack_update_natural_layout_kernel(dev, n, sparse):
     dA2 = dev.to_device(A2)
     assert relerr(host(dev.stack_left_op(dL, dx, dA2)), K.stack_left_op(L, x, A2)) < 1e-13
     assert relerr(host(dev.stack_right_op(dR, dx, dA2)), K.stack_right_op(Rt, x, A2)) < 1e-13
+
+
+def test_qr_deferred_mode(dev):
+    """Tall QR / RQ in the deferred mode the sweeps use (sktt_ctx_set_qr_deferred): the sketched CholeskyQR runs alone -- one
+    launch, no Householder kernel behind its failure flag -- and a failure is reported through the sticky word instead."""
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((4096, 64))
+    dA = dev.to_device(A)
+    ref = host(dev.qr(dA))
+    dev.set_qr_deferred(True)
+    try:
+        assert dev.qr_deferred_failures() == 0
+        l0 = dev.launches()
+        q = host(dev.qr(dA))
+        assert dev.launches() - l0 == 1
+        assert np.array_equal(q, ref)                     # the same kernel, the same bits
+        assert np.linalg.norm(q.T @ q - np.eye(64)) < 1e-13
+        assert dev.qr_deferred_failures() == 0
+        bad = A.copy()
+        bad[17, 3] = np.nan                               # nothing can be factorised here: the kernel must say so
+        dev.qr(dev.to_device(bad))
+        assert dev.qr_deferred_failures() == 1
+        assert dev.qr_deferred_failures() == 0            # read once, cleared
+    finally:
+        dev.set_qr_deferred(False)
