@@ -251,12 +251,19 @@ def _micro_als(st, i, solver, guess=None):
     r, n, r2 = L.shape[0], A.shape[2], R.shape[0]
     if guess is None or tuple(guess.shape) != (r, n, r2):
         guess = st.x[i] if tuple(st.x[i].shape) == (r, n, r2) else None
-    if st.group is not None and _wants_guess(solver, r * n * r2) and solver != 'gmres' and r >= 2 * _group_size(st.group):
+    if (st.group is not None and _wants_guess(solver, r * n * r2) and solver != 'gmres' and r >= 2 * _group_size(st.group)
+            and r * n * r2 >= SHARD_MIN_UNKNOWNS):
         return _solve_sharded(st, L, A, R, f, guess), (r, n, r2)
     op = dev.local_op(L, A, R)
     with _local.phase(dev, 'solve'):
         u = _local.solve_micro(dev, solver, lambda: dev.micro_matrix_als(L, A, R), op, f, guess, st.cache)
     return u, (r, n, r2)
+
+
+# Micro systems below this many unknowns are solved by every rank of `group` on its own (replicated): measured on 2 / 4 B200,
+# the exchange of the sharded matvec costs more than the compute it saves at r = 128, n = 16 (262 144 unknowns: 16.6 ->
+# 16.8 -> 10.2 half-sweeps/s at 1 / 2 / 4 GPUs), and pays at r = 256 (1 048 576 unknowns: 5.0 -> 6.8 -> 7.4 at 1 / 2 / 8).
+SHARD_MIN_UNKNOWNS = 1 << 20
 
 
 def _group_size(group):
