@@ -6,6 +6,22 @@
 
 // scratch layout (bytes): [0,2048) scalar slots | [2048,4096) counters | [4096,65536) dot partials
 // | [65536, ...) split-K partials and solver workspaces
+// Map of the scalar area [0, SKTT_SCRATCH_BULK_OFF) of the context scratch (zeroed when the scratch is allocated; every user
+// below leaves its words in the state the next launch of the same kernel expects; all accesses are ordered by the
+// context's stream).  Byte offsets:
+//      0 ..  191  reduction results of blas1 / dotc (read back through the mailbox)
+//    192 ..  511  convergence flags of the host-driven Krylov loops (krylov.cu)
+//    512 ..  1023 Jacobi shift / small scalars of the SVD driver (svd.cu)
+//   1024 .. 1031  info word of lu.cu / Cholesky; {fail, passes} of cholqr_kernel (CQ_STATUS_OFF, qr.cu) -- never live at once
+//   1088 .. 1095  rank and sweep counter of the SVD driver (svd.cu)
+//   1536 .. 2047  phase time stamps of cholqr_kernel (CQ_DEBUG_OFF, debug bit 0)
+//   2048 .. 3071  arrival counters of the blas1 / Krylov reductions (SKTT_SCRATCH_COUNTER_OFF), SVD counters at + 256
+//   3072 .. 3583  arrival counter of the small right-hand-side kernels (RHS_COUNTER_OFF, stacks.cu)
+//   3584 .. 3591  block mask of stack_nat_kernel (cleared by the kernel itself)
+//   3592 .. 3595  grid-barrier counter of stack_nat_kernel (self-resetting)
+//   3600 .. 3855  phase time stamps of stack_nat_kernel / pcg_persistent_kernel / lu_fused_kernel (debug bit 0)
+//   3864 .. 3867  sticky failure word of the deferred QR mode (CQ_STICKY_OFF, qr.cu)
+//   4096 .. 65535 per-CTA partial sums of the reductions (SKTT_SCRATCH_PARTIAL_OFF)
 #define SKTT_SCRATCH_COUNTER_OFF 2048
 #define SKTT_SCRATCH_PARTIAL_OFF 4096
 #define SKTT_SCRATCH_BULK_OFF 65536
