@@ -505,8 +505,45 @@ class Device:
         return True
 
     # ------------------------------------------------------------------ orthonormalisation
+    # Tall matrices with 64 < n <= 512 columns (the unfoldings of BASELINE config 4: 4096 x 128 / 256): the sketched
+    # CholeskyQR kernel takes at most 64 columns and the Householder kernel behind it pays one grid barrier and a
+    # G x n reduction per reflector (measured 3.4 / 8.1 ms at 128 / 256 columns: half of a config-4 sweep).  Block classical
+    # Gram-Schmidt with re-orthogonalisation (BCGS2) over blocks of 64 columns instead: every block is projected against
+    # the finished ones by two contractions and orthonormalised by the 64-column kernel, twice -- the second pass restores
+    # orthogonality to rounding level, and an accurate intra-block QR (the sketched CholeskyQR is Householder-grade, DESIGN.md
+    # 4.4) is what BCGS2 needs.  The economic Q of a full-rank matrix is unique up to the sign of each column, so the
+    # result equals Householder's up to signs (an exact symmetry of the sweeps); R is not formed (the sweeps discard it).
+    QR_BLOCK = 64
+    QR_BLOCKED_MAX_N = 512
+    blocked_qr = True
+
+    def _qr_blocked(self, A):
+        m, n = A.shape
+        big = 1 << 40
+        Q = self.empty((m, n), A.dtype)
+        for c0 in range(0, n, self.QR_BLOCK):
+            nb = min(self.QR_BLOCK, n - c0)
+            Xb = A[:, c0:c0 + nb].contiguous()
+            for _ in range(2):
+                if c0 > 0:
+                    H = self.empty((c0, nb), A.dtype)                     # H = Q_done^T X_b
+                    self.gemm2(c0, nb, m, Q, (big, 0, 1), (big, 0, n), Xb, (big, 0, nb), (big, 0, 1), H, (big, 0, nb), (big, 0, 1))
+                    self.gemm2(m, nb, c0, Q, (big, 0, n), (big, 0, 1), H, (big, 0, nb), (big, 0, 1), Xb, (big, 0, nb), (big, 0, 1),
+                               alpha=(-1.0, 0.0), beta=(1.0, 0.0))        # X_b -= Q_done H
+                Qb = self.empty((m, nb), A.dtype)
+                self._check(self.lib.sktt_qr_left(self.h, dtype_code(A), m, nb, _ptr(Xb), _ptr(Qb), C.c_void_p(0), C.c_void_p(0)))
+                Xb = Qb
+            Q[:, c0:c0 + nb].copy_(Xb)
+        return Q
+
+    def _wants_blocked_qr(self, m, n, dtype, want_r):
+        return (self.blocked_qr and not want_r and dtype == torch.float64 and self.QR_BLOCK < n <= self.QR_BLOCKED_MAX_N
+                and m >= 8 * self.QR_BLOCK and m >= 2 * n)
+
     def qr(self, A, want_r=False):
         m, n = A.shape
+        if self._wants_blocked_qr(m, n, A.dtype, want_r):
+            return self._qr_blocked(A)
         k = min(m, n)
         Q = self.empty((m, k), A.dtype)
         R = self.empty((k, n), A.dtype) if want_r else None
@@ -515,6 +552,10 @@ class Device:
 
     def rq(self, A, want_r=False):
         m, n = A.shape
+        if self._wants_blocked_qr(n, m, A.dtype, want_r):
+            # A = R Q with the conventions of LAPACK's gerqf: C = (J A J)^T = Qc Rc  =>  Q = J Qc^T J (csrc/qr.cu, sktt_rq_right)
+            Cm = torch.flip(A, dims=[0, 1]).t().contiguous()
+            return torch.flip(self._qr_blocked(Cm).t(), dims=[0, 1]).contiguous()
         k = min(m, n)
         Q = self.empty((k, n), A.dtype)
         R = self.empty((m, k), A.dtype) if want_r else None

@@ -596,3 +596,39 @@ def test_qr_deferred_mode(dev):
         assert dev.qr_deferred_failures() == 0            # read once, cleared
     finally:
         dev.set_qr_deferred(False)
+
+
+@pytest.mark.parametrize("shape", [(4096, 128), (4096, 256), (2048, 200), (1100, 96)])
+def test_blocked_qr_of_wide_unfoldings(dev, shape):
+    """Tall QR / RQ beyond the 64 columns of the sketched CholeskyQR kernel (BASELINE config 4: 4096 x 128 / 256): block
+    Gram-Schmidt with re-orthogonalisation over 64-column blocks (scikit_tt_b200/_device.py::_qr_blocked).  Orthogonality and
+    span to rounding level, equality with LAPACK's Q up to the sign of each column (row), a rank-deficient input, and the
+    Householder kernel it replaces as the second reference."""
+    m, n = shape
+    rng = np.random.default_rng(m + n)
+    A = rng.standard_normal((m, n)) @ np.diag(np.geomspace(1.0, 1e-6, n)) @ rng.standard_normal((n, n))
+    dA = dev.to_device(A)
+    q = host(dev.qr(dA))
+    assert np.linalg.norm(q.T @ q - np.eye(n)) < 1e-13
+    assert np.linalg.norm(A - q @ (q.T @ A)) < 1e-12 * np.linalg.norm(A)
+    qref = np.linalg.qr(A)[0]
+    signs = np.sign(np.sum(q * qref, axis=0))
+    assert np.linalg.norm(q * signs - qref) < 1e-7             # cond 1e6 x 1e6: the columns agree to eps * cond
+    dev.blocked_qr = False
+    try:
+        qh = host(dev.qr(dA))
+    finally:
+        dev.blocked_qr = True
+    assert np.linalg.norm(q * np.sign(np.sum(q * qh, axis=0)) - qh) < 1e-7
+    # RQ of the transposed problem: orthonormal rows, same row space, LAPACK's Q up to the sign of each row
+    B = np.ascontiguousarray(A.T)
+    p = host(dev.rq(dev.to_device(B)))
+    assert p.shape == (n, m) and np.linalg.norm(p @ p.T - np.eye(n)) < 1e-13
+    assert np.linalg.norm(B - (B @ p.T) @ p) < 1e-12 * np.linalg.norm(B)
+    pref = sla.rq(B, mode='economic')[1]
+    assert np.linalg.norm(p * np.sign(np.sum(p * pref, axis=1))[:, None] - pref) < 1e-7
+    # numerically rank-deficient (rank n - 40): still an orthonormal basis that contains the column space
+    D = rng.standard_normal((m, n - 40)) @ rng.standard_normal((n - 40, n))
+    qd = host(dev.qr(dev.to_device(D)))
+    assert np.linalg.norm(qd.T @ qd - np.eye(n)) < 1e-12
+    assert np.linalg.norm(D - qd @ (qd.T @ D)) < 1e-11 * np.linalg.norm(D)
