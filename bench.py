@@ -651,6 +651,8 @@ def run_ours(args, cfg):
                           f"`same_config`); rank {cfg['r']} is not runnable by the reference algorithm (512 GiB micro matrix)"}
         print(json.dumps(line), flush=True)
     if env.world > 1:
+        from scikit_tt_b200.solvers import multi
+        multi.close_peer_exchanges()                         # cached exchange buffers of the sharded C4 leg
         env.dist.destroy_process_group()
 
 

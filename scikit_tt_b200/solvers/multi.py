@@ -301,6 +301,33 @@ class PeerExchange:
         self.local = None
 
 
+# Exchange buffers are kept between calls: creating them costs three cudaMalloc, an all_gather_object and 3 (world - 1)
+# cudaIpcOpenMemHandle per rank (tens of milliseconds at 8 GPUs, with large jitter: one sle.als(group=) sweep at rank 256
+# measured between 4.9 and 12.8 half-sweeps/s on 4 GPUs depending on it).  One set per (process group, dtype, device), grown
+# when a call needs more; released by close_peer_exchanges() or at interpreter exit.
+_PX_CACHE = {}
+
+
+def peer_exchange(dev, nelem, dtype, group=None):
+    key = (id(group) if group is not None else None, str(dtype), dev.index)
+    px = _PX_CACHE.get(key)
+    if px is not None and (px.local is None or px.nelem < int(nelem)):
+        px.close()
+        px = None
+    if px is None:
+        px = _PX_CACHE[key] = PeerExchange(dev, nelem, dtype, group)
+    return px
+
+
+def close_peer_exchanges():
+    for px in list(_PX_CACHE.values()):
+        try:
+            px.close()
+        except Exception:
+            pass
+    _PX_CACHE.clear()
+
+
 SHARDED_TOL = 1e-14
 SHARDED_ACCEPT = 1e-12
 SHARDED_MAX_ITERS = 5000

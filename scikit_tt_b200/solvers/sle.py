@@ -125,14 +125,10 @@ def als(operator, initial_guess, right_hand_side, repeats=1, solver='solve', gro
     st = _State(operator, initial_guess, right_hand_side)
     st.group = group
     if st.group is not None:
-        try:
-            _sweeps_als(st, repeats, solver)
-            if st.px is not None:
-                st.px.check()
-        finally:
-            if st.px is not None:
-                st.px.close()
-                st.px = None
+        _sweeps_als(st, repeats, solver)
+        if st.px is not None:
+            st.px.check()                                    # the exchange buffers stay mapped for the next call (multi._PX_CACHE)
+            st.px = None
         return st.result()
     st.stream_results = True
     _run_als(st, repeats, solver)
@@ -278,7 +274,7 @@ def _solve_sharded(st, L, A, R, f, guess):
     dev = st.dev
     if st.px is None:
         nmax = max(int(st.x[i].shape[0] * st.A[i].shape[1] * st.x[i].shape[2]) for i in range(st.d))
-        st.px = multi.PeerExchange(dev, nmax, st.dtype, st.group)
+        st.px = multi.peer_exchange(dev, nmax, st.dtype, st.group)
     return multi.solve_sharded(dev, lambda v: st.px.matvec(L, A, R, v), f, guess)
 
 

@@ -125,6 +125,7 @@ def _nccl_worker(rank, world, port, out):
         import traceback
         out.put((rank, traceback.format_exc()))
     finally:
+        multi.close_peer_exchanges()
         dist.destroy_process_group()
 
 
