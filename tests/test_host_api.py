@@ -122,3 +122,13 @@ def test_warm_start_plumbing_of_the_sweep():
     assert sle._pushed(FakeDev(), None, core, left=True) is None
     assert sle._pushed(FakeDev(), torch.zeros(4, 6, dtype=torch.float64), core, left=True) is None     # rank changed
     assert sle._pushed(FakeDev(), torch.zeros(4, 2, dtype=torch.float64), core, left=False) is None
+
+
+def test_multi_gpu_policy_surface():
+    """Host-side surface of the sharded sweep: the size policy of sle.als(group=) and the cache of peer exchange buffers exist
+    with the documented defaults (their behaviour on GPUs is covered by tests/test_gpu_multi.py)."""
+    from scikit_tt_b200.solvers import sle, multi
+    assert sle.SHARD_MIN_UNKNOWNS == 1 << 20
+    assert callable(multi.peer_exchange) and callable(multi.close_peer_exchanges)
+    multi.close_peer_exchanges()                              # nothing cached: a no-op
+    assert multi._PX_CACHE == {}
